@@ -1,0 +1,90 @@
+"""ctypes binding of libhosnerf_b200.so (the C ABI declared in include/hosnerf_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call
+returns a non-zero status, a RuntimeError is raised.  Build the library with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C hosnerf_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhosnerf_b200.so")
+
+c_f = C.c_void_p      # device pointers travel as integers
+c_i = C.c_int
+c_l = C.c_int64
+c_fl = C.c_float
+c_hp = C.POINTER(C.c_float)   # HOST float pointer (small parameter vectors)
+
+
+class MlpLayer(C.Structure):
+    _fields_ = [("out_dim", c_i), ("in_h", c_i), ("in_x", c_i), ("x_first", c_i),
+                ("relu", c_i), ("rowbias", c_i), ("head", c_i)]
+
+
+class MlpHead(C.Structure):
+    _fields_ = [("out_dim", c_i), ("post", c_i), ("shift", c_fl), ("out_slot", c_i)]
+
+
+# name -> (restype, argtypes); mirrors include/hosnerf_b200.h one to one
+SIGNATURES = {
+    "hos_last_error": (C.c_char_p, []),
+    "hos_version": (c_i, []),
+    "hos_device_check": (c_i, [c_i]),
+    "hos_max_dilate": (c_i, [c_f, c_f, c_i, c_i, c_fl, c_fl, c_fl, c_f, c_f, c_f]),
+    "hos_sample_intervals": (c_i, [c_f, c_f, c_f, c_f, c_i, c_fl, c_i, c_i, c_i, c_fl, c_fl, c_f, c_f, c_f, c_f]),
+    "hos_resample_level": (c_i, [c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_f, c_f, c_i, c_fl, c_i, c_fl,
+                                 c_fl, c_fl, c_fl, c_f, c_f, c_f]),
+    "hos_human_samples": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f]),
+    "hos_ipe_features": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_f, c_f]),
+    "hos_pos_enc": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
+    "hos_fourier_embed": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f, c_i, c_i, c_f]),
+    "hos_lbs_warp": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f]),
+    "hos_linear_f32": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_f, c_i, c_f]),
+    "hos_linear_f32_ex": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_f, c_i, c_f]),
+    "hos_head_f32": (c_i, [c_f, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_fl, c_f, c_f, c_i, c_f]),
+    "hos_mlp_create": (C.c_void_p, [c_i, c_i, C.POINTER(MlpLayer), c_i, C.POINTER(MlpHead)]),
+    "hos_mlp_destroy": (None, [C.c_void_p]),
+    "hos_mlp_set_layer": (c_i, [C.c_void_p, c_i, c_f, c_f, c_f]),
+    "hos_mlp_set_bias": (c_i, [C.c_void_p, c_i, c_f, c_f]),
+    "hos_mlp_set_head": (c_i, [C.c_void_p, c_i, c_f, c_f, c_f]),
+    "hos_mlp_in_kblocks": (c_i, [C.c_void_p]),
+    "hos_mlp_forward": (c_i, [C.c_void_p, c_f, c_l, c_f, c_i, c_f, c_f, c_f, c_f]),
+    "hos_pack_rows_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f]),
+    "hos_composite_mip360": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
+    "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
+    "hos_composite_s3": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_hp, c_f, c_f, c_i, c_i, c_i, c_fl,
+                               c_f, c_f, c_f, c_f]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built and hosnerf_b200 has no CPU "
+            "fallback.  Run `python -c 'import __graft_entry__ as g; g.build()'` in the repo root.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().hos_last_error().decode(errors="replace")
+        raise RuntimeError(f"libhosnerf_b200 {what} failed (status {status}): {msg}")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

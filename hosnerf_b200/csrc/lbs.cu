@@ -1,0 +1,103 @@
+// LBS motion field: S3/core/nets/human_nerf/network.py:304-354.
+//
+// The reference loops 26x over {3x3 matmul, F.grid_sample(32^3 volume)} in Python and
+// materialises 26 [P,1] weight tensors and 26 [P,3] positions.  Here one thread owns one
+// sample point: bone transforms sit in shared memory, the 3.4 MiB weight volume is read
+// through the read-only path and stays L2-resident (gathers from neighbouring samples of
+// a ray hit the same cache lines), and only pts (12 B) in / x_skel+mask (16 B) out touch HBM.
+#include "common.cuh"
+
+namespace hos {
+
+constexpr int kMaxBones = 32;
+struct LbsParams {
+  float bbox_min[3];
+  float bbox_scale[3];
+};
+
+// trilinear sample with zeros padding, align_corners=True; term order follows ATen's
+// grid_sampler_3d CPU kernel (tnw, tne, tsw, tse, bnw, bne, bsw, bse).
+__device__ __forceinline__ float trilinear_zeros(const float* __restrict__ v, int G, float gx, float gy, float gz) {
+  float s = (float)(G - 1);
+  float ix = ((gx + 1.f) / 2.f) * s;
+  float iy = ((gy + 1.f) / 2.f) * s;
+  float iz = ((gz + 1.f) / 2.f) * s;
+  float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  // completely outside (or NaN): every corner is out of range
+  if (!(ix > -1.f && ix < (float)G && iy > -1.f && iy < (float)G && iz > -1.f && iz < (float)G)) return 0.f;
+  int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  int x1 = x0 + 1, y1 = y0 + 1, z1 = z0 + 1;
+  float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;     // weight of the +1 corner
+  float wx0 = (float)x1 - ix, wy0 = (float)y1 - iy, wz0 = (float)z1 - iz;
+  bool bx0 = x0 >= 0 && x0 < G, bx1 = x1 >= 0 && x1 < G;
+  bool by0 = y0 >= 0 && y0 < G, by1 = y1 >= 0 && y1 < G;
+  bool bz0 = z0 >= 0 && z0 < G, bz1 = z1 >= 0 && z1 < G;
+  auto at = [&](int z, int y, int x) { return __ldg(v + ((size_t)z * G + y) * G + x); };
+  float acc = 0.f;
+  if (bz0 && by0 && bx0) acc += at(z0, y0, x0) * (wx0 * wy0 * wz0);
+  if (bz0 && by0 && bx1) acc += at(z0, y0, x1) * (wx1 * wy0 * wz0);
+  if (bz0 && by1 && bx0) acc += at(z0, y1, x0) * (wx0 * wy1 * wz0);
+  if (bz0 && by1 && bx1) acc += at(z0, y1, x1) * (wx1 * wy1 * wz0);
+  if (bz1 && by0 && bx0) acc += at(z1, y0, x0) * (wx0 * wy0 * wz1);
+  if (bz1 && by0 && bx1) acc += at(z1, y0, x1) * (wx1 * wy0 * wz1);
+  if (bz1 && by1 && bx0) acc += at(z1, y1, x0) * (wx0 * wy1 * wz1);
+  if (bz1 && by1 && bx1) acc += at(z1, y1, x1) * (wx1 * wy1 * wz1);
+  return acc;
+}
+
+__global__ void __launch_bounds__(256)
+lbs_warp_kernel(const float* __restrict__ pts, const float* __restrict__ R, const float* __restrict__ T,
+                const float* __restrict__ vol, LbsParams prm, int64_t P, int bones, int G,
+                float* __restrict__ x_skel, float* __restrict__ mask) {
+  __shared__ float sR[kMaxBones * 9];
+  __shared__ float sT[kMaxBones * 3];
+  for (int i = threadIdx.x; i < bones * 9; i += blockDim.x) sR[i] = R[i];
+  for (int i = threadIdx.x; i < bones * 3; i += blockDim.x) sT[i] = T[i];
+  __syncthreads();
+  const size_t vstride = (size_t)G * G * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    float px = pts[i * 3 + 0], py = pts[i * 3 + 1], pz = pts[i * 3 + 2];
+    float ax = 0.f, ay = 0.f, az = 0.f, wsum = 0.f;
+#pragma unroll 2
+    for (int b = 0; b < bones; ++b) {
+      const float* r = sR + b * 9;
+      float qx = r[0] * px + r[1] * py + r[2] * pz + sT[b * 3 + 0];
+      float qy = r[3] * px + r[4] * py + r[5] * pz + sT[b * 3 + 1];
+      float qz = r[6] * px + r[7] * py + r[8] * pz + sT[b * 3 + 2];
+      float gx = (qx - prm.bbox_min[0]) * prm.bbox_scale[0] - 1.0f;
+      float gy = (qy - prm.bbox_min[1]) * prm.bbox_scale[1] - 1.0f;
+      float gz = (qz - prm.bbox_min[2]) * prm.bbox_scale[2] - 1.0f;
+      float w = trilinear_zeros(vol + b * vstride, G, gx, gy, gz);
+      wsum += w;
+      ax += w * qx;
+      ay += w * qy;
+      az += w * qz;
+    }
+    float den = fmaxf(wsum, 0.0001f);
+    x_skel[i * 3 + 0] = ax / den;
+    x_skel[i * 3 + 1] = ay / den;
+    x_skel[i * 3 + 2] = az / den;
+    mask[i] = wsum;
+  }
+}
+
+}  // namespace hos
+
+using namespace hos;
+
+extern "C" int hos_lbs_warp(const float* pts, const float* R, const float* T, const float* vol,
+                            const float* bbox_min_host, const float* bbox_scale_host, int64_t P,
+                            int bones, int G, float* x_skel, float* mask, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(pts && R && T && vol && bbox_min_host && bbox_scale_host && x_skel && mask, "hos_lbs_warp: null pointer");
+  HOS_REQUIRE(P >= 0 && bones >= 1 && bones <= kMaxBones && G >= 2, "hos_lbs_warp: bad shape (bones=%d G=%d)", bones, G);
+  if (P == 0) return HOS_OK;
+  LbsParams prm;
+  for (int i = 0; i < 3; ++i) { prm.bbox_min[i] = bbox_min_host[i]; prm.bbox_scale[i] = bbox_scale_host[i]; }
+  int64_t blocks = (P + 255) / 256;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  lbs_warp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pts, R, T, vol, prm, P, bones, G, x_skel, mask);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}

@@ -1,0 +1,555 @@
+// Fused multi-layer MLP on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+// SURVEY 8a rows a9 (Prop/NeRF MLP), a17 (non-rigid MLP), a19 (canonical MLP).
+//
+// One persistent CTA per SM walks 128-row tiles of the flattened (rays x samples) batch.
+// For every tile the whole layer stack runs without touching HBM in between:
+//
+//   warp 0  (producer)  1-D bulk copies (cp.async.bulk -> UBLKCP) of pre-tiled, pre-swizzled
+//                       weight chunks [N x 64] fp16 and, for layers that read the encoded
+//                       input (first layer, skip layer), of the input-feature chunks
+//                       [128 x 64] fp16 into a shared-memory ring, signalled by mbarriers.
+//   warp 1  (MMA)       one lane issues tcgen05.mma (M=128, N=layer width, K=16, fp16 x fp16 ->
+//                       fp32) with A = activations in shared memory (K-major, 128B swizzle),
+//                       B = weight chunk, D = TMEM accumulator; tcgen05.commit releases ring
+//                       stages and signals the epilogue.
+//   warps 2-5 (epilogue) tcgen05.ld the accumulator (lane = row), + bias (+ per-ray bias),
+//                       ReLU, pack to fp16 and store straight back into shared memory in the
+//                       UMMA canonical layout as the next layer's A operand; small output
+//                       heads (density / rgb / raw4 / xyz offset) are evaluated in fp32 from
+//                       the registers and are the only thing written to HBM.
+//
+// HBM layout ("tiled fp16"): activations entering the kernel and all weights are stored as
+// consecutive 16 KB (resp. N*128 B) images of exactly what the tensor core reads from shared
+// memory - element (r, k) of a [rows x 64] K-block lives at  r*128 + (((k>>3) ^ (r&7))<<4) + (k&7)*2 -
+// so a chunk is one contiguous bulk copy, no tensor map needed.
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace hos {
+
+constexpr int kTileM = 128;
+constexpr int kKB = 64;                    // K elements per chunk (128 bytes of fp16)
+constexpr int kXChunkBytes = kTileM * 128; // 16 KB
+constexpr int kMaxLayers = 12;
+constexpr int kMaxHeads = 4;
+constexpr int kStages = 3;
+constexpr int kMlpThreads = 192;
+constexpr int kTmemCols = 256;
+
+struct LayerDev {
+  uint32_t w_off;      // byte offset of the first weight chunk in the packed fp16 buffer
+  uint32_t bias_off;   // float offset of bias[n] in the fp32 parameter block
+  uint16_t n;          // output width (multiple of 16, <= 256)
+  uint8_t kb_h;        // K-blocks read from the previous layer's activations
+  uint8_t kb_x;        // K-blocks read from the streamed input features
+  uint8_t relu;
+  uint8_t rowbias;
+  int8_t head;         // head evaluated on this layer's output, or -1
+  uint8_t pad_;
+};
+struct HeadDev {
+  uint32_t w_off;      // float offset of W[hn][n]
+  uint32_t b_off;
+  float shift;
+  uint8_t hn;
+  uint8_t post;        // 0 identity, 1 softplus(v+shift), 2 sigmoid*(1+2 shift)-shift, 3 v+add, 4 rgb sigmoid / sigma relu
+  uint8_t slot;        // which output pointer
+  uint8_t pad_;
+};
+struct MlpProgram {
+  int n_layers;
+  int n_heads;
+  int kbx;             // K-blocks per row tile in the input feature buffer
+  int kbh;             // K-blocks of the hidden activation buffer (width / 64)
+  int n_max;           // widest layer
+  int param_floats;
+  LayerDev layers[kMaxLayers];
+  HeadDev heads[kMaxHeads];
+};
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+// (bit layout: cute/arch/mma_sm100_desc.hpp, SmemDescriptor).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);        // start address, 16 B units
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M=128.
+__host__ __device__ inline uint32_t umma_idesc_f16(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+
+struct MlpArgs {
+  const unsigned char* x_tiled;   // [ntiles][kbx][16 KB]
+  const unsigned char* w_packed;  // fp16 chunks
+  const float* params;            // biases + head weights
+  const float* rowbias;           // [rows / rowbias_div][n] or null
+  const float* add;               // [rows][hn] for post 3, or null
+  float* out[2];
+  int64_t rows;
+  int ntiles;
+  int rowbias_div;
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const MlpArgs args) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // carve-up (all chunk bases 1024-aligned, required by SWIZZLE_128B)
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_stage_bytes = prog.n_max * 128;
+  unsigned char* sH = smem;                                            // kbh * 16 KB
+  unsigned char* sRingW = sH + prog.kbh * kXChunkBytes;                // kStages * w_stage_bytes
+  unsigned char* sRingX = sRingW + kStages * w_stage_bytes;            // kStages * 16 KB
+  float* sParams = reinterpret_cast<float*>(sRingX + kStages * kXChunkBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((prog.param_floats + 3) & ~3));
+  uint64_t* bar_full = bars;                 // [kStages]
+  uint64_t* bar_empty = bars + kStages;      // [kStages]
+  uint64_t* bar_tmem_full = bars + 2 * kStages;
+  uint64_t* bar_act = bars + 2 * kStages + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < prog.param_floats; i += kMlpThreads) sParams[i] = args.params[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(bar_tmem_full, 1);
+    mbar_init(bar_act, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
+        for (int l = 0; l < prog.n_layers; ++l) {
+          const LayerDev L = prog.layers[l];
+          const uint32_t wbytes = (uint32_t)L.n * 128u;
+          const int nkb = L.kb_h + L.kb_x;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int st = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&bar_empty[st], ph ^ 1);
+            const bool needx = kb >= L.kb_h;
+            mbar_expect_tx(&bar_full[st], wbytes + (needx ? (uint32_t)kXChunkBytes : 0u));
+            bulk_g2s(sRingW + st * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * wbytes, wbytes, &bar_full[st]);
+            if (needx)
+              bulk_g2s(sRingX + st * kXChunkBytes,
+                       args.x_tiled + ((size_t)tile * prog.kbx + (kb - L.kb_h)) * kXChunkBytes, kXChunkBytes,
+                       &bar_full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    uint32_t it = 0, li = 0;
+    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
+      for (int l = 0; l < prog.n_layers; ++l, ++li) {
+        const LayerDev L = prog.layers[l];
+        const uint32_t idesc = umma_idesc_f16(L.n);
+        if (li > 0) {                         // previous epilogue: H written, TMEM drained
+          mbar_wait(bar_act, (li - 1) & 1);
+          tc_fence_after();
+        }
+        const int nkb = L.kb_h + L.kb_x;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&bar_full[st], ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_base = smem_u32(kb < L.kb_h ? sH + kb * kXChunkBytes : sRingX + st * kXChunkBytes);
+            const uint32_t b_base = smem_u32(sRingW + st * w_stage_bytes);
+#pragma unroll
+            for (int k = 0; k < kKB / 16; ++k)
+              tc_mma_f16(tmem_base, umma_desc(a_base + k * 32), umma_desc(b_base + k * 32), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+            tc_commit(&bar_empty[st]);          // frees the ring stage when these MMAs retire
+            if (kb == nkb - 1) tc_commit(bar_tmem_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                // row within the tile
+    uint32_t li = 0;
+    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
+      const int64_t row = (int64_t)tile * kTileM + r;
+      const bool row_ok = row < args.rows;
+      for (int l = 0; l < prog.n_layers; ++l, ++li) {
+        const LayerDev L = prog.layers[l];
+        const bool last = (l == prog.n_layers - 1);
+        mbar_wait(bar_tmem_full, li & 1);
+        tc_fence_after();
+        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+        const HeadDev Hd = prog.heads[L.head >= 0 ? L.head : 0];
+        const float* rb = nullptr;
+        if (L.rowbias && args.rowbias && row_ok) rb = args.rowbias + (row / args.rowbias_div) * L.n;
+        for (int c0 = 0; c0 < L.n; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) + sParams[L.bias_off + c0 + j];
+            if (rb) x += __ldg(rb + c0 + j);
+            f[j] = L.relu ? fmaxf(x, 0.f) : x;
+          }
+          if (L.head >= 0) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              if (n < Hd.hn) {
+                const float* w = sParams + Hd.w_off + n * L.n + c0;
+                float a = hacc[n];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a = fmaf(f[j], w[j], a);
+                hacc[n] = a;
+              }
+            }
+          }
+          if (!last) {
+            unsigned char* dst = sH + (c0 >> 6) * kXChunkBytes;
+            const int kk = c0 & 63;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              __half2 h0 = __floats2half2_rn(f[g * 8 + 0], f[g * 8 + 1]);
+              __half2 h1 = __floats2half2_rn(f[g * 8 + 2], f[g * 8 + 3]);
+              __half2 h2 = __floats2half2_rn(f[g * 8 + 4], f[g * 8 + 5]);
+              __half2 h3 = __floats2half2_rn(f[g * 8 + 6], f[g * 8 + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(dst + tile_byte_offset(r, kk + g * 8)) = pk;
+            }
+          }
+        }
+        if (L.head >= 0 && row_ok) {
+          float* o = args.out[Hd.slot] + row * Hd.hn;
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            if (n >= Hd.hn) break;
+            float x = hacc[n] + sParams[Hd.b_off + n];
+            if (Hd.post == 1) {
+              float z = x + Hd.shift;
+              x = z > 20.f ? z : log1pf(expf(z));
+            } else if (Hd.post == 2) {
+              x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * Hd.shift) - Hd.shift;
+            } else if (Hd.post == 3) {
+              x = args.add[row * Hd.hn + n] + x;
+            } else if (Hd.post == 4) {
+              x = (n < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+            }
+            o[n] = x;
+          }
+        }
+        fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
+        tc_fence_before();          // TMEM loads ordered before the arrive
+        mbar_arrive(bar_act);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+  }
+}
+
+// ----------------------------------------------------------------------------- packing
+// W fp32 [N, in_h + in_x] (nn.Linear layout, columns ordered [x|h] if x_first else [h|x])
+// -> fp16 chunks in kernel K order: kb_h chunks of h columns, then kb_x chunks of x columns.
+__global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h, int in_x, int x_first, int kb_h,
+                                   int kb_x, unsigned char* __restrict__ dst) {
+  const int nkb = kb_h + kb_x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)nkb * N * kKB) return;
+  int kk = (int)(i % kKB);
+  int n = (int)((i / kKB) % N);
+  int kb = (int)(i / ((int64_t)kKB * N));
+  float v = 0.f;
+  const int ktot = in_h + in_x;
+  if (kb < kb_h) {
+    int c = kb * kKB + kk;
+    if (c < in_h) v = W[(int64_t)n * ktot + (x_first ? in_x + c : c)];
+  } else {
+    int c = (kb - kb_h) * kKB + kk;
+    if (c < in_x) v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
+  }
+  *reinterpret_cast<__half*>(dst + (size_t)kb * N * 128 + tile_byte_offset(n, kk)) = __float2half_rn(v);
+}
+
+// X fp32 [rows, ld] (first K columns) -> tiled fp16 [ntiles][kbx][16 KB], zero padded.
+__global__ void pack_rows_kernel(const float* __restrict__ X, int64_t rows, int ld, int K, int kbx,
+                                 unsigned char* __restrict__ dst, int64_t total) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int k = (int)(i % (kbx * kKB));
+  int64_t row = i / (kbx * kKB);
+  float v = (row < rows && k < K) ? X[row * ld + k] : 0.f;
+  int64_t tile = row / kTileM;
+  int r = (int)(row % kTileM);
+  *reinterpret_cast<__half*>(dst + ((size_t)tile * kbx + (k >> 6)) * kXChunkBytes + tile_byte_offset(r, k & 63)) =
+      __float2half_rn(v);
+}
+
+}  // namespace hos
+
+using namespace hos;
+
+struct hos_mlp {
+  MlpProgram prog;
+  int in_dim;
+  std::vector<hos_mlp_layer> layers;
+  std::vector<hos_mlp_head> heads;
+  unsigned char* d_w = nullptr;      // packed fp16 weights
+  float* d_params = nullptr;         // biases + head weights (fp32)
+  size_t w_bytes = 0;
+  size_t smem_bytes = 0;
+};
+
+extern "C" {
+
+hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers, int n_heads,
+                          const hos_mlp_head* heads) {
+  if (hos::check_arch() != HOS_OK) return nullptr;
+  if (!layers || n_layers < 1 || n_layers > kMaxLayers || n_heads < 0 || n_heads > kMaxHeads || in_dim < 1) {
+    hos::set_error("hos_mlp_create: bad layer/head count");
+    return nullptr;
+  }
+  hos_mlp* m = new hos_mlp();
+  m->in_dim = in_dim;
+  m->layers.assign(layers, layers + n_layers);
+  if (n_heads) m->heads.assign(heads, heads + n_heads);
+  MlpProgram& P = m->prog;
+  memset(&P, 0, sizeof(P));
+  P.n_layers = n_layers;
+  P.n_heads = n_heads;
+  P.kbx = (in_dim + kKB - 1) / kKB;
+  uint32_t woff = 0, poff = 0;
+  int width = 0, nmax = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const hos_mlp_layer& L = layers[l];
+    bool ok = L.out_dim >= 16 && L.out_dim <= 256 && (L.out_dim % 16) == 0 && L.in_h >= 0 && L.in_x >= 0 &&
+              (L.in_h + L.in_x) > 0 && L.in_x <= in_dim && (L.in_h % kKB) == 0 &&
+              (l == 0 ? L.in_h == 0 : L.in_h == layers[l - 1].out_dim) && L.head < n_heads;
+    if (!ok) {
+      hos::set_error("hos_mlp_create: unsupported layer %d (out=%d in_h=%d in_x=%d)", l, L.out_dim, L.in_h, L.in_x);
+      delete m;
+      return nullptr;
+    }
+    LayerDev& D = P.layers[l];
+    D.n = (uint16_t)L.out_dim;
+    D.kb_h = (uint8_t)(L.in_h / kKB);
+    D.kb_x = (uint8_t)((L.in_x + kKB - 1) / kKB);
+    D.relu = (uint8_t)(L.relu != 0);
+    D.rowbias = (uint8_t)(L.rowbias != 0);
+    D.head = (int8_t)L.head;
+    D.w_off = woff;
+    D.bias_off = poff;
+    woff += (uint32_t)(D.kb_h + D.kb_x) * D.n * 128u;
+    poff += D.n;
+    if (l < n_layers - 1 && L.out_dim > width) width = L.out_dim;
+    if (L.out_dim > nmax) nmax = L.out_dim;
+    if (L.head >= 0 && heads[L.head].out_dim > 4) {
+      hos::set_error("hos_mlp_create: head width > 4");
+      delete m;
+      return nullptr;
+    }
+  }
+  for (int h = 0; h < n_heads; ++h) {
+    int owner = -1;
+    for (int l = 0; l < n_layers; ++l) if (layers[l].head == h) owner = l;
+    if (owner < 0) { hos::set_error("hos_mlp_create: head %d unused", h); delete m; return nullptr; }
+    HeadDev& H = P.heads[h];
+    H.hn = (uint8_t)heads[h].out_dim;
+    H.post = (uint8_t)heads[h].post;
+    H.shift = heads[h].shift;
+    H.slot = (uint8_t)heads[h].out_slot;
+    H.w_off = poff;
+    poff += (uint32_t)H.hn * layers[owner].out_dim;
+    H.b_off = poff;
+    poff += 4;
+  }
+  if (width == 0) width = kKB;
+  P.kbh = (width + kKB - 1) / kKB;
+  P.n_max = nmax;
+  P.param_floats = (int)poff;
+  m->w_bytes = woff;
+  m->smem_bytes = 1024 + (size_t)P.kbh * kXChunkBytes + (size_t)kStages * (nmax * 128 + kXChunkBytes) +
+                  (((size_t)poff + 3) & ~(size_t)3) * 4 + (2 * kStages + 2) * 8 + 16;
+  if (m->smem_bytes > 227 * 1024) {
+    hos::set_error("hos_mlp_create: needs %zu B shared memory (> 227 KB)", m->smem_bytes);
+    delete m;
+    return nullptr;
+  }
+  if (cudaMalloc(&m->d_w, m->w_bytes) != cudaSuccess || cudaMalloc(&m->d_params, (size_t)poff * 4) != cudaSuccess ||
+      cudaMemset(m->d_params, 0, (size_t)poff * 4) != cudaSuccess ||
+      cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
+    hos::set_error("hos_mlp_create: CUDA allocation/attribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    hos_mlp_destroy(m);
+    return nullptr;
+  }
+  return m;
+}
+
+void hos_mlp_destroy(hos_mlp_t* m) {
+  if (!m) return;
+  if (m->d_w) cudaFree(m->d_w);
+  if (m->d_params) cudaFree(m->d_params);
+  delete m;
+}
+
+int hos_mlp_set_layer(hos_mlp_t* m, int layer, const float* W, const float* b, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && W && layer >= 0 && layer < m->prog.n_layers, "hos_mlp_set_layer: bad handle/layer");
+  const hos_mlp_layer& L = m->layers[layer];
+  const LayerDev& D = m->prog.layers[layer];
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t tot = (int64_t)(D.kb_h + D.kb_x) * D.n * kKB;
+  pack_weight_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(W, D.n, L.in_h, L.in_x, L.x_first, D.kb_h, D.kb_x,
+                                                                   m->d_w + D.w_off);
+  HOS_LAUNCH_CHECK();
+  if (b) HOS_CUDA(cudaMemcpyAsync(m->d_params + D.bias_off, b, (size_t)D.n * 4, cudaMemcpyDeviceToDevice, st));
+  else HOS_CUDA(cudaMemsetAsync(m->d_params + D.bias_off, 0, (size_t)D.n * 4, st));
+  return HOS_OK;
+}
+
+int hos_mlp_set_bias(hos_mlp_t* m, int layer, const float* b, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && b && layer >= 0 && layer < m->prog.n_layers, "hos_mlp_set_bias: bad handle/layer");
+  const LayerDev& D = m->prog.layers[layer];
+  HOS_CUDA(cudaMemcpyAsync(m->d_params + D.bias_off, b, (size_t)D.n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HOS_OK;
+}
+
+int hos_mlp_set_head(hos_mlp_t* m, int head, const float* W, const float* b, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && W && head >= 0 && head < m->prog.n_heads, "hos_mlp_set_head: bad handle/head");
+  const HeadDev& H = m->prog.heads[head];
+  cudaStream_t st = (cudaStream_t)stream;
+  HOS_CUDA(cudaMemcpyAsync(m->d_params + H.w_off, W, (size_t)(H.b_off - H.w_off) * 4, cudaMemcpyDeviceToDevice, st));
+  if (b) HOS_CUDA(cudaMemcpyAsync(m->d_params + H.b_off, b, (size_t)H.hn * 4, cudaMemcpyDeviceToDevice, st));
+  return HOS_OK;
+}
+
+int hos_mlp_in_kblocks(const hos_mlp_t* m) { return m ? m->prog.kbx : 0; }
+
+int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float* rowbias, int rowbias_div,
+                    const float* add, float* out0, float* out1, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && x_tiled && rows >= 0, "hos_mlp_forward: bad handle/input");
+  for (int l = 0; l < m->prog.n_layers; ++l)
+    HOS_REQUIRE(!m->prog.layers[l].rowbias || (rowbias && rowbias_div >= 1), "hos_mlp_forward: layer %d needs rowbias", l);
+  for (int h = 0; h < m->prog.n_heads; ++h) {
+    HOS_REQUIRE(m->prog.heads[h].slot < 2 && (m->prog.heads[h].slot == 0 ? out0 : out1), "hos_mlp_forward: missing output for head %d", h);
+    HOS_REQUIRE(m->prog.heads[h].post != 3 || add, "hos_mlp_forward: head %d needs `add`", h);
+  }
+  if (rows == 0) return HOS_OK;
+  MlpArgs a;
+  a.x_tiled = (const unsigned char*)x_tiled;
+  a.w_packed = m->d_w;
+  a.params = m->d_params;
+  a.rowbias = rowbias;
+  a.add = add;
+  a.out[0] = out0;
+  a.out[1] = out1;
+  a.rows = rows;
+  a.ntiles = (int)((rows + kTileM - 1) / kTileM);
+  a.rowbias_div = rowbias_div < 1 ? 1 : rowbias_div;
+  int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
+  mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}
+
+int hos_pack_rows_f16(const float* X, int64_t rows, int ld, int K, void* dst_tiled, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(X && dst_tiled && rows >= 0 && K >= 1 && ld >= K, "hos_pack_rows_f16: bad arguments");
+  if (rows == 0) return HOS_OK;
+  int kbx = (K + kKB - 1) / kKB;
+  int64_t ntiles = (rows + kTileM - 1) / kTileM;
+  int64_t total = ntiles * kTileM * (int64_t)kbx * kKB;
+  pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      X, rows, ld, K, kbx, (unsigned char*)dst_tiled, total);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,277 @@
+"""Thin torch <-> C-ABI glue: every function here checks its tensors (CUDA, fp32,
+contiguous), allocates the outputs with torch, and calls one entry point of
+libhosnerf_b200.so on the current CUDA stream.  No arithmetic happens in Python and
+there is no CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+_F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name, dtype=_F32):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"hosnerf_b200: `{name}` must be a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"hosnerf_b200: `{name}` must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"hosnerf_b200: `{name}` must be contiguous")
+    return t
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _host3(v, n=3):
+    vals = [float(x) for x in (v.detach().cpu().reshape(-1).tolist() if isinstance(v, torch.Tensor) else v)]
+    assert len(vals) == n
+    return (C.c_float * n)(*vals)
+
+
+# ----------------------------------------------------------------------------- sampler
+def max_dilate(t, w, dilation, lo, hi):
+    _chk(t, "t"), _chk(w, "w")
+    n, s = w.shape
+    t_out = torch.empty(n, 3 * s + 1, device=t.device, dtype=_F32)
+    w_out = torch.empty(n, 3 * s, device=t.device, dtype=_F32)
+    _lib.call("hos_max_dilate", _p(t), _p(w), n, s, dilation, lo, hi, _p(t_out), _p(w_out), _stream())
+    return t_out, w_out
+
+
+def sample_intervals(t, logits, u_base, jitter, max_jitter, lo, hi, want_aux=False):
+    _chk(t, "t"), _chk(logits, "logits"), _chk(u_base, "u_base"), _chk(jitter, "jitter")
+    n, m = logits.shape
+    s = u_base.numel()
+    out = torch.empty(n, s + 1, device=t.device, dtype=_F32)
+    centers = torch.empty(n, s, device=t.device, dtype=_F32) if want_aux else None
+    idx = torch.empty(n, s, device=t.device, dtype=torch.int32) if want_aux else None
+    jc = 0 if jitter is None else jitter.shape[-1]
+    _lib.call("hos_sample_intervals", _p(t), _p(logits), _p(u_base), _p(jitter), jc, max_jitter, n, m, s,
+              lo, hi, _p(out), _p(centers), _p(idx), _stream())
+    return (out, centers, idx) if want_aux else out
+
+
+def resample_level(sdist, weights, dilate, dilation, anneal, padding, u_base, jitter, max_jitter,
+                   lo, hi, s_near, s_far):
+    _chk(sdist, "sdist"), _chk(weights, "weights"), _chk(u_base, "u_base"), _chk(jitter, "jitter")
+    n, m = weights.shape
+    s = u_base.numel()
+    sd = torch.empty(n, s + 1, device=sdist.device, dtype=_F32)
+    td = torch.empty(n, s + 1, device=sdist.device, dtype=_F32)
+    jc = 0 if jitter is None else jitter.shape[-1]
+    _lib.call("hos_resample_level", _p(sdist), _p(weights), n, m, int(dilate), dilation, anneal, padding,
+              _p(u_base), _p(jitter), jc, max_jitter, s, lo, hi, s_near, s_far, _p(sd), _p(td), _stream())
+    return sd, td
+
+
+def human_samples(rays_o, rays_d, near, far, t_lin, rand=None):
+    for t, nm in ((rays_o, "rays_o"), (rays_d, "rays_d"), (near, "near"), (far, "far"), (t_lin, "t_lin"), (rand, "rand")):
+        _chk(t, nm)
+    n, s = rays_o.shape[0], t_lin.numel()
+    z = torch.empty(n, s, device=rays_o.device, dtype=_F32)
+    pts = torch.empty(n, s, 3, device=rays_o.device, dtype=_F32)
+    _lib.call("hos_human_samples", _p(rays_o), _p(rays_d), _p(near), _p(far), _p(t_lin), _p(rand), n, s,
+              _p(z), _p(pts), _stream())
+    return z, pts
+
+
+# ----------------------------------------------------------------------------- encodings
+def tiled_bytes(rows: int, k: int) -> int:
+    return ((rows + 127) // 128) * ((k + 63) // 64) * 16384
+
+
+def ipe_features(tdist, rays_o, rays_d, radii, basis, min_deg=0, max_deg=12, out="fp32", want_aux=False):
+    for t, nm in ((tdist, "tdist"), (rays_o, "rays_o"), (rays_d, "rays_d"), (radii, "radii"), (basis, "basis")):
+        _chk(t, nm)
+    n, s1 = tdist.shape
+    s = s1 - 1
+    b = basis.shape[1]
+    width = 2 * (max_deg - min_deg) * b
+    dev = tdist.device
+    if out == "fp32":
+        feat, ld, code = torch.empty(n * s, width, device=dev, dtype=_F32), width, 0
+    elif out == "fp16":
+        feat, ld, code = torch.empty(n * s, width, device=dev, dtype=torch.float16), width, 1
+    elif out == "tiled":
+        feat, ld, code = torch.empty(tiled_bytes(n * s, width), device=dev, dtype=torch.uint8), 0, 2
+    else:
+        raise ValueError(out)
+    means = torch.empty(n * s, 3, device=dev, dtype=_F32) if want_aux else None
+    lvar = torch.empty(n * s, b, device=dev, dtype=_F32) if want_aux else None
+    _lib.call("hos_ipe_features", _p(tdist), _p(rays_o), _p(rays_d), _p(radii), _p(basis), n, s, b,
+              min_deg, max_deg, _p(feat), ld, code, _p(means), _p(lvar), _stream())
+    return (feat, means, lvar) if want_aux else feat
+
+
+def pos_enc(x, min_deg, max_deg, append_identity=True):
+    _chk(x, "x")
+    n = x.shape[0]
+    width = (3 if append_identity else 0) + 6 * (max_deg - min_deg)
+    out = torch.empty(n, width, device=x.device, dtype=_F32)
+    _lib.call("hos_pos_enc", _p(x), n, min_deg, max_deg, int(append_identity), _p(out), _stream())
+    return out
+
+
+def fourier_embed(x, n_freqs, include_input, hann_w=None, out="fp32"):
+    _chk(x, "x"), _chk(hann_w, "hann_w")
+    p = x.shape[0]
+    width = (3 if include_input else 0) + 6 * n_freqs
+    if out == "fp32":
+        o, ld, code = torch.empty(p, width, device=x.device, dtype=_F32), width, 0
+    else:
+        o, ld, code = torch.empty(tiled_bytes(p, width), device=x.device, dtype=torch.uint8), 0, 2
+    _lib.call("hos_fourier_embed", _p(x), p, n_freqs, int(include_input), _p(hann_w), _p(o), ld, code, _stream())
+    return o
+
+
+# ----------------------------------------------------------------------------- LBS
+def lbs_warp(pts, R, T, vol, bbox_min, bbox_scale):
+    _chk(pts, "pts"), _chk(R, "R"), _chk(T, "T"), _chk(vol, "vol")
+    p = pts.numel() // 3
+    bones = R.shape[0]
+    g = vol.shape[-1]
+    assert vol.shape[0] >= bones and vol.shape[1] == g and vol.shape[2] == g
+    x = torch.empty(p, 3, device=pts.device, dtype=_F32)
+    m = torch.empty(p, device=pts.device, dtype=_F32)
+    _lib.call("hos_lbs_warp", _p(pts), _p(R), _p(T), _p(vol), _host3(bbox_min), _host3(bbox_scale), p, bones, g,
+              _p(x), _p(m), _stream())
+    return x, m
+
+
+# ----------------------------------------------------------------------------- fp32 MLP blocks
+def linear_f32(x1, w, b, act=0, x2=None, x2_row_div=1, k1=None, k2=None):
+    """y = act([x1[:, :k1] | x2[:, :k2]] @ w.T + b)."""
+    _chk(x1, "x1"), _chk(w, "w"), _chk(b, "b"), _chk(x2, "x2")
+    m = x1.shape[0]
+    k1 = x1.shape[1] if k1 is None else k1
+    k2 = 0 if x2 is None else (x2.shape[1] if k2 is None else k2)
+    n = w.shape[0]
+    assert w.shape[1] == k1 + k2, (w.shape, k1, k2)
+    y = torch.empty(m, n, device=x1.device, dtype=_F32)
+    _lib.call("hos_linear_f32_ex", _p(x1), x1.stride(0), k1, _p(x2), 0 if x2 is None else x2.stride(0), k2,
+              x2_row_div, _p(w), _p(b), m, n, act, _p(y), n, _stream())
+    return y
+
+
+def head_f32(x, w, b, post=0, shift=0.0, add=None):
+    _chk(x, "x"), _chk(w, "w"), _chk(b, "b"), _chk(add, "add")
+    m, k = x.shape
+    n = w.shape[0]
+    assert w.shape[1] == k
+    y = torch.empty(m, n, device=x.device, dtype=_F32)
+    _lib.call("hos_head_f32", _p(x), x.stride(0), k, _p(w), _p(b), m, n, post, shift, _p(add), _p(y), n, _stream())
+    return y
+
+
+# ----------------------------------------------------------------------------- tcgen05 MLP
+class FusedMLP:
+    """Owner of an opaque ``hos_mlp_t`` (repacked fp16 weights for the tcgen05 kernel)."""
+
+    def __init__(self, in_dim, layers, heads):
+        lib = _lib.load()
+        self.in_dim = in_dim
+        self.layers = layers
+        self.heads = heads
+        la = (_lib.MlpLayer * len(layers))(*[_lib.MlpLayer(**l) for l in layers])
+        ha = (_lib.MlpHead * max(len(heads), 1))(*[_lib.MlpHead(**h) for h in heads])
+        self._h = lib.hos_mlp_create(in_dim, len(layers), la, len(heads), ha)
+        if not self._h:
+            raise RuntimeError("hos_mlp_create failed: " + lib.hos_last_error().decode())
+        self.kblocks = lib.hos_mlp_in_kblocks(self._h)
+
+    def set_layer(self, i, w, b):
+        _chk(w, "w"), _chk(b, "b")
+        l = self.layers[i]
+        assert tuple(w.shape) == (l["out_dim"], l["in_h"] + l["in_x"]), (i, w.shape, l)
+        _lib.call("hos_mlp_set_layer", self._h, i, _p(w), _p(b), _stream())
+
+    def set_bias(self, i, b):
+        _chk(b, "b")
+        assert b.numel() == self.layers[i]["out_dim"]
+        _lib.call("hos_mlp_set_bias", self._h, i, _p(b), _stream())
+
+    def set_head(self, i, w, b):
+        _chk(w, "w"), _chk(b, "b")
+        _lib.call("hos_mlp_set_head", self._h, i, _p(w), _p(b), _stream())
+
+    def forward(self, x_tiled, rows, rowbias=None, rowbias_div=1, add=None):
+        _chk(x_tiled, "x_tiled", torch.uint8), _chk(rowbias, "rowbias"), _chk(add, "add")
+        assert x_tiled.numel() >= tiled_bytes(rows, self.kblocks * 64), "x_tiled too small for this MLP"
+        outs = [None, None]
+        for h in self.heads:
+            outs[h["out_slot"]] = torch.empty(rows, h["out_dim"], device=x_tiled.device, dtype=_F32)
+        _lib.call("hos_mlp_forward", self._h, _p(x_tiled), rows, _p(rowbias), rowbias_div, _p(add),
+                  _p(outs[0]), _p(outs[1]), _stream())
+        return outs
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().hos_mlp_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def pack_rows_f16(x, k=None):
+    _chk(x, "x")
+    rows = x.shape[0]
+    k = x.shape[1] if k is None else k
+    out = torch.empty(tiled_bytes(rows, k), device=x.device, dtype=torch.uint8)
+    _lib.call("hos_pack_rows_f16", _p(x), rows, x.stride(0), k, _p(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------- composite
+def composite_mip360(density, tdist, dirs, rgb=None, opaque_background=False, bg=1.0):
+    _chk(density, "density"), _chk(tdist, "tdist"), _chk(dirs, "dirs"), _chk(rgb, "rgb")
+    n, s = density.shape
+    w = torch.empty(n, s, device=density.device, dtype=_F32)
+    out = torch.empty(n, 3, device=density.device, dtype=_F32) if rgb is not None else None
+    _lib.call("hos_composite_mip360", _p(density), _p(tdist), _p(dirs), _p(rgb), n, s, int(opaque_background),
+              float(bg), _p(w), _p(out), _stream())
+    return w, out
+
+
+def composite_nerf(raw, mask, z, dirs, bgcolor=None, activate=True):
+    _chk(raw, "raw"), _chk(mask, "mask"), _chk(z, "z"), _chk(dirs, "dirs")
+    n, s = z.shape
+    dev = raw.device
+    rgb = torch.empty(n, 3, device=dev, dtype=_F32)
+    acc = torch.empty(n, device=dev, dtype=_F32)
+    w = torch.empty(n, s, device=dev, dtype=_F32)
+    depth = torch.empty(n, device=dev, dtype=_F32)
+    bg = None if bgcolor is None else _host3(bgcolor)
+    _lib.call("hos_composite_nerf", _p(raw), _p(mask), _p(z), _p(dirs), bg, n, s, int(activate), _p(rgb), _p(acc),
+              _p(w), _p(depth), _stream())
+    return rgb, acc, w, depth
+
+
+def composite_s3(bkg_rgb, bkg_density, bkg_tdist, human_rgb, human_density, pts_mask, newsmpl_pts, M,
+                 rays_o, rays_d, thre_fg=5e-3, want_human_w=True):
+    for t, nm in ((bkg_rgb, "bkg_rgb"), (bkg_density, "bkg_density"), (bkg_tdist, "bkg_tdist"),
+                  (human_rgb, "human_rgb"), (human_density, "human_density"), (pts_mask, "pts_mask"),
+                  (newsmpl_pts, "newsmpl_pts"), (rays_o, "rays_o"), (rays_d, "rays_d")):
+        _chk(t, nm)
+    n, sb = bkg_density.shape
+    sh = human_density.shape[1]
+    dev = bkg_rgb.device
+    rgb = torch.empty(n, 3, device=dev, dtype=_F32)
+    is_fg = torch.empty(n, device=dev, dtype=torch.uint8)
+    hw = torch.empty(n, sh, device=dev, dtype=_F32) if want_human_w else None
+    _lib.call("hos_composite_s3", _p(bkg_rgb), _p(bkg_density), _p(bkg_tdist), _p(human_rgb), _p(human_density),
+              _p(pts_mask), _p(newsmpl_pts), _host3(M, 16), _p(rays_o), _p(rays_d), n, sb, sh, thre_fg,
+              _p(rgb), _p(is_fg), _p(hw), _stream())
+    return rgb, is_fg.bool(), hw
