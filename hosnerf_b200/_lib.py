@@ -60,6 +60,8 @@ SIGNATURES = {
 }
 
 _lib = None
+LAUNCHES = 0          # kernels of this library launched so far (bench.py reports it per timed region)
+_KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_bias": 0, "hos_mlp_set_head": 0}
 
 
 def load():
@@ -87,4 +89,12 @@ def check(status: int, what: str = ""):
 
 
 def call(name: str, *args):
+    global LAUNCHES
     check(getattr(load(), name)(*args), name)
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+
+
+def call_unless_empty(n, name: str, *args):
+    """torch gives empty tensors a NULL data pointer; an empty batch is a no-op by contract."""
+    if n != 0:
+        call(name, *args)

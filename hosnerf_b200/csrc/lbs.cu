@@ -5,6 +5,8 @@
 // sample point: bone transforms sit in shared memory, the 3.4 MiB weight volume is read
 // through the read-only path and stays L2-resident (gathers from neighbouring samples of
 // a ray hit the same cache lines), and only pts (12 B) in / x_skel+mask (16 B) out touch HBM.
+// Compiled with -fmad=false: the canonical MLP downstream sees sin(2^9 x), so the warp is kept
+// rounding-compatible with the reference's un-fused torch ops (see tests/test_gpu_models.py).
 #include "common.cuh"
 
 namespace hos {
@@ -61,9 +63,10 @@ lbs_warp_kernel(const float* __restrict__ pts, const float* __restrict__ R, cons
 #pragma unroll 2
     for (int b = 0; b < bones; ++b) {
       const float* r = sR + b * 9;
-      float qx = r[0] * px + r[1] * py + r[2] * pz + sT[b * 3 + 0];
-      float qy = r[3] * px + r[4] * py + r[5] * pz + sT[b * 3 + 1];
-      float qz = r[6] * px + r[7] * py + r[8] * pz + sT[b * 3 + 2];
+      // matmul(R_i, pts.T): K=3 GEMM micro-kernel order (fma chain), then the separate "+ T_i"
+      float qx = fmaf(r[2], pz, fmaf(r[1], py, r[0] * px)) + sT[b * 3 + 0];
+      float qy = fmaf(r[5], pz, fmaf(r[4], py, r[3] * px)) + sT[b * 3 + 1];
+      float qz = fmaf(r[8], pz, fmaf(r[7], py, r[6] * px)) + sT[b * 3 + 2];
       float gx = (qx - prm.bbox_min[0]) * prm.bbox_scale[0] - 1.0f;
       float gy = (qy - prm.bbox_min[1]) * prm.bbox_scale[1] - 1.0f;
       float gz = (qz - prm.bbox_min[2]) * prm.bbox_scale[2] - 1.0f;

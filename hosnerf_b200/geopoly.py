@@ -64,4 +64,4 @@ def generate_basis(base_shape: str = "icosahedron", angular_tesselation: int = 2
     if remove_symmetries:
         mirrored = _pairwise_sq(verts, -verts) < eps
         verts = verts[np.any(np.triu(mirrored), 1), :]
-    return torch.from_numpy(verts[:, ::-1].copy().T).to(dtype=torch.float32)
+    return torch.from_numpy(verts[:, ::-1].copy().T).to(dtype=torch.float32).contiguous()

@@ -247,7 +247,7 @@ class MotionBasisComputer(nn.Module):
         self.total_bones = total_bones
 
     def forward(self, dst_Rs, dst_Ts, cnl_gtfms):
-        dev = dst_Rs.device
+        dev = cnl_gtfms.device
         Rs, Ts, cg = dst_Rs.detach().cpu(), dst_Ts.detach().cpu(), cnl_gtfms.detach().cpu()
         b, nb = Rs.shape[:2]
         local = torch.zeros(b, nb, 4, 4, dtype=Rs.dtype)
@@ -444,11 +444,28 @@ class Network(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _correct_pose(self, dst_Rs, dst_Ts, posevec):
-        out = self.pose_decoder(posevec)
+        """Pose refinement (network.py:590-605) on the HOST: a 4-layer MLP on one 75-vector and 25
+        3x3 products per frame - a handful of microseconds on the CPU versus ~20 kernel launches."""
+        key = self._versions([self.pose_decoder])
+        if self._cache.get("pose_key") != key:
+            self._cache["pose_key"] = key
+            self._cache["pose_cpu"] = {k: v.detach().cpu() for k, v in self.pose_decoder.state_dict().items()}
+        sd = self._cache["pose_cpu"]
+
+        def seq(prefix, x, n_relu_last):
+            idxs = sorted({int(k.split(".")[1]) for k in sd if k.startswith(prefix + ".") and k.endswith("weight")})
+            for j, i in enumerate(idxs):
+                x = F.linear(x, sd[f"{prefix}.{i}.weight"], sd[f"{prefix}.{i}.bias"])
+                if n_relu_last or j < len(idxs) - 1:
+                    x = F.relu(x)
+            return x
+        h = seq("block_mlps", posevec, True)
         nb = self.cfg.total_bones - 1
-        Rn = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), out["Rs"].reshape(-1, 3, 3)).reshape(-1, nb, 3, 3)
+        dR = BodyPoseRefiner._rodrigues(seq("block_mlps_dstR", h, False).view(-1, 3)).view(-1, nb, 3, 3)
+        dT = seq("block_mlps_dstT", h, False).view(-1, nb, 3)
+        Rn = torch.matmul(dst_Rs[:, 1:].reshape(-1, 3, 3), dR.reshape(-1, 3, 3)).reshape(-1, nb, 3, 3)
         Rs = torch.cat([dst_Rs[:, 0:1], Rn], dim=1)
-        Ts = torch.cat([dst_Ts[:, 0:1], dst_Ts[:, 1:] + out["Ts"]], dim=1)
+        Ts = torch.cat([dst_Ts[:, 0:1], dst_Ts[:, 1:] + dT], dim=1)
         return Rs, Ts
 
     def forward(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec=None,
@@ -465,10 +482,11 @@ class Network(nn.Module):
         cfg = self.cfg
         it = float(iter_val.reshape(-1)[0]) if isinstance(iter_val, torch.Tensor) else float(iter_val)
         with torch.no_grad():
-            dst_Rs, dst_Ts = dst_Rs[None, ...], dst_Ts[None, ...]
+            # per-frame prologue runs on the host (26 bones of 4x4 algebra), see MotionBasisComputer
+            dst_Rs, dst_Ts = dst_Rs[None, ...].detach().cpu(), dst_Ts[None, ...].detach().cpu()
             posevec = dst_posevec[None, ...]
             if it >= cfg.pose_decoder.get("kick_in_iter", 0):
-                dst_Rs, dst_Ts = self._correct_pose(dst_Rs, dst_Ts, posevec)
+                dst_Rs, dst_Ts = self._correct_pose(dst_Rs, dst_Ts, posevec.detach().cpu())
             hann_w = hann_window_weights(self.nr_freqs, it, cfg.non_rigid_motion_mlp.kick_in_iter,
                                          cfg.non_rigid_motion_mlp.full_band_iter).to(rays.device)
             cond = torch.zeros_like(posevec) * posevec if it < cfg.non_rigid_motion_mlp.kick_in_iter else posevec

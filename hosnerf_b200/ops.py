@@ -12,6 +12,7 @@ import torch
 from . import _lib
 
 _F32 = torch.float32
+PROFILE = None        # bench.py sets this to a list: (n_layers, rows, start_event, stop_event) per MLP launch
 
 
 def _stream():
@@ -71,7 +72,7 @@ def resample_level(sdist, weights, dilate, dilation, anneal, padding, u_base, ji
     sd = torch.empty(n, s + 1, device=sdist.device, dtype=_F32)
     td = torch.empty(n, s + 1, device=sdist.device, dtype=_F32)
     jc = 0 if jitter is None else jitter.shape[-1]
-    _lib.call("hos_resample_level", _p(sdist), _p(weights), n, m, int(dilate), dilation, anneal, padding,
+    _lib.call_unless_empty(n, "hos_resample_level", _p(sdist), _p(weights), n, m, int(dilate), dilation, anneal, padding,
               _p(u_base), _p(jitter), jc, max_jitter, s, lo, hi, s_near, s_far, _p(sd), _p(td), _stream())
     return sd, td
 
@@ -82,7 +83,7 @@ def human_samples(rays_o, rays_d, near, far, t_lin, rand=None):
     n, s = rays_o.shape[0], t_lin.numel()
     z = torch.empty(n, s, device=rays_o.device, dtype=_F32)
     pts = torch.empty(n, s, 3, device=rays_o.device, dtype=_F32)
-    _lib.call("hos_human_samples", _p(rays_o), _p(rays_d), _p(near), _p(far), _p(t_lin), _p(rand), n, s,
+    _lib.call_unless_empty(n, "hos_human_samples", _p(rays_o), _p(rays_d), _p(near), _p(far), _p(t_lin), _p(rand), n, s,
               _p(z), _p(pts), _stream())
     return z, pts
 
@@ -145,7 +146,7 @@ def lbs_warp(pts, R, T, vol, bbox_min, bbox_scale):
     assert vol.shape[0] >= bones and vol.shape[1] == g and vol.shape[2] == g
     x = torch.empty(p, 3, device=pts.device, dtype=_F32)
     m = torch.empty(p, device=pts.device, dtype=_F32)
-    _lib.call("hos_lbs_warp", _p(pts), _p(R), _p(T), _p(vol), _host3(bbox_min), _host3(bbox_scale), p, bones, g,
+    _lib.call_unless_empty(p, "hos_lbs_warp", _p(pts), _p(R), _p(T), _p(vol), _host3(bbox_min), _host3(bbox_scale), p, bones, g,
               _p(x), _p(m), _stream())
     return x, m
 
@@ -212,8 +213,14 @@ class FusedMLP:
         outs = [None, None]
         for h in self.heads:
             outs[h["out_slot"]] = torch.empty(rows, h["out_dim"], device=x_tiled.device, dtype=_F32)
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.call("hos_mlp_forward", self._h, _p(x_tiled), rows, _p(rowbias), rowbias_div, _p(add),
                   _p(outs[0]), _p(outs[1]), _stream())
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((len(self.layers), rows, e0, e1))
         return outs
 
     def __del__(self):
@@ -240,7 +247,7 @@ def composite_mip360(density, tdist, dirs, rgb=None, opaque_background=False, bg
     n, s = density.shape
     w = torch.empty(n, s, device=density.device, dtype=_F32)
     out = torch.empty(n, 3, device=density.device, dtype=_F32) if rgb is not None else None
-    _lib.call("hos_composite_mip360", _p(density), _p(tdist), _p(dirs), _p(rgb), n, s, int(opaque_background),
+    _lib.call_unless_empty(n, "hos_composite_mip360", _p(density), _p(tdist), _p(dirs), _p(rgb), n, s, int(opaque_background),
               float(bg), _p(w), _p(out), _stream())
     return w, out
 
@@ -254,7 +261,7 @@ def composite_nerf(raw, mask, z, dirs, bgcolor=None, activate=True):
     w = torch.empty(n, s, device=dev, dtype=_F32)
     depth = torch.empty(n, device=dev, dtype=_F32)
     bg = None if bgcolor is None else _host3(bgcolor)
-    _lib.call("hos_composite_nerf", _p(raw), _p(mask), _p(z), _p(dirs), bg, n, s, int(activate), _p(rgb), _p(acc),
+    _lib.call_unless_empty(n, "hos_composite_nerf", _p(raw), _p(mask), _p(z), _p(dirs), bg, n, s, int(activate), _p(rgb), _p(acc),
               _p(w), _p(depth), _stream())
     return rgb, acc, w, depth
 
@@ -271,7 +278,7 @@ def composite_s3(bkg_rgb, bkg_density, bkg_tdist, human_rgb, human_density, pts_
     rgb = torch.empty(n, 3, device=dev, dtype=_F32)
     is_fg = torch.empty(n, device=dev, dtype=torch.uint8)
     hw = torch.empty(n, sh, device=dev, dtype=_F32) if want_human_w else None
-    _lib.call("hos_composite_s3", _p(bkg_rgb), _p(bkg_density), _p(bkg_tdist), _p(human_rgb), _p(human_density),
+    _lib.call_unless_empty(n, "hos_composite_s3", _p(bkg_rgb), _p(bkg_density), _p(bkg_tdist), _p(human_rgb), _p(human_density),
               _p(pts_mask), _p(newsmpl_pts), _host3(M, 16), _p(rays_o), _p(rays_d), n, sb, sh, thre_fg,
               _p(rgb), _p(is_fg), _p(hw), _stream())
     return rgb, is_fg.bool(), hw

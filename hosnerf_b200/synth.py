@@ -36,6 +36,18 @@ def _name_seed(name: str, seed: int) -> int:
     return (zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF
 
 
+# Output layers that the reference initialises to ~0 (offsets / pose corrections start at
+# identity, mlp_offset.py:45-50, mlp_delta_body_pose.py:52-60) and that stay small after
+# training: a uniformly Kaiming-scaled fill would make the synthetic human warp metre-sized
+# instead of centimetre-sized, which no trained model does.
+SMALL_OUTPUT_LAYERS = {
+    "non_rigid_mlp.block_mlps.12.": 0.02,
+    "non_rigid_forward_mlp.block_mlps.12.": 0.02,
+    "pose_decoder.block_mlps_dstR.2.": 0.1,
+    "pose_decoder.block_mlps_dstT.2.": 0.02,
+}
+
+
 @torch.no_grad()
 def fill_params_(module: torch.nn.Module, seed: int = 0, skip_prefixes=()) -> None:
     """Overwrite every parameter of ``module`` with values that depend only on
@@ -58,6 +70,9 @@ def fill_params_(module: torch.nn.Module, seed: int = 0, skip_prefixes=()) -> No
             v = (torch.rand(p.shape, generator=g) * 2 - 1) * 0.05
         else:
             v = torch.randn(p.shape, generator=g)
+        for key, sc in SMALL_OUTPUT_LAYERS.items():
+            if key in name + ".":
+                v = v * sc
         p.copy_(v.to(p.dtype))
 
 

