@@ -35,9 +35,12 @@ constexpr int kKB = 64;                    // K elements per chunk (128 bytes of
 constexpr int kXChunkBytes = kTileM * 128; // 16 KB
 constexpr int kMaxLayers = 12;
 constexpr int kMaxHeads = 4;
-constexpr int kStages = 3;
-constexpr int kMlpThreads = 192;
+constexpr int kStages = 3;       // weight ring depth
+constexpr int kStagesX = 3;      // input-feature ring depth
+constexpr int kMlpThreads = 320; // warp 0 producer, 1 MMA, 2-5 epilogue, 6-9 feature generators
 constexpr int kTmemCols = 256;
+constexpr int kIpeB = 21;        // geodesic basis directions (icosahedron, 2 subdivisions)
+constexpr int kIpeDeg = 12;      // octaves 2^0 .. 2^11
 
 struct LayerDev {
   uint32_t w_off;      // byte offset of the first weight chunk in the packed fp16 buffer
@@ -140,8 +143,19 @@ __host__ __device__ inline uint32_t umma_idesc_f16(int n) {
 }
 
 
+// Inputs of the fused integrated-positional-encoding prologue (S1 helper.py:242-302, 26-78):
+// the feature warps turn ray intervals straight into fp16 A-operand chunks in shared memory.
+struct IpeArgs {
+  const float* tdist;    // [N, S+1]
+  const float* rays_o;   // [N, 3]
+  const float* rays_d;   // [N, 3]
+  const float* radii;    // [N]
+  int S;
+  float basis[3 * kIpeB];
+};
+
 struct MlpArgs {
-  const unsigned char* x_tiled;   // [ntiles][kbx][16 KB]
+  const unsigned char* x_tiled;   // [ntiles][kbx][16 KB], or null when the IPE prologue is fused
   const unsigned char* w_packed;  // fp16 chunks
   const float* params;            // biases + head weights
   const float* rowbias;           // [rows / rowbias_div][n] or null
@@ -150,30 +164,160 @@ struct MlpArgs {
   int64_t rows;
   int ntiles;
   int rowbias_div;
+  int fused_ipe;
 };
 
+// ----------------------------------------------------------------------------- fused IPE prologue
+// One feature thread owns one row (sample) of the 128-row tile and produces its 504 features
+// octave by octave.  Kernel column order is  col = (l*21 + j)*2 + {0: sin, 1: cos}  (the weight
+// columns are permuted to match at upload time), so octave l lands in columns [42 l, 42 l + 42) and
+// the K-blocks come out in order while the recurrences run along l:
+//   sin/cos(2^l m): angle doubling, re-seeded from MUFU sin/cos after Cody-Waite reduction every 4
+//                   octaves (error <= ~1e-5, below the fp16 resolution of the operand);
+//   exp(-.5 4^l v): ex2.approx every 3rd octave, e_{l+1} = e_l^4 in between.
+// Per row and pass: ~210 MUFU + ~2.5 k FP instructions instead of 756 libm calls, and the features
+// never exist outside shared memory.
+struct IpeRowState {
+  float s[kIpeB], c[kIpeB], e[kIpeB], lv[kIpeB];
+  float mean[3];
+};
+
+__device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, bool row_ok, IpeRowState& st) {
+  float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, t0 = 1.f, t1 = 2.f, radius = 0.f;
+  if (row_ok) {
+    const int64_t ray = row / A.S;
+    const int smp = (int)(row % A.S);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { o[i] = A.rays_o[ray * 3 + i]; d[i] = A.rays_d[ray * 3 + i]; }
+    t0 = A.tdist[ray * (A.S + 1) + smp];
+    t1 = A.tdist[ray * (A.S + 1) + smp + 1];
+    radius = A.radii[ray];
+  }
+  // conical frustum -> Gaussian (helper.py:257-267)
+  const float mu = 0.5f * (t0 + t1), hw = 0.5f * (t1 - t0);
+  const float mu2 = mu * mu, hw2 = hw * hw, hw4 = hw2 * hw2;
+  const float denom = fmaxf(3.f * mu2 + hw2, 1.1920929e-07f);
+  const float inv_den = 1.f / denom;
+  const float t_mean = mu + 2.f * mu * hw2 * inv_den;
+  const float t_var = hw2 * (1.f / 3.f) - (4.f / 15.f) * hw4 * (12.f * mu2 - hw2) * inv_den * inv_den;
+  const float r_var = (mu2 * 0.25f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 * inv_den) * radius * radius;
+  const float dsq = fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-10f);
+  const float inv_dsq = 1.f / dsq;
+  float x[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) x[i] = fmaf(d[i], t_mean, o[i]);
+  // contraction (helper.py:26-60): z = a x, J = a I + b x x^T (identity inside the unit ball)
+  const float m = fmaxf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2], 1e-32f);
+  float a = 1.f, bq = 0.f;
+  if (m > 1.f) {
+    const float r = sqrtf(m), inv_m = 1.f / m;
+    a = (2.f * r - 1.f) * inv_m;
+    bq = 2.f * (1.f - r) * inv_m * inv_m;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) st.mean[i] = a * x[i];
+  const float xd = x[0] * d[0] + x[1] * d[1] + x[2] * d[2];
+  // lifted variance b_j^T J cov J^T b_j with cov = t_var d d^T + r_var (I - d d^T / |d|^2):
+  //   v = J b_j = a b_j + bq (x.b_j) x ;  var = t_var (d.v)^2 + r_var (|v|^2 - (d.v)^2 / |d|^2)
+#pragma unroll
+  for (int j = 0; j < kIpeB; ++j) {
+    const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
+    const float xb = x[0] * b0 + x[1] * b1 + x[2] * b2;
+    const float db = d[0] * b0 + d[1] * b1 + d[2] * b2;
+    const float k = bq * xb;
+    const float dv = fmaf(k, xd, a * db);
+    const float vv = a * a + k * (2.f * a * xb + k * m);        // |b_j| = 1
+    st.lv[j] = fmaxf(fmaf(t_var, dv * dv, r_var * (vv - dv * dv * inv_dsq)), 0.f);
+  }
+}
+
+// Produce the kb_x feature chunks of one pass for row r into the X ring.
+__device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, IpeRowState& st, int r, unsigned char* sRingX,
+                                                  uint64_t* bar_xfull, uint64_t* bar_xempty, uint32_t& xi) {
+  constexpr float kInv2Pi = 0.15915494309189535f;
+  constexpr float k2PiHi = 6.2831854820251465f;           // fl32(2 pi)
+  constexpr float k2PiLo = -1.7484555e-07f;               // 2 pi - fl32(2 pi)
+  constexpr float kHalfLog2e = 0.72134752044448170f;      // 0.5 * log2(e)
+  uint32_t pk[4];
+  unsigned char* slot = nullptr;
+#pragma unroll
+  for (int l = 0; l < kIpeDeg; ++l) {
+#pragma unroll
+    for (int j = 0; j < kIpeB; ++j) {
+      const int p = l * kIpeB + j;                // pair index; columns 2p, 2p+1
+      if ((p & 31) == 0) {                        // first pair of a 64-column chunk: acquire a slot
+        const int xs = xi % kStagesX;
+        mbar_wait(&bar_xempty[xs], ((xi / kStagesX) & 1) ^ 1);
+        slot = sRingX + xs * kXChunkBytes;
+      }
+      // ---- sin/cos of 2^l m_j
+      if ((l & 3) == 0) {
+        const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
+        const float arg = (st.mean[0] * b0 + st.mean[1] * b1 + st.mean[2] * b2) * (float)(1 << l);
+        const float kq = rintf(arg * kInv2Pi);
+        float xr = fmaf(-kq, k2PiHi, arg);
+        xr = fmaf(-kq, k2PiLo, xr);
+        st.s[j] = __sinf(xr);
+        st.c[j] = __cosf(xr);
+      } else {
+        const float s2 = st.s[j] * st.c[j];
+        st.c[j] = fmaf(-2.f * st.s[j], st.s[j], 1.f);
+        st.s[j] = s2 + s2;
+      }
+      // ---- exp(-0.5 * 4^l * var_j)
+      if ((l % 3) == 0) {
+        st.e[j] = exp2f(-kHalfLog2e * (float)(1 << (2 * l)) * st.lv[j]);
+      } else {
+        const float e2 = st.e[j] * st.e[j];
+        st.e[j] = e2 * e2;
+      }
+      __half2 h = __floats2half2_rn(st.e[j] * st.s[j], st.e[j] * st.c[j]);
+      pk[p & 3] = *reinterpret_cast<uint32_t*>(&h);
+      if ((p & 3) == 3) {
+        const int g = (p & 31) >> 2;              // 16-byte group inside the chunk row
+        *reinterpret_cast<uint4*>(slot + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      if ((p & 31) == 31) {                       // chunk complete
+        fence_proxy_async();
+        mbar_arrive(&bar_xfull[xi % kStagesX]);
+        ++xi;
+      }
+    }
+  }
+  // 252 pairs = 7 chunks + 28 pairs: groups 0..6 of the last chunk are written, zero the 8th
+  *reinterpret_cast<uint4*>(slot + r * 128 + ((7 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  mbar_arrive(&bar_xfull[xi % kStagesX]);
+  ++xi;
+}
+
 __global__ void __launch_bounds__(kMlpThreads, 1)
-mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const MlpArgs args) {
+mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
+              const __grid_constant__ IpeArgs ipe) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // carve-up (all chunk bases 1024-aligned, required by SWIZZLE_128B)
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_stage_bytes = prog.n_max * 128;
   unsigned char* sH = smem;                                            // kbh * 16 KB
   unsigned char* sRingW = sH + prog.kbh * kXChunkBytes;                // kStages * w_stage_bytes
-  unsigned char* sRingX = sRingW + kStages * w_stage_bytes;            // kStages * 16 KB
-  float* sParams = reinterpret_cast<float*>(sRingX + kStages * kXChunkBytes);
+  unsigned char* sRingX = sRingW + kStages * w_stage_bytes;            // kStagesX * 16 KB
+  float* sParams = reinterpret_cast<float*>(sRingX + kStagesX * kXChunkBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((prog.param_floats + 3) & ~3));
-  uint64_t* bar_full = bars;                 // [kStages]
-  uint64_t* bar_empty = bars + kStages;      // [kStages]
-  uint64_t* bar_tmem_full = bars + 2 * kStages;
-  uint64_t* bar_act = bars + 2 * kStages + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  uint64_t* bar_wfull = bars;                           // [kStages]
+  uint64_t* bar_wempty = bar_wfull + kStages;           // [kStages]
+  uint64_t* bar_xfull = bar_wempty + kStages;           // [kStagesX]
+  uint64_t* bar_xempty = bar_xfull + kStagesX;          // [kStagesX]
+  uint64_t* bar_tmem_full = bar_xempty + kStagesX;
+  uint64_t* bar_act = bar_tmem_full + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_act + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fused = args.fused_ipe != 0;
 
   for (int i = threadIdx.x; i < prog.param_floats; i += kMlpThreads) sParams[i] = args.params[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wempty[s], 1); }
+    for (int s = 0; s < kStagesX; ++s) { mbar_init(&bar_xfull[s], fused ? 128 : 1); mbar_init(&bar_xempty[s], 1); }
     mbar_init(bar_tmem_full, 1);
     mbar_init(bar_act, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -188,32 +332,35 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const MlpArgs args) {
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0) {
-    // ===================== producer =====================
+    // ===================== producer: bulk copies of weight (and, un-fused, input) chunks =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t wi = 0, xi = 0;
       for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
         for (int l = 0; l < prog.n_layers; ++l) {
           const LayerDev L = prog.layers[l];
           const uint32_t wbytes = (uint32_t)L.n * 128u;
           const int nkb = L.kb_h + L.kb_x;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int st = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(&bar_empty[st], ph ^ 1);
-            const bool needx = kb >= L.kb_h;
-            mbar_expect_tx(&bar_full[st], wbytes + (needx ? (uint32_t)kXChunkBytes : 0u));
-            bulk_g2s(sRingW + st * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * wbytes, wbytes, &bar_full[st]);
-            if (needx)
-              bulk_g2s(sRingX + st * kXChunkBytes,
+          for (int kb = 0; kb < nkb; ++kb, ++wi) {
+            const int ws = wi % kStages;
+            mbar_wait(&bar_wempty[ws], ((wi / kStages) & 1) ^ 1);
+            mbar_expect_tx(&bar_wfull[ws], wbytes);
+            bulk_g2s(sRingW + ws * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * wbytes, wbytes, &bar_wfull[ws]);
+            if (kb >= L.kb_h && !fused) {
+              const int xs = xi % kStagesX;
+              mbar_wait(&bar_xempty[xs], ((xi / kStagesX) & 1) ^ 1);
+              mbar_expect_tx(&bar_xfull[xs], kXChunkBytes);
+              bulk_g2s(sRingX + xs * kXChunkBytes,
                        args.x_tiled + ((size_t)tile * prog.kbx + (kb - L.kb_h)) * kXChunkBytes, kXChunkBytes,
-                       &bar_full[st]);
+                       &bar_xfull[xs]);
+              ++xi;
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    uint32_t it = 0, li = 0;
+    uint32_t wi = 0, xi = 0, li = 0;
     for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
       for (int l = 0; l < prog.n_layers; ++l, ++li) {
         const LayerDev L = prog.layers[l];
@@ -223,26 +370,30 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const MlpArgs args) {
           tc_fence_after();
         }
         const int nkb = L.kb_h + L.kb_x;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int st = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&bar_full[st], ph);
+        for (int kb = 0; kb < nkb; ++kb, ++wi) {
+          const int ws = wi % kStages;
+          const bool from_x = kb >= L.kb_h;
+          const int xs = xi % kStagesX;
+          mbar_wait(&bar_wfull[ws], (wi / kStages) & 1);
+          if (from_x) mbar_wait(&bar_xfull[xs], (xi / kStagesX) & 1);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_base = smem_u32(kb < L.kb_h ? sH + kb * kXChunkBytes : sRingX + st * kXChunkBytes);
-            const uint32_t b_base = smem_u32(sRingW + st * w_stage_bytes);
+            const uint32_t a_base = smem_u32(from_x ? sRingX + xs * kXChunkBytes : sH + kb * kXChunkBytes);
+            const uint32_t b_base = smem_u32(sRingW + ws * w_stage_bytes);
 #pragma unroll
             for (int k = 0; k < kKB / 16; ++k)
               tc_mma_f16(tmem_base, umma_desc(a_base + k * 32), umma_desc(b_base + k * 32), idesc,
                          (kb | k) != 0 ? 1u : 0u);
-            tc_commit(&bar_empty[st]);          // frees the ring stage when these MMAs retire
+            tc_commit(&bar_wempty[ws]);         // ring slots are released when these MMAs retire
+            if (from_x) tc_commit(&bar_xempty[xs]);
             if (kb == nkb - 1) tc_commit(bar_tmem_full);
           }
           __syncwarp();
+          if (from_x) ++xi;
         }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                // row within the tile
@@ -323,6 +474,19 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const MlpArgs args) {
         mbar_arrive(bar_act);
       }
     }
+  } else if (fused) {
+    // ===================== feature generators (warps 6..9): fused IPE prologue =====================
+    const int r = (warp - 6) * 32 + lane;
+    uint32_t xi = 0;
+    IpeRowState st;
+    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
+      const int64_t row = (int64_t)tile * kTileM + r;
+      for (int l = 0; l < prog.n_layers; ++l) {
+        if (prog.layers[l].kb_x == 0) continue;
+        ipe_row_setup(ipe, row, row < args.rows, st);
+        ipe_generate_pass(ipe, st, r, sRingX, bar_xfull, bar_xempty, xi);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -335,8 +499,10 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const MlpArgs args) {
 // ----------------------------------------------------------------------------- packing
 // W fp32 [N, in_h + in_x] (nn.Linear layout, columns ordered [x|h] if x_first else [h|x])
 // -> fp16 chunks in kernel K order: kb_h chunks of h columns, then kb_x chunks of x columns.
+// ipe_perm != 0: the x columns are re-ordered from the reference's IPE layout
+// f = half*252 + l*21 + j  to the kernel's generation order  col = (l*21 + j)*2 + half.
 __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h, int in_x, int x_first, int kb_h,
-                                   int kb_x, unsigned char* __restrict__ dst) {
+                                   int kb_x, int ipe_perm, unsigned char* __restrict__ dst) {
   const int nkb = kb_h + kb_x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)nkb * N * kKB) return;
@@ -350,7 +516,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h,
     if (c < in_h) v = W[(int64_t)n * ktot + (x_first ? in_x + c : c)];
   } else {
     int c = (kb - kb_h) * kKB + kk;
-    if (c < in_x) v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
+    if (c < in_x) {
+      if (ipe_perm) c = (c & 1) * (kIpeDeg * kIpeB) + (c >> 1);
+      v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
+    }
   }
   *reinterpret_cast<__half*>(dst + (size_t)kb * N * 128 + tile_byte_offset(n, kk)) = __float2half_rn(v);
 }
@@ -382,6 +551,7 @@ struct hos_mlp {
   float* d_params = nullptr;         // biases + head weights (fp32)
   size_t w_bytes = 0;
   size_t smem_bytes = 0;
+  int ipe_perm = 0;        // weights packed for the fused-IPE column order
 };
 
 extern "C" {
@@ -452,8 +622,9 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   P.n_max = nmax;
   P.param_floats = (int)poff;
   m->w_bytes = woff;
-  m->smem_bytes = 1024 + (size_t)P.kbh * kXChunkBytes + (size_t)kStages * (nmax * 128 + kXChunkBytes) +
-                  (((size_t)poff + 3) & ~(size_t)3) * 4 + (2 * kStages + 2) * 8 + 16;
+  m->smem_bytes = 1024 + (size_t)P.kbh * kXChunkBytes + (size_t)kStages * nmax * 128 +
+                  (size_t)kStagesX * kXChunkBytes + (((size_t)poff + 3) & ~(size_t)3) * 4 +
+                  (2 * kStages + 2 * kStagesX + 2) * 8 + 16;
   if (m->smem_bytes > 227 * 1024) {
     hos::set_error("hos_mlp_create: needs %zu B shared memory (> 227 KB)", m->smem_bytes);
     delete m;
@@ -484,7 +655,7 @@ int hos_mlp_set_layer(hos_mlp_t* m, int layer, const float* W, const float* b, v
   cudaStream_t st = (cudaStream_t)stream;
   int64_t tot = (int64_t)(D.kb_h + D.kb_x) * D.n * kKB;
   pack_weight_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(W, D.n, L.in_h, L.in_x, L.x_first, D.kb_h, D.kb_x,
-                                                                   m->d_w + D.w_off);
+                                                                   m->ipe_perm, m->d_w + D.w_off);
   HOS_LAUNCH_CHECK();
   if (b) HOS_CUDA(cudaMemcpyAsync(m->d_params + D.bias_off, b, (size_t)D.n * 4, cudaMemcpyDeviceToDevice, st));
   else HOS_CUDA(cudaMemsetAsync(m->d_params + D.bias_off, 0, (size_t)D.n * 4, st));
@@ -511,10 +682,8 @@ int hos_mlp_set_head(hos_mlp_t* m, int head, const float* W, const float* b, voi
 
 int hos_mlp_in_kblocks(const hos_mlp_t* m) { return m ? m->prog.kbx : 0; }
 
-int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float* rowbias, int rowbias_div,
-                    const float* add, float* out0, float* out1, void* stream) {
-  HOS_ARCH_GUARD();
-  HOS_REQUIRE(m && x_tiled && rows >= 0, "hos_mlp_forward: bad handle/input");
+static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int64_t rows, const float* rowbias,
+                      int rowbias_div, const float* add, float* out0, float* out1, void* stream) {
   for (int l = 0; l < m->prog.n_layers; ++l)
     HOS_REQUIRE(!m->prog.layers[l].rowbias || (rowbias && rowbias_div >= 1), "hos_mlp_forward: layer %d needs rowbias", l);
   for (int h = 0; h < m->prog.n_heads; ++h) {
@@ -533,10 +702,44 @@ int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float
   a.rows = rows;
   a.ntiles = (int)((rows + kTileM - 1) / kTileM);
   a.rowbias_div = rowbias_div < 1 ? 1 : rowbias_div;
+  a.fused_ipe = ipe != nullptr;
+  static const IpeArgs kNoIpe = {};
   int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a);
+  mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
   HOS_LAUNCH_CHECK();
   return HOS_OK;
+}
+
+int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float* rowbias, int rowbias_div,
+                    const float* add, float* out0, float* out1, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && x_tiled && rows >= 0, "hos_mlp_forward: bad handle/input");
+  HOS_REQUIRE(!m->ipe_perm, "hos_mlp_forward: this MLP was created for the fused IPE prologue (use hos_mlp_forward_ipe)");
+  return mlp_launch(m, x_tiled, nullptr, rows, rowbias, rowbias_div, add, out0, out1, stream);
+}
+
+int hos_mlp_set_ipe_input(hos_mlp_t* m, int enable) {
+  HOS_REQUIRE(m, "hos_mlp_set_ipe_input: null handle");
+  HOS_REQUIRE(!enable || m->in_dim == 2 * kIpeDeg * kIpeB, "hos_mlp_set_ipe_input: the fused prologue produces %d features, MLP reads %d",
+              2 * kIpeDeg * kIpeB, m->in_dim);
+  m->ipe_perm = enable ? 1 : 0;
+  return HOS_OK;
+}
+
+int hos_mlp_forward_ipe(hos_mlp_t* m, const float* tdist, const float* rays_o, const float* rays_d,
+                        const float* radii, const float* basis_host, int N, int S, const float* rowbias,
+                        int rowbias_div, float* out0, float* out1, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && tdist && rays_o && rays_d && radii && basis_host && N >= 0 && S >= 1, "hos_mlp_forward_ipe: bad arguments");
+  HOS_REQUIRE(m->ipe_perm, "hos_mlp_forward_ipe: call hos_mlp_set_ipe_input(mlp, 1) before uploading the weights");
+  IpeArgs ipe;
+  ipe.tdist = tdist;
+  ipe.rays_o = rays_o;
+  ipe.rays_d = rays_d;
+  ipe.radii = radii;
+  ipe.S = S;
+  for (int i = 0; i < 3 * kIpeB; ++i) ipe.basis[i] = basis_host[i];
+  return mlp_launch(m, nullptr, &ipe, (int64_t)N * S, rowbias, rowbias_div, nullptr, out0, out1, stream);
 }
 
 int hos_pack_rows_f16(const float* X, int64_t rows, int ld, int K, void* dst_tiled, void* stream) {

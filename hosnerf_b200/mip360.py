@@ -20,6 +20,7 @@ Not in this round: autograd (the kernels are forward-only; ``training_step`` rai
 """
 from __future__ import annotations
 
+import ctypes
 import json
 import os
 from typing import Optional, Tuple
@@ -43,6 +44,9 @@ except Exception:  # pragma: no cover - gin is absent in the build image
 
 EPS = 1.1920929e-07
 _DEFAULT_PRECISION = "fp32"
+# fp16 mode: generate the IPE features inside the tcgen05 MLP kernel (False: materialise them in HBM
+# with hos_ipe_features first - kept for A/B measurements and as the accurate-sin/cos variant)
+FUSE_IPE = os.environ.get("HOSNERF_UNFUSED_IPE", "0") != "1"
 
 
 def set_precision(p: str):
@@ -193,6 +197,13 @@ class MipNeRF360MLP(nn.Module):
                                relu=1, rowbias=1, head=1))
             heads.append(dict(out_dim=self.num_rgb_channels, post=2, shift=float(self.rgb_padding), out_slot=1))
         mlp = ops.FusedMLP(F, layers, heads)
+        fuse = (FUSE_IPE and self.pos_basis_t.shape[1] == 21 and self.max_deg_point - self.min_deg_point == 12
+                and self.min_deg_point == 0)
+        if fuse:   # feature generation inside the MLP kernel: weights take the generation column order
+            mlp.set_ipe_input(True)
+            b = self.pos_basis_t.detach().float().cpu().contiguous().reshape(-1).tolist()
+            mlp.basis_host = (ctypes.c_float * len(b))(*b)
+        mlp.fused_ipe = fuse
         for i in range(self.netdepth):
             W, b, _ = f["layers"][i]
             mlp.set_layer(i, W, b)
@@ -214,12 +225,16 @@ class MipNeRF360MLP(nn.Module):
         basis = self.pos_basis_t
         if precision == "fp16":
             mlp = self._fused(st)
-            feat = ops.ipe_features(tdist, rays_o, rays_d, radii, basis, self.min_deg_point, self.max_deg_point, "tiled")
             rowbias = None
             if not self.disable_rgb:
                 de = ops.pos_enc(viewdirs, 0, self.deg_view, True)
                 rowbias = ops.linear_f32(de, f["views"][3], f["views"][1])        # per-ray view term + bias
-            dens, rgb = mlp.forward(feat, n * s, rowbias=rowbias, rowbias_div=s)
+            if mlp.fused_ipe:
+                dens, rgb = mlp.forward_ipe(tdist, rays_o, rays_d, radii, mlp.basis_host, rowbias=rowbias, rowbias_div=s)
+            else:
+                feat = ops.ipe_features(tdist, rays_o, rays_d, radii, basis, self.min_deg_point, self.max_deg_point,
+                                        "tiled")
+                dens, rgb = mlp.forward(feat, n * s, rowbias=rowbias, rowbias_div=s)
             density = dens.view(n, s)
             rgb = rgb.view(n, s, 3) if rgb is not None else torch.zeros(n, s, 3, device=tdist.device)
             return density, rgb

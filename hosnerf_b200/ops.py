@@ -198,6 +198,30 @@ class FusedMLP:
         assert tuple(w.shape) == (l["out_dim"], l["in_h"] + l["in_x"]), (i, w.shape, l)
         _lib.call("hos_mlp_set_layer", self._h, i, _p(w), _p(b), _stream())
 
+    def set_ipe_input(self, enable=True):
+        """Select the fused-IPE weight-column order; call before set_layer()."""
+        _lib.call("hos_mlp_set_ipe_input", self._h, int(enable))
+        self.ipe = bool(enable)
+
+    def forward_ipe(self, tdist, rays_o, rays_d, radii, basis_host, rowbias=None, rowbias_div=1):
+        """Fused prologue: ray intervals in, head outputs out (features never leave the SM)."""
+        for t, nm in ((tdist, "tdist"), (rays_o, "rays_o"), (rays_d, "rays_d"), (radii, "radii"), (rowbias, "rowbias")):
+            _chk(t, nm)
+        n, s = tdist.shape[0], tdist.shape[1] - 1
+        rows = n * s
+        outs = [None, None]
+        for h in self.heads:
+            outs[h["out_slot"]] = torch.empty(rows, h["out_dim"], device=tdist.device, dtype=_F32)
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.call("hos_mlp_forward_ipe", self._h, _p(tdist), _p(rays_o), _p(rays_d), _p(radii), basis_host, n, s,
+                  _p(rowbias), rowbias_div, _p(outs[0]), _p(outs[1]), _stream())
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((len(self.layers), rows, e0, e1))
+        return outs
+
     def set_bias(self, i, b):
         _chk(b, "b")
         assert b.numel() == self.layers[i]["out_dim"]

@@ -132,6 +132,29 @@ def test_mip360_c2_fp16_golden(golden):
     assert max_abs(hist[1]["sdist"].cpu(), g["L1_sdist"]) < 2e-3
 
 
+def test_fused_ipe_matches_materialised_features():
+    """fp16 mode, fused prologue (fast sin/cos/exp recurrences in the MLP kernel) vs the same MLP fed with
+    the accurately computed, HBM-materialised features: both round to fp16 operands."""
+    import hosnerf_b200.mip360 as M
+    b = {k: cu(v) for k, v in synth.make_bkg_batch(300, seed=11).items()}
+    outs = []
+    for fuse in (True, False):
+        M.FUSE_IPE = fuse
+        try:
+            net = _bkg(num_levels=2, num_prop_samples=128, num_nerf_samples=128, nerf_netwidth=256, precision="fp16")
+            with torch.no_grad():
+                rend, hist = net(b, 1.0, False, False, 0.1, 1e6)
+            assert net.mlps[0]._cache["f16"].fused_ipe == fuse
+            outs.append((rend, hist))
+        finally:
+            M.FUSE_IPE = True
+    (ra, ha), (rb, hb) = outs
+    print("fused vs materialised: L0 density rel", rel_err(ha[0]["density"].cpu(), hb[0]["density"].cpu()),
+          "final rgb abs", max_abs(ra[-1]["rgb"].cpu(), rb[-1]["rgb"].cpu()))
+    assert rel_err(ha[0]["density"].cpu(), hb[0]["density"].cpu()) < 2e-2
+    assert max_abs(ra[-1]["rgb"].cpu(), rb[-1]["rgb"].cpu()) < 1e-2
+
+
 def test_render_rays_surface(golden):
     g = golden("s1_forward_default")
     lit = LitMipNeRF360("/nonexistent", opaque_background=True, precision="fp32")
