@@ -37,7 +37,9 @@ constexpr int kMaxLayers = 12;
 constexpr int kMaxHeads = 4;
 constexpr int kStages = 3;       // weight ring depth
 constexpr int kStagesX = 3;      // input-feature ring depth
-constexpr int kMlpThreads = 320; // warp 0 producer, 1 MMA, 2-5 epilogue, 6-9 feature generators
+constexpr int kMlpThreads = 512; // warp 0 producer, 1 MMA, (2-3 idle), 4-11 epilogue, 12-15 feature generators
+constexpr int kEpiWarp0 = 4, kEpiWarps = 8, kFeatWarp0 = 12;
+constexpr int kJGroup = 7;       // basis directions per feature-generation group (3 groups of 7)
 constexpr int kTmemCols = 256;
 constexpr int kIpeB = 21;        // geodesic basis directions (icosahedron, 2 subdivisions)
 constexpr int kIpeDeg = 12;      // octaves 2^0 .. 2^11
@@ -177,18 +179,21 @@ struct MlpArgs {
 //   exp(-.5 4^l v): ex2.approx every 3rd octave, e_{l+1} = e_l^4 in between.
 // Per row and pass: ~210 MUFU + ~2.5 k FP instructions instead of 756 libm calls, and the features
 // never exist outside shared memory.
-struct IpeRowState {
-  float s[kIpeB], c[kIpeB], e[kIpeB], lv[kIpeB];
-  float mean[3];
+// Geometry of one sample, shared by the three j-group passes of a feature pass.
+struct IpeRowGeom {
+  float x[3], d[3];        // pre-contraction mean, ray direction
+  float a, bq, m, xd;      // contraction: z = a x, J = a I + bq x x^T ; m = |x|^2 ; xd = x.d
+  float t_var, r_var, inv_dsq;
 };
 
-__device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, bool row_ok, IpeRowState& st) {
-  float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 1.f}, t0 = 1.f, t1 = 2.f, radius = 0.f;
+__device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, bool row_ok, IpeRowGeom& G) {
+  float o[3] = {0.f, 0.f, 0.f}, t0 = 1.f, t1 = 2.f, radius = 0.f;
+  G.d[0] = 0.f; G.d[1] = 0.f; G.d[2] = 1.f;
   if (row_ok) {
     const int64_t ray = row / A.S;
     const int smp = (int)(row % A.S);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { o[i] = A.rays_o[ray * 3 + i]; d[i] = A.rays_d[ray * 3 + i]; }
+    for (int i = 0; i < 3; ++i) { o[i] = A.rays_o[ray * 3 + i]; G.d[i] = A.rays_d[ray * 3 + i]; }
     t0 = A.tdist[ray * (A.S + 1) + smp];
     t1 = A.tdist[ray * (A.S + 1) + smp + 1];
     radius = A.radii[ray];
@@ -199,40 +204,28 @@ __device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, boo
   const float denom = fmaxf(3.f * mu2 + hw2, 1.1920929e-07f);
   const float inv_den = 1.f / denom;
   const float t_mean = mu + 2.f * mu * hw2 * inv_den;
-  const float t_var = hw2 * (1.f / 3.f) - (4.f / 15.f) * hw4 * (12.f * mu2 - hw2) * inv_den * inv_den;
-  const float r_var = (mu2 * 0.25f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 * inv_den) * radius * radius;
-  const float dsq = fmaxf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2], 1e-10f);
-  const float inv_dsq = 1.f / dsq;
-  float x[3];
+  G.t_var = hw2 * (1.f / 3.f) - (4.f / 15.f) * hw4 * (12.f * mu2 - hw2) * inv_den * inv_den;
+  G.r_var = (mu2 * 0.25f + (5.f / 12.f) * hw2 - (4.f / 15.f) * hw4 * inv_den) * radius * radius;
+  const float dsq = fmaxf(G.d[0] * G.d[0] + G.d[1] * G.d[1] + G.d[2] * G.d[2], 1e-10f);
+  G.inv_dsq = 1.f / dsq;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) x[i] = fmaf(d[i], t_mean, o[i]);
-  // contraction (helper.py:26-60): z = a x, J = a I + b x x^T (identity inside the unit ball)
-  const float m = fmaxf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2], 1e-32f);
-  float a = 1.f, bq = 0.f;
-  if (m > 1.f) {
-    const float r = sqrtf(m), inv_m = 1.f / m;
-    a = (2.f * r - 1.f) * inv_m;
-    bq = 2.f * (1.f - r) * inv_m * inv_m;
+  for (int i = 0; i < 3; ++i) G.x[i] = fmaf(G.d[i], t_mean, o[i]);
+  // contraction (helper.py:26-60): z = a x, J = a I + bq x x^T (identity inside the unit ball)
+  G.m = fmaxf(G.x[0] * G.x[0] + G.x[1] * G.x[1] + G.x[2] * G.x[2], 1e-32f);
+  G.a = 1.f;
+  G.bq = 0.f;
+  if (G.m > 1.f) {
+    const float r = sqrtf(G.m), inv_m = 1.f / G.m;
+    G.a = (2.f * r - 1.f) * inv_m;
+    G.bq = 2.f * (1.f - r) * inv_m * inv_m;
   }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) st.mean[i] = a * x[i];
-  const float xd = x[0] * d[0] + x[1] * d[1] + x[2] * d[2];
-  // lifted variance b_j^T J cov J^T b_j with cov = t_var d d^T + r_var (I - d d^T / |d|^2):
-  //   v = J b_j = a b_j + bq (x.b_j) x ;  var = t_var (d.v)^2 + r_var (|v|^2 - (d.v)^2 / |d|^2)
-#pragma unroll
-  for (int j = 0; j < kIpeB; ++j) {
-    const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
-    const float xb = x[0] * b0 + x[1] * b1 + x[2] * b2;
-    const float db = d[0] * b0 + d[1] * b1 + d[2] * b2;
-    const float k = bq * xb;
-    const float dv = fmaf(k, xd, a * db);
-    const float vv = a * a + k * (2.f * a * xb + k * m);        // |b_j| = 1
-    st.lv[j] = fmaxf(fmaf(t_var, dv * dv, r_var * (vv - dv * dv * inv_dsq)), 0.f);
-  }
+  G.xd = G.x[0] * G.d[0] + G.x[1] * G.d[1] + G.x[2] * G.d[2];
 }
 
-// Produce the kb_x feature chunks of one pass for row r into the X ring.
-__device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, IpeRowState& st, int r, unsigned char* sRingX,
+// Produce the 8 feature chunks of one pass for row r into the X ring.  Kernel column order:
+//   col = jg*168 + l*14 + jj*2 + {0: sin, 1: cos},  j = jg*7 + jj   (3 groups of 7 directions)
+// so that a thread only carries 7 directions of recurrence state at a time.
+__device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRowGeom& G, int r, unsigned char* sRingX,
                                                   uint64_t* bar_xfull, uint64_t* bar_xempty, uint32_t& xi) {
   constexpr float kInv2Pi = 0.15915494309189535f;
   constexpr float k2PiHi = 6.2831854820251465f;           // fl32(2 pi)
@@ -241,46 +234,63 @@ __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, IpeRowState&
   uint32_t pk[4];
   unsigned char* slot = nullptr;
 #pragma unroll
-  for (int l = 0; l < kIpeDeg; ++l) {
+  for (int jg = 0; jg < kIpeB / kJGroup; ++jg) {
+    float s[kJGroup], c[kJGroup], e[kJGroup], lv[kJGroup], lm[kJGroup];
+    // lifted mean  m_j = z.b_j  and variance  b_j^T J cov J^T b_j  with cov = t_var d d^T + r_var (I - d d^T/|d|^2):
+    //   v = J b_j = a b_j + bq (x.b_j) x ;  var = t_var (d.v)^2 + r_var (|v|^2 - (d.v)^2 / |d|^2)
 #pragma unroll
-    for (int j = 0; j < kIpeB; ++j) {
-      const int p = l * kIpeB + j;                // pair index; columns 2p, 2p+1
-      if ((p & 31) == 0) {                        // first pair of a 64-column chunk: acquire a slot
-        const int xs = xi % kStagesX;
-        mbar_wait(&bar_xempty[xs], ((xi / kStagesX) & 1) ^ 1);
-        slot = sRingX + xs * kXChunkBytes;
-      }
-      // ---- sin/cos of 2^l m_j
-      if ((l & 3) == 0) {
-        const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
-        const float arg = (st.mean[0] * b0 + st.mean[1] * b1 + st.mean[2] * b2) * (float)(1 << l);
-        const float kq = rintf(arg * kInv2Pi);
-        float xr = fmaf(-kq, k2PiHi, arg);
-        xr = fmaf(-kq, k2PiLo, xr);
-        st.s[j] = __sinf(xr);
-        st.c[j] = __cosf(xr);
-      } else {
-        const float s2 = st.s[j] * st.c[j];
-        st.c[j] = fmaf(-2.f * st.s[j], st.s[j], 1.f);
-        st.s[j] = s2 + s2;
-      }
-      // ---- exp(-0.5 * 4^l * var_j)
-      if ((l % 3) == 0) {
-        st.e[j] = exp2f(-kHalfLog2e * (float)(1 << (2 * l)) * st.lv[j]);
-      } else {
-        const float e2 = st.e[j] * st.e[j];
-        st.e[j] = e2 * e2;
-      }
-      __half2 h = __floats2half2_rn(st.e[j] * st.s[j], st.e[j] * st.c[j]);
-      pk[p & 3] = *reinterpret_cast<uint32_t*>(&h);
-      if ((p & 3) == 3) {
-        const int g = (p & 31) >> 2;              // 16-byte group inside the chunk row
-        *reinterpret_cast<uint4*>(slot + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
-      if ((p & 31) == 31) {                       // chunk complete
-        fence_proxy_async();
-        mbar_arrive(&bar_xfull[xi % kStagesX]);
-        ++xi;
+    for (int jj = 0; jj < kJGroup; ++jj) {
+      const int j = jg * kJGroup + jj;
+      const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
+      const float xb = G.x[0] * b0 + G.x[1] * b1 + G.x[2] * b2;
+      const float db = G.d[0] * b0 + G.d[1] * b1 + G.d[2] * b2;
+      const float k = G.bq * xb;
+      const float dv = fmaf(k, G.xd, G.a * db);
+      const float vv = G.a * G.a + k * (2.f * G.a * xb + k * G.m);        // |b_j| = 1
+      lv[jj] = fmaxf(fmaf(G.t_var, dv * dv, G.r_var * (vv - dv * dv * G.inv_dsq)), 0.f);
+      lm[jj] = G.a * xb;
+    }
+#pragma unroll
+    for (int l = 0; l < kIpeDeg; ++l) {
+#pragma unroll
+      for (int jj = 0; jj < kJGroup; ++jj) {
+        const int p = (jg * kIpeDeg + l) * kJGroup + jj;   // pair index; columns 2p, 2p+1
+        if ((p & 31) == 0) {                               // first pair of a 64-column chunk: acquire a slot
+          const int xs = xi % kStagesX;
+          mbar_wait(&bar_xempty[xs], ((xi / kStagesX) & 1) ^ 1);
+          slot = sRingX + xs * kXChunkBytes;
+        }
+        // ---- sin/cos of 2^l m_j: angle doubling, re-seeded every 4 octaves
+        if ((l & 3) == 0) {
+          const float arg = lm[jj] * (float)(1 << l);
+          const float kq = rintf(arg * kInv2Pi);
+          float xr = fmaf(-kq, k2PiHi, arg);
+          xr = fmaf(-kq, k2PiLo, xr);
+          s[jj] = __sinf(xr);
+          c[jj] = __cosf(xr);
+        } else {
+          const float s2 = s[jj] * c[jj];
+          c[jj] = fmaf(-2.f * s[jj], s[jj], 1.f);
+          s[jj] = s2 + s2;
+        }
+        // ---- exp(-0.5 * 4^l * var_j): ex2 every 3rd octave, fourth powers in between
+        if ((l % 3) == 0) {
+          e[jj] = exp2f(-kHalfLog2e * (float)(1 << (2 * l)) * lv[jj]);
+        } else {
+          const float e2 = e[jj] * e[jj];
+          e[jj] = e2 * e2;
+        }
+        __half2 h = __floats2half2_rn(e[jj] * s[jj], e[jj] * c[jj]);
+        pk[p & 3] = *reinterpret_cast<uint32_t*>(&h);
+        if ((p & 3) == 3) {
+          const int g = (p & 31) >> 2;              // 16-byte group inside the chunk row
+          *reinterpret_cast<uint4*>(slot + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        if ((p & 31) == 31) {                       // chunk complete
+          fence_proxy_async();
+          mbar_arrive(&bar_xfull[xi % kStagesX]);
+          ++xi;
+        }
       }
     }
   }
@@ -310,6 +320,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
   uint64_t* bar_tmem_full = bar_xempty + kStagesX;
   uint64_t* bar_act = bar_tmem_full + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_act + 1);
+  float* s_headx = reinterpret_cast<float*>(s_tmem + 4);     // [128][4] partial head sums of the upper column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool fused = args.fused_ipe != 0;
@@ -319,7 +330,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
     for (int s = 0; s < kStages; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wempty[s], 1); }
     for (int s = 0; s < kStagesX; ++s) { mbar_init(&bar_xfull[s], fused ? 128 : 1); mbar_init(&bar_xempty[s], 1); }
     mbar_init(bar_tmem_full, 1);
-    mbar_init(bar_act, 128);
+    mbar_init(bar_act, kEpiWarps * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -393,9 +404,10 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
         }
       }
     }
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    // ===================== epilogue (8 warps): 2 warps per TMEM lane quarter, half the columns each ============
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access (warp id % 4)
+    const int ch = (warp - kEpiWarp0) >> 2;     // which half of the layer's columns
     const int r = q * 32 + lane;                // row within the tile
     uint32_t li = 0;
     for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
@@ -404,30 +416,50 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
       for (int l = 0; l < prog.n_layers; ++l, ++li) {
         const LayerDev L = prog.layers[l];
         const bool last = (l == prog.n_layers - 1);
+        const bool has_head = L.head >= 0;
+        const HeadDev Hd = prog.heads[has_head ? L.head : 0];
+        const float* rb = (L.rowbias && args.rowbias && row_ok) ? args.rowbias + (row / args.rowbias_div) * L.n : nullptr;
+        const int nh = L.n >> 1;
+        const int cbeg = ch * nh, cend = cbeg + nh;
+        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         mbar_wait(bar_tmem_full, li & 1);
         tc_fence_after();
-        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-        const HeadDev Hd = prog.heads[L.head >= 0 ? L.head : 0];
-        const float* rb = nullptr;
-        if (L.rowbias && args.rowbias && row_ok) rb = args.rowbias + (row / args.rowbias_div) * L.n;
-        for (int c0 = 0; c0 < L.n; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
           float f[32];
+          const float4* b4 = reinterpret_cast<const float4*>(sParams + L.bias_off + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + sParams[L.bias_off + c0 + j];
-            if (rb) x += __ldg(rb + c0 + j);
-            f[j] = L.relu ? fmaxf(x, 0.f) : x;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
           }
-          if (L.head >= 0) {
+          if (rb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(rb + c0) + j);
+              f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+            }
+          }
+          if (L.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (has_head) {
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
               if (n < Hd.hn) {
-                const float* w = sParams + Hd.w_off + n * L.n + c0;
+                const float4* w4 = reinterpret_cast<const float4*>(sParams + Hd.w_off + n * L.n + c0);
                 float a = hacc[n];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a = fmaf(f[j], w[j], a);
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w = w4[j];
+                  a = fmaf(f[4 * j + 0], w.x, a); a = fmaf(f[4 * j + 1], w.y, a);
+                  a = fmaf(f[4 * j + 2], w.z, a); a = fmaf(f[4 * j + 3], w.w, a);
+                }
                 hacc[n] = a;
               }
             }
@@ -450,41 +482,48 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
             }
           }
         }
-        if (L.head >= 0 && row_ok) {
-          float* o = args.out[Hd.slot] + row * Hd.hn;
+        if (has_head) {                         // combine the two column halves, then post-process
+          if (ch == 1) *reinterpret_cast<float4*>(s_headx + r * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          if (ch == 0 && row_ok) {
+            const float4 o4 = *reinterpret_cast<const float4*>(s_headx + r * 4);
+            hacc[0] += o4.x; hacc[1] += o4.y; hacc[2] += o4.z; hacc[3] += o4.w;
+            float* o = args.out[Hd.slot] + row * Hd.hn;
 #pragma unroll
-          for (int n = 0; n < 4; ++n) {
-            if (n >= Hd.hn) break;
-            float x = hacc[n] + sParams[Hd.b_off + n];
-            if (Hd.post == 1) {
-              float z = x + Hd.shift;
-              x = z > 20.f ? z : log1pf(expf(z));
-            } else if (Hd.post == 2) {
-              x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * Hd.shift) - Hd.shift;
-            } else if (Hd.post == 3) {
-              x = args.add[row * Hd.hn + n] + x;
-            } else if (Hd.post == 4) {
-              x = (n < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+            for (int n = 0; n < 4; ++n) {
+              if (n >= Hd.hn) break;
+              float x = hacc[n] + sParams[Hd.b_off + n];
+              if (Hd.post == 1) {
+                float z = x + Hd.shift;
+                x = z > 20.f ? z : log1pf(expf(z));
+              } else if (Hd.post == 2) {
+                x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * Hd.shift) - Hd.shift;
+              } else if (Hd.post == 3) {
+                x = args.add[row * Hd.hn + n] + x;
+              } else if (Hd.post == 4) {
+                x = (n < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+              }
+              o[n] = x;
             }
-            o[n] = x;
           }
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // s_headx may be reused by the next head
         }
         fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
         tc_fence_before();          // TMEM loads ordered before the arrive
         mbar_arrive(bar_act);
       }
     }
-  } else if (fused) {
-    // ===================== feature generators (warps 6..9): fused IPE prologue =====================
-    const int r = (warp - 6) * 32 + lane;
+  } else if (fused && warp >= kFeatWarp0) {
+    // ===================== feature generators (warps 12..15): fused IPE prologue =====================
+    const int r = (warp - kFeatWarp0) * 32 + lane;
     uint32_t xi = 0;
-    IpeRowState st;
     for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
       const int64_t row = (int64_t)tile * kTileM + r;
+      IpeRowGeom G;
+      ipe_row_setup(ipe, row, row < args.rows, G);
       for (int l = 0; l < prog.n_layers; ++l) {
         if (prog.layers[l].kb_x == 0) continue;
-        ipe_row_setup(ipe, row, row < args.rows, st);
-        ipe_generate_pass(ipe, st, r, sRingX, bar_xfull, bar_xempty, xi);
+        ipe_generate_pass(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi);
       }
     }
   }
@@ -500,7 +539,8 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
 // W fp32 [N, in_h + in_x] (nn.Linear layout, columns ordered [x|h] if x_first else [h|x])
 // -> fp16 chunks in kernel K order: kb_h chunks of h columns, then kb_x chunks of x columns.
 // ipe_perm != 0: the x columns are re-ordered from the reference's IPE layout
-// f = half*252 + l*21 + j  to the kernel's generation order  col = (l*21 + j)*2 + half.
+// f = half*252 + l*21 + j  to the kernel's generation order
+// col = jg*168 + l*14 + jj*2 + half  with j = jg*7 + jj.
 __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h, int in_x, int x_first, int kb_h,
                                    int kb_x, int ipe_perm, unsigned char* __restrict__ dst) {
   const int nkb = kb_h + kb_x;
@@ -517,7 +557,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h,
   } else {
     int c = (kb - kb_h) * kKB + kk;
     if (c < in_x) {
-      if (ipe_perm) c = (c & 1) * (kIpeDeg * kIpeB) + (c >> 1);
+      if (ipe_perm) {
+        const int half = c & 1, pr = c >> 1;
+        const int jg = pr / (kIpeDeg * kJGroup), l = (pr / kJGroup) % kIpeDeg, jj = pr % kJGroup;
+        c = half * (kIpeDeg * kIpeB) + l * kIpeB + jg * kJGroup + jj;
+      }
       v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
     }
   }
@@ -592,7 +636,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
     D.rowbias = (uint8_t)(L.rowbias != 0);
     D.head = (int8_t)L.head;
     D.w_off = woff;
-    D.bias_off = poff;
+    D.bias_off = poff;                      // multiples of 16 floats: the epilogue reads float4
     woff += (uint32_t)(D.kb_h + D.kb_x) * D.n * 128u;
     poff += D.n;
     if (l < n_layers - 1 && L.out_dim > width) width = L.out_dim;
@@ -612,7 +656,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
     H.post = (uint8_t)heads[h].post;
     H.shift = heads[h].shift;
     H.slot = (uint8_t)heads[h].out_slot;
-    H.w_off = poff;
+    H.w_off = poff;                         // [hn][n], n % 16 == 0 keeps every row float4-aligned
     poff += (uint32_t)H.hn * layers[owner].out_dim;
     H.b_off = poff;
     poff += 4;
@@ -624,7 +668,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   m->w_bytes = woff;
   m->smem_bytes = 1024 + (size_t)P.kbh * kXChunkBytes + (size_t)kStages * nmax * 128 +
                   (size_t)kStagesX * kXChunkBytes + (((size_t)poff + 3) & ~(size_t)3) * 4 +
-                  (2 * kStages + 2 * kStagesX + 2) * 8 + 16;
+                  (2 * kStages + 2 * kStagesX + 2) * 8 + 16 + kTileM * 4 * sizeof(float);
   if (m->smem_bytes > 227 * 1024) {
     hos::set_error("hos_mlp_create: needs %zu B shared memory (> 227 KB)", m->smem_bytes);
     delete m;
