@@ -54,6 +54,7 @@ SIGNATURES = {
     "hos_mlp_forward": (c_i, [C.c_void_p, c_f, c_l, c_f, c_i, c_f, c_f, c_f, c_f]),
     "hos_mlp_set_ipe_input": (c_i, [C.c_void_p, c_i]),
     "hos_mlp_forward_ipe": (c_i, [C.c_void_p, c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_f, c_i, c_f, c_f, c_f]),
+    "hos_mlp_debug_timeline": (c_i, [c_f]),
     "hos_pack_rows_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f]),
     "hos_composite_mip360": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),

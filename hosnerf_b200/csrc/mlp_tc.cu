@@ -167,6 +167,7 @@ struct MlpArgs {
   int ntiles;
   int rowbias_div;
   int fused_ipe;
+  long long* timeline;            // optional debug: per (tile iteration, layer) 4 clock64() stamps of CTA 0
 };
 
 // ----------------------------------------------------------------------------- fused IPE prologue
@@ -380,6 +381,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
           mbar_wait(bar_act, (li - 1) & 1);
           tc_fence_after();
         }
+        if (args.timeline && blockIdx.x == 0 && lane == 0 && li < 64) args.timeline[li * 4 + 0] = clock64();
         const int nkb = L.kb_h + L.kb_x;
         for (int kb = 0; kb < nkb; ++kb, ++wi) {
           const int ws = wi % kStages;
@@ -402,6 +404,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
           __syncwarp();
           if (from_x) ++xi;
         }
+        if (args.timeline && blockIdx.x == 0 && lane == 0 && li < 64) args.timeline[li * 4 + 1] = clock64();
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
@@ -424,6 +427,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         mbar_wait(bar_tmem_full, li & 1);
         tc_fence_after();
+        if (args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && li < 64) args.timeline[li * 4 + 2] = clock64();
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -511,6 +515,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
         fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
         tc_fence_before();          // TMEM loads ordered before the arrive
         mbar_arrive(bar_act);
+        if (args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && li < 64) args.timeline[li * 4 + 3] = clock64();
       }
     }
   } else if (fused && warp >= kFeatWarp0) {
@@ -726,6 +731,8 @@ int hos_mlp_set_head(hos_mlp_t* m, int head, const float* W, const float* b, voi
 
 int hos_mlp_in_kblocks(const hos_mlp_t* m) { return m ? m->prog.kbx : 0; }
 
+static long long* g_timeline = nullptr;     // debug hook, see hos_mlp_debug_timeline
+
 static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int64_t rows, const float* rowbias,
                       int rowbias_div, const float* add, float* out0, float* out1, void* stream) {
   for (int l = 0; l < m->prog.n_layers; ++l)
@@ -747,6 +754,7 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   a.ntiles = (int)((rows + kTileM - 1) / kTileM);
   a.rowbias_div = rowbias_div < 1 ? 1 : rowbias_div;
   a.fused_ipe = ipe != nullptr;
+  a.timeline = g_timeline;
   static const IpeArgs kNoIpe = {};
   int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
   mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
@@ -760,6 +768,11 @@ int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float
   HOS_REQUIRE(m && x_tiled && rows >= 0, "hos_mlp_forward: bad handle/input");
   HOS_REQUIRE(!m->ipe_perm, "hos_mlp_forward: this MLP was created for the fused IPE prologue (use hos_mlp_forward_ipe)");
   return mlp_launch(m, x_tiled, nullptr, rows, rowbias, rowbias_div, add, out0, out1, stream);
+}
+
+int hos_mlp_debug_timeline(long long* device_buf_256) {
+  g_timeline = device_buf_256;
+  return HOS_OK;
 }
 
 int hos_mlp_set_ipe_input(hos_mlp_t* m, int enable) {
