@@ -39,6 +39,15 @@ FLOP_NERF = 2 * 851968
 WORKLOAD = "C2: stage-1 bkg render_rays, 4096 rays x (128 prop + 128 nerf) samples, PropMLP 4x256 + NeRFMLP 8x256"
 
 
+def ncu_traffic():
+    """DRAM bytes of the dominant kernel (both MLP launches of a step) from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "r1_mlp_ncu.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -227,7 +236,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel (tcgen05 fused MLP, 2 launches/step)",
                          "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-                         "peak_source": f"{src} bf16_tflops (burst)", "traffic": None,
+                         "peak_source": f"{src} bf16_tflops (burst)", "traffic": ncu_traffic(),
+                         "traffic_note": "DRAM read+write bytes of the two MLP launches of one step, ncu --set full (profiles/r1_mlp_ncu.json)",
                          "kernel_share_of_step": mlp_ms / dev_ms if dev_ms > 0 else None,
                          "flop_per_launch": [N_RAYS * S_PROP * FLOP_PROP, N_RAYS * S_NERF * FLOP_NERF]},
             "clocks": sampler.summary(),

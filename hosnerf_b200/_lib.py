@@ -42,6 +42,7 @@ SIGNATURES = {
     "hos_pos_enc": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
     "hos_fourier_embed": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f, c_i, c_i, c_f]),
     "hos_lbs_warp": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f]),
+    "hos_lbs_forward": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f]),
     "hos_linear_f32": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_f, c_i, c_f]),
     "hos_linear_f32_ex": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_f, c_i, c_f]),
     "hos_head_f32": (c_i, [c_f, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_fl, c_f, c_f, c_i, c_f]),
@@ -102,3 +103,4 @@ def call_unless_empty(n, name: str, *args):
     """torch gives empty tensors a NULL data pointer; an empty batch is a no-op by contract."""
     if n != 0:
         call(name, *args)
+    # (LAUNCHES is only incremented by real launches)

@@ -84,9 +84,63 @@ lbs_warp_kernel(const float* __restrict__ pts, const float* __restrict__ R, cons
   }
 }
 
+// Forward warp of the cycle / flow side paths, S3 network.py:357-398: all bone channels are
+// sampled at ONE position (the canonical point), x_deform = sum_i w_i (Rf_i p + Tf_i) / max(sum w, 1e-4).
+__global__ void __launch_bounds__(256)
+lbs_forward_kernel(const float* __restrict__ pts, const float* __restrict__ R, const float* __restrict__ T,
+                   const float* __restrict__ vol, LbsParams prm, int64_t P, int bones, int G,
+                   float* __restrict__ x_deform, float* __restrict__ mask) {
+  __shared__ float sR[kMaxBones * 9];
+  __shared__ float sT[kMaxBones * 3];
+  for (int i = threadIdx.x; i < bones * 9; i += blockDim.x) sR[i] = R[i];
+  for (int i = threadIdx.x; i < bones * 3; i += blockDim.x) sT[i] = T[i];
+  __syncthreads();
+  const size_t vstride = (size_t)G * G * G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+    float px = pts[i * 3 + 0], py = pts[i * 3 + 1], pz = pts[i * 3 + 2];
+    float gx = (px - prm.bbox_min[0]) * prm.bbox_scale[0] - 1.0f;
+    float gy = (py - prm.bbox_min[1]) * prm.bbox_scale[1] - 1.0f;
+    float gz = (pz - prm.bbox_min[2]) * prm.bbox_scale[2] - 1.0f;
+    float ax = 0.f, ay = 0.f, az = 0.f, wsum = 0.f;
+    for (int b = 0; b < bones; ++b) {
+      const float* r = sR + b * 9;
+      float w = trilinear_zeros(vol + b * vstride, G, gx, gy, gz);
+      float qx = fmaf(r[2], pz, fmaf(r[1], py, r[0] * px)) + sT[b * 3 + 0];
+      float qy = fmaf(r[5], pz, fmaf(r[4], py, r[3] * px)) + sT[b * 3 + 1];
+      float qz = fmaf(r[8], pz, fmaf(r[7], py, r[6] * px)) + sT[b * 3 + 2];
+      wsum += w;
+      ax += w * qx;
+      ay += w * qy;
+      az += w * qz;
+    }
+    float den = fmaxf(wsum, 0.0001f);
+    x_deform[i * 3 + 0] = ax / den;
+    x_deform[i * 3 + 1] = ay / den;
+    x_deform[i * 3 + 2] = az / den;
+    if (mask) mask[i] = wsum;
+  }
+}
+
 }  // namespace hos
 
 using namespace hos;
+
+extern "C" int hos_lbs_forward(const float* cnl_pts, const float* R_fwd, const float* T_fwd, const float* vol,
+                               const float* bbox_min_host, const float* bbox_scale_host, int64_t P,
+                               int bones, int G, float* x_deform, float* mask, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(cnl_pts && R_fwd && T_fwd && vol && bbox_min_host && bbox_scale_host && x_deform, "hos_lbs_forward: null pointer");
+  HOS_REQUIRE(P >= 0 && bones >= 1 && bones <= kMaxBones && G >= 2, "hos_lbs_forward: bad shape (bones=%d G=%d)", bones, G);
+  if (P == 0) return HOS_OK;
+  LbsParams prm;
+  for (int i = 0; i < 3; ++i) { prm.bbox_min[i] = bbox_min_host[i]; prm.bbox_scale[i] = bbox_scale_host[i]; }
+  int64_t blocks = (P + 255) / 256;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  lbs_forward_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(cnl_pts, R_fwd, T_fwd, vol, prm, P, bones, G, x_deform, mask);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}
 
 extern "C" int hos_lbs_warp(const float* pts, const float* R, const float* T, const float* vol,
                             const float* bbox_min_host, const float* bbox_scale_host, int64_t P,

@@ -80,7 +80,7 @@ __device__ void bitonic_sort(float* a, int n2) {
 // max_dilate_weights on one ray.  in: t[M+1], w[M] (global).  out (smem): sm.knots[0..3M]
 // sorted+clipped, sm.wts[0..3M) renormalised.  S1 helper.py:130-143,152-164.
 __device__ void dilate_ray(SamplerSmem& sm, const float* __restrict__ t, const float* __restrict__ w,
-                           int M, float dilation, float lo, float hi) {
+                           int M, float dilation, float lo, float hi, bool sorted_input) {
   const int K = 3 * M + 1;
   int n2 = 1;
   while (n2 < K) n2 <<= 1;
@@ -104,9 +104,21 @@ __device__ void dilate_ray(SamplerSmem& sm, const float* __restrict__ t, const f
   for (int k = threadIdx.x; k < K - 1; k += blockDim.x) {
     float x = sm.knots[k];
     float pm = 0.f;                                  // where(mask, p, 0).max()
-    for (int j = 0; j < M; ++j) {
-      bool in = (sm.t0[j] <= x) && (sm.t1[j] > x);
-      pm = fmaxf(pm, in ? sm.pdf[j] : 0.f);
+    if (sorted_input) {
+      // t ascending => t0, t1 ascending => {j : t0[j] <= x < t1[j]} is the contiguous range
+      // [#{t1 <= x}, #{t0 <= x}): two binary searches and a walk over the handful of overlapping
+      // intervals instead of a scan over all M (same set, same max - still bit-exact).
+      int a = 0, b = M;
+      while (a < b) { int m = (a + b) >> 1; if (sm.t1[m] <= x) a = m + 1; else b = m; }
+      const int lo_j = a;
+      a = 0; b = M;
+      while (a < b) { int m = (a + b) >> 1; if (sm.t0[m] <= x) a = m + 1; else b = m; }
+      for (int j = lo_j; j < a; ++j) pm = fmaxf(pm, sm.pdf[j]);
+    } else {
+      for (int j = 0; j < M; ++j) {
+        bool in = (sm.t0[j] <= x) && (sm.t1[j] > x);
+        pm = fmaxf(pm, in ? sm.pdf[j] : 0.f);
+      }
     }
     float wd = pm * (sm.knots[k + 1] - x);           // pdf_to_weight
     sm.wts[k] = wd;
@@ -196,7 +208,7 @@ max_dilate_kernel(const float* __restrict__ t, const float* __restrict__ w, int 
                   float lo, float hi, float* __restrict__ t_out, float* __restrict__ w_out) {
   __shared__ SamplerSmem sm;
   const int ray = blockIdx.x;
-  dilate_ray(sm, t + (size_t)ray * (M + 1), w + (size_t)ray * M, M, dilation, lo, hi);
+  dilate_ray(sm, t + (size_t)ray * (M + 1), w + (size_t)ray * M, M, dilation, lo, hi, false);   // arbitrary t
   const int K = 3 * M + 1;
   for (int i = threadIdx.x; i < K; i += blockDim.x) t_out[(size_t)ray * K + i] = sm.knots[i];
   for (int i = threadIdx.x; i < K - 1; i += blockDim.x) w_out[(size_t)ray * (K - 1) + i] = sm.wts[i];
@@ -233,7 +245,12 @@ resample_level_kernel(const float* __restrict__ sdist, const float* __restrict__
   const float* w = weights + (size_t)ray * M_in;
   int off, M;
   if (dilate) {
-    dilate_ray(sm, t, w, M_in, dilation, lo, hi);
+    // sdist comes from the previous level's sample_intervals: ascending by construction; a ray that
+    // is not (NaNs, foreign input) falls back to the exhaustive scan
+    bool asc = true;
+    for (int j = threadIdx.x; j < M_in; j += blockDim.x) asc = asc && (t[j] <= t[j + 1]);
+    asc = __syncthreads_and(asc);
+    dilate_ray(sm, t, w, M_in, dilation, lo, hi, asc);
     off = 1;                 // sdist[..., 1:-1], weights[..., 1:-1]   (model.py:381-382)
     M = 3 * M_in - 2;
     // logits overwrite the trimmed weights in place: wts[j] <- f(wts[j+1])

@@ -533,13 +533,19 @@ class Network(nn.Module):
                 else:
                     ret.update(human_rgb=raw[..., :3], human_density=raw[..., 3], newsmpl_pts=pts,
                                pts_mask=mask, z_vals=z, rays_d=rays_d[c0:c1])
-                # cycle-consistency side path (network.py:505-536): forward warp of the masked points
+                # cycle-consistency side path (network.py:505-536): forward warp of the points the motion
+                # field considers foreground.  The reference evaluates it in eval too (its outputs are only
+                # read by the training loss); here it runs when asked for (default: training calls).
+                ret["deform_pts_final"] = pts[0, 0, :][None, :]
+                ret["observe_pts"] = pts[0, 0, :][None, :]
                 if kwargs.get("cycle_outputs", is_train):
                     sel = mask.reshape(-1) > 0.005
                     if bool(sel.any()):
-                        raise NotImplementedError("hosnerf_b200: forward LBS (cycle path) is not built yet")
-                ret["deform_pts_final"] = pts[0, 0, :][None, :]
-                ret["observe_pts"] = pts[0, 0, :][None, :]
+                        observe = pts.reshape(-1, 3)[sel].contiguous()
+                        xd, _ = ops.lbs_forward(cnl.reshape(-1, 3)[sel].contiguous(), Rf[0], Tf[0], vol, bbox_min, bbox_scale)
+                        if not cfg.ignore_non_rigid_motions:
+                            xd = self._eval_non_rigid("nrf", self.non_rigid_forward_mlp, xd, cond, hann_w, precision)
+                        ret["deform_pts_final"], ret["observe_pts"] = xd, observe
                 for k, v in ret.items():
                     outs.setdefault(k, []).append(v)
             all_ret = {k: torch.cat(v, 0) for k, v in outs.items()}

@@ -47,7 +47,7 @@ def max_dilate(t, w, dilation, lo, hi):
     n, s = w.shape
     t_out = torch.empty(n, 3 * s + 1, device=t.device, dtype=_F32)
     w_out = torch.empty(n, 3 * s, device=t.device, dtype=_F32)
-    _lib.call("hos_max_dilate", _p(t), _p(w), n, s, dilation, lo, hi, _p(t_out), _p(w_out), _stream())
+    _lib.call_unless_empty(n, "hos_max_dilate", _p(t), _p(w), n, s, dilation, lo, hi, _p(t_out), _p(w_out), _stream())
     return t_out, w_out
 
 
@@ -59,7 +59,7 @@ def sample_intervals(t, logits, u_base, jitter, max_jitter, lo, hi, want_aux=Fal
     centers = torch.empty(n, s, device=t.device, dtype=_F32) if want_aux else None
     idx = torch.empty(n, s, device=t.device, dtype=torch.int32) if want_aux else None
     jc = 0 if jitter is None else jitter.shape[-1]
-    _lib.call("hos_sample_intervals", _p(t), _p(logits), _p(u_base), _p(jitter), jc, max_jitter, n, m, s,
+    _lib.call_unless_empty(n, "hos_sample_intervals", _p(t), _p(logits), _p(u_base), _p(jitter), jc, max_jitter, n, m, s,
               lo, hi, _p(out), _p(centers), _p(idx), _stream())
     return (out, centers, idx) if want_aux else out
 
@@ -111,7 +111,7 @@ def ipe_features(tdist, rays_o, rays_d, radii, basis, min_deg=0, max_deg=12, out
         raise ValueError(out)
     means = torch.empty(n * s, 3, device=dev, dtype=_F32) if want_aux else None
     lvar = torch.empty(n * s, b, device=dev, dtype=_F32) if want_aux else None
-    _lib.call("hos_ipe_features", _p(tdist), _p(rays_o), _p(rays_d), _p(radii), _p(basis), n, s, b,
+    _lib.call_unless_empty(n * s, "hos_ipe_features", _p(tdist), _p(rays_o), _p(rays_d), _p(radii), _p(basis), n, s, b,
               min_deg, max_deg, _p(feat), ld, code, _p(means), _p(lvar), _stream())
     return (feat, means, lvar) if want_aux else feat
 
@@ -121,7 +121,7 @@ def pos_enc(x, min_deg, max_deg, append_identity=True):
     n = x.shape[0]
     width = (3 if append_identity else 0) + 6 * (max_deg - min_deg)
     out = torch.empty(n, width, device=x.device, dtype=_F32)
-    _lib.call("hos_pos_enc", _p(x), n, min_deg, max_deg, int(append_identity), _p(out), _stream())
+    _lib.call_unless_empty(n, "hos_pos_enc", _p(x), n, min_deg, max_deg, int(append_identity), _p(out), _stream())
     return out
 
 
@@ -133,7 +133,7 @@ def fourier_embed(x, n_freqs, include_input, hann_w=None, out="fp32"):
         o, ld, code = torch.empty(p, width, device=x.device, dtype=_F32), width, 0
     else:
         o, ld, code = torch.empty(tiled_bytes(p, width), device=x.device, dtype=torch.uint8), 0, 2
-    _lib.call("hos_fourier_embed", _p(x), p, n_freqs, int(include_input), _p(hann_w), _p(o), ld, code, _stream())
+    _lib.call_unless_empty(p, "hos_fourier_embed", _p(x), p, n_freqs, int(include_input), _p(hann_w), _p(o), ld, code, _stream())
     return o
 
 
@@ -151,6 +151,18 @@ def lbs_warp(pts, R, T, vol, bbox_min, bbox_scale):
     return x, m
 
 
+def lbs_forward(cnl_pts, R_fwd, T_fwd, vol, bbox_min, bbox_scale):
+    _chk(cnl_pts, "cnl_pts"), _chk(R_fwd, "R_fwd"), _chk(T_fwd, "T_fwd"), _chk(vol, "vol")
+    p = cnl_pts.numel() // 3
+    bones = R_fwd.shape[0]
+    g = vol.shape[-1]
+    x = torch.empty(p, 3, device=cnl_pts.device, dtype=_F32)
+    m = torch.empty(p, device=cnl_pts.device, dtype=_F32)
+    _lib.call_unless_empty(p, "hos_lbs_forward", _p(cnl_pts), _p(R_fwd), _p(T_fwd), _p(vol), _host3(bbox_min),
+                           _host3(bbox_scale), p, bones, g, _p(x), _p(m), _stream())
+    return x, m
+
+
 # ----------------------------------------------------------------------------- fp32 MLP blocks
 def linear_f32(x1, w, b, act=0, x2=None, x2_row_div=1, k1=None, k2=None):
     """y = act([x1[:, :k1] | x2[:, :k2]] @ w.T + b)."""
@@ -161,7 +173,7 @@ def linear_f32(x1, w, b, act=0, x2=None, x2_row_div=1, k1=None, k2=None):
     n = w.shape[0]
     assert w.shape[1] == k1 + k2, (w.shape, k1, k2)
     y = torch.empty(m, n, device=x1.device, dtype=_F32)
-    _lib.call("hos_linear_f32_ex", _p(x1), x1.stride(0), k1, _p(x2), 0 if x2 is None else x2.stride(0), k2,
+    _lib.call_unless_empty(m, "hos_linear_f32_ex", _p(x1), x1.stride(0), k1, _p(x2), 0 if x2 is None else x2.stride(0), k2,
               x2_row_div, _p(w), _p(b), m, n, act, _p(y), n, _stream())
     return y
 
@@ -172,7 +184,7 @@ def head_f32(x, w, b, post=0, shift=0.0, add=None):
     n = w.shape[0]
     assert w.shape[1] == k
     y = torch.empty(m, n, device=x.device, dtype=_F32)
-    _lib.call("hos_head_f32", _p(x), x.stride(0), k, _p(w), _p(b), m, n, post, shift, _p(add), _p(y), n, _stream())
+    _lib.call_unless_empty(m, "hos_head_f32", _p(x), x.stride(0), k, _p(w), _p(b), m, n, post, shift, _p(add), _p(y), n, _stream())
     return y
 
 
@@ -215,7 +227,7 @@ class FusedMLP:
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.call("hos_mlp_forward_ipe", self._h, _p(tdist), _p(rays_o), _p(rays_d), _p(radii), basis_host, n, s,
+        _lib.call_unless_empty(rows, "hos_mlp_forward_ipe", self._h, _p(tdist), _p(rays_o), _p(rays_d), _p(radii), basis_host, n, s,
                   _p(rowbias), rowbias_div, _p(outs[0]), _p(outs[1]), _stream())
         if PROFILE is not None:
             e1.record()
@@ -240,7 +252,7 @@ class FusedMLP:
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.call("hos_mlp_forward", self._h, _p(x_tiled), rows, _p(rowbias), rowbias_div, _p(add),
+        _lib.call_unless_empty(rows, "hos_mlp_forward", self._h, _p(x_tiled), rows, _p(rowbias), rowbias_div, _p(add),
                   _p(outs[0]), _p(outs[1]), _stream())
         if PROFILE is not None:
             e1.record()
@@ -261,7 +273,7 @@ def pack_rows_f16(x, k=None):
     rows = x.shape[0]
     k = x.shape[1] if k is None else k
     out = torch.empty(tiled_bytes(rows, k), device=x.device, dtype=torch.uint8)
-    _lib.call("hos_pack_rows_f16", _p(x), rows, x.stride(0), k, _p(out), _stream())
+    _lib.call_unless_empty(rows, "hos_pack_rows_f16", _p(x), rows, x.stride(0), k, _p(out), _stream())
     return out
 
 

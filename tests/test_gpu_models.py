@@ -366,3 +366,62 @@ def test_stage3_composite_end_to_end(golden):
     with torch.no_grad():
         rend, hist = net(b, 1.0, False, False, 0.1, 1e6)
     assert rend == [] and "tdist" in hist[-1] and hist[-1]["tdist"].shape == (n, 33)
+
+
+def test_stage3_pipeline_vs_oracle():
+    """Complete HOSNeRF chunk (background + human + depth merge) on seeded rays against the oracle run
+    end to end on the CPU.  rgb gate 2e-3: the composite inherits the human branch's end-to-end
+    conditioning (see module docstring); fg/bg classification must agree exactly."""
+    from hosnerf_b200 import render_hosnerf_chunk
+    n = 96
+    hb = synth.make_human_batch(n)
+    Mw = synth.random_rigid()
+    ro, rd = hb["rays"][0], hb["rays"][1]
+    ro_w = (Mw[:3, :3] @ ro.T).T + Mw[:3, 3]
+    rd_w = (Mw[:3, :3] @ rd.T).T
+    bb = {"rays_o": ro_w, "rays_d": rd_w, "viewdirs": rd_w / rd_w.norm(dim=-1, keepdim=True),
+          "radii": torch.full((n, 1), 1e-3), "times": torch.tensor(0.0)}
+    bkg = MipNeRF360("/nonexistent", opaque_background=True, nerf_netwidth=256, stage3=True, precision="fp32")
+    synth.fill_params_(bkg, 0)
+    human = _human()
+    sd_b = {k: v.detach().cpu() for k, v in bkg.state_dict().items()}
+    sd_h = {k: v.detach().cpu() for k, v in human.state_dict().items()}
+    with torch.no_grad():
+        _, hist = R.mip360_forward(sd_b, bb, 1.0, False, 0.1, 1e6, stage3=True)
+        ho = HR.network_forward(sd_h, hb)
+        ref_rgb, ref_fg, ref_hw, _ = HR.composite_s3(hist[-1]["rgb"], hist[-1]["density"], hist[-1]["tdist"], ho["human_rgb"],
+                                                     ho["human_density"], ho["pts_mask"], ho["newsmpl_pts"], Mw, ro_w, rd_w)
+    out = render_hosnerf_chunk(bkg.to(DEV), human, {k: cu(v) for k, v in bb.items()}, {k: cu(v) for k, v in hb.items()}, Mw)
+    assert torch.equal(out["idx_fg"].cpu(), ref_fg)
+    assert 0 < int(ref_fg.sum()) < n
+    print("stage3 pipeline: rgb abs", max_abs(out["rgb"].cpu(), ref_rgb))
+    assert max_abs(out["rgb"].cpu(), ref_rgb) < 2e-3
+    assert rel_err(out["human_weights"].cpu()[ref_fg], ref_hw) < 2e-2
+
+
+def test_human_cycle_outputs_vs_oracle():
+    """Cycle side path (forward LBS + forward non-rigid MLP, network.py:505-536), on request in eval."""
+    net = _human()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    b = synth.make_human_batch(32)
+    with torch.no_grad():
+        ref = HR.network_forward(sd, b)
+        out = net(**{k: cu(v) for k, v in b.items()}, cycle_outputs=True)
+    assert out["observe_pts"].shape == ref["observe_pts"].shape
+    assert torch.equal(out["observe_pts"].cpu(), ref["observe_pts"])
+    assert max_abs(out["deform_pts_final"].cpu(), ref["deform_pts_final"]) < 1e-3
+
+
+def test_edge_cases():
+    """Empty batch, single ray, ragged tile counts (rows not a multiple of 128) in both precisions."""
+    for prec in ("fp32", "fp16"):
+        net = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256, precision=prec)
+        ref_b = synth.make_bkg_batch(131, seed=2)
+        with torch.no_grad():
+            full, _ = net({k: cu(v) for k, v in ref_b.items()}, 1.0, False, False, 0.1, 1e6)
+            one, _ = net({k: cu(v[:1]) for k, v in ref_b.items()}, 1.0, False, False, 0.1, 1e6)
+            none, hist = net({k: cu(v[:0]) for k, v in ref_b.items()}, 1.0, False, False, 0.1, 1e6)
+        assert full[-1]["rgb"].shape == (131, 3) and torch.isfinite(full[-1]["rgb"]).all()
+        assert none[-1]["rgb"].shape == (0, 3) and hist[-1]["weights"].shape == (0, 32)
+        # a ray renders the same alone as inside a batch (rays are independent units)
+        assert max_abs(one[-1]["rgb"].cpu(), full[-1]["rgb"][:1].cpu()) < (1e-6 if prec == "fp32" else 1e-3)
