@@ -47,6 +47,7 @@ _DEFAULT_PRECISION = "fp32"
 # fp16 mode: generate the IPE features inside the tcgen05 MLP kernel (False: materialise them in HBM
 # with hos_ipe_features first - kept for A/B measurements and as the accurate-sin/cos variant)
 FUSE_IPE = os.environ.get("HOSNERF_UNFUSED_IPE", "0") != "1"
+MERGE_BOTTLENECK = os.environ.get("HOSNERF_KEEP_BOTTLENECK", "0") != "1"
 
 
 def set_precision(p: str):
@@ -191,10 +192,15 @@ class MipNeRF360MLP(nn.Module):
                                x_first=0, relu=1, rowbias=0, head=-1))
         heads.append(dict(out_dim=1, post=1, shift=float(self.density_bias), out_slot=0))
         layers[-1]["head"] = 0
+        # The bottleneck layer has no activation (S1 model.py:238-248), so bottleneck -> view layer is one
+        # linear map:  Wv[:, :bw] (Wb h + bb) = (Wv[:, :bw] Wb) h + Wv[:, :bw] bb.  Merging them on the
+        # host removes a 256x256 layer (7.7 % of the NeRF MLP's FLOPs) from the tensor-core program.
+        merge = MERGE_BOTTLENECK and not self.disable_rgb
         if not self.disable_rgb:
-            layers.append(dict(out_dim=self.bottleneck_width, in_h=nw, in_x=0, x_first=0, relu=0, rowbias=0, head=-1))
-            layers.append(dict(out_dim=self.netwidth_condition, in_h=self.bottleneck_width, in_x=0, x_first=0,
-                               relu=1, rowbias=1, head=1))
+            if not merge:
+                layers.append(dict(out_dim=self.bottleneck_width, in_h=nw, in_x=0, x_first=0, relu=0, rowbias=0, head=-1))
+            layers.append(dict(out_dim=self.netwidth_condition, in_h=nw if merge else self.bottleneck_width, in_x=0,
+                               x_first=0, relu=1, rowbias=1, head=1))
             heads.append(dict(out_dim=self.num_rgb_channels, post=2, shift=float(self.rgb_padding), out_slot=1))
         mlp = ops.FusedMLP(F, layers, heads)
         fuse = (FUSE_IPE and self.pos_basis_t.shape[1] == 21 and self.max_deg_point - self.min_deg_point == 12
@@ -209,8 +215,15 @@ class MipNeRF360MLP(nn.Module):
             mlp.set_layer(i, W, b)
         mlp.set_head(0, *f["density"])
         if not self.disable_rgb:
-            mlp.set_layer(self.netdepth, *f["bottleneck"])
-            mlp.set_layer(self.netdepth + 1, f["views"][2], None)
+            Wb, bb = f["bottleneck"]
+            Wv1, bv = f["views"][2], f["views"][1]
+            if merge:
+                mlp.set_layer(self.netdepth, (Wv1 @ Wb).contiguous(), None)
+                mlp.view_bias = (bv + Wv1 @ bb).contiguous()
+            else:
+                mlp.set_layer(self.netdepth, Wb, bb)
+                mlp.set_layer(self.netdepth + 1, Wv1, None)
+                mlp.view_bias = bv
             mlp.set_head(1, *f["rgb"])
         self._cache["f16_key"], self._cache["f16"] = key, mlp
         return mlp
@@ -228,7 +241,7 @@ class MipNeRF360MLP(nn.Module):
             rowbias = None
             if not self.disable_rgb:
                 de = ops.pos_enc(viewdirs, 0, self.deg_view, True)
-                rowbias = ops.linear_f32(de, f["views"][3], f["views"][1])        # per-ray view term + bias
+                rowbias = ops.linear_f32(de, f["views"][3], mlp.view_bias)        # per-ray view term + bias
             if mlp.fused_ipe:
                 dens, rgb = mlp.forward_ipe(tdist, rays_o, rays_d, radii, mlp.basis_host, rowbias=rowbias, rowbias_div=s)
             else:
