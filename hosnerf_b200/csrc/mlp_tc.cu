@@ -40,7 +40,8 @@ constexpr int kStagesX = 3;      // input-feature ring depth
 constexpr int kMlpThreads = 512; // warp 0 producer, 1 MMA, (2-3 idle), 4-11 epilogue, 12-15 feature generators
 constexpr int kEpiWarp0 = 4, kEpiWarps = 8, kFeatWarp0 = 12;
 constexpr int kJGroup = 7;       // basis directions per feature-generation group (3 groups of 7)
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;   // two accumulator buffers: consecutive tiles alternate, so the first layer of
+                                 // tile t+1 (input = features, no dependence on tile t) overlaps tile t's last read-out
 constexpr int kIpeB = 21;        // geodesic basis directions (icosahedron, 2 subdivisions)
 constexpr int kIpeDeg = 12;      // octaves 2^0 .. 2^11
 
@@ -319,8 +320,8 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
   uint64_t* bar_xfull = bar_wempty + kStages;           // [kStagesX]
   uint64_t* bar_xempty = bar_xfull + kStagesX;          // [kStagesX]
   uint64_t* bar_tmem_full = bar_xempty + kStagesX;
-  uint64_t* bar_act = bar_tmem_full + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_act + 1);
+  uint64_t* bar_act = bar_tmem_full + 2;                // [2] each: layer iterations alternate between the two,
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_act + 2);   // so a waiter is never two phases behind
   float* s_headx = reinterpret_cast<float*>(s_tmem + 4);     // [128][4] partial head sums of the upper column half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -330,8 +331,10 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wempty[s], 1); }
     for (int s = 0; s < kStagesX; ++s) { mbar_init(&bar_xfull[s], fused ? 128 : 1); mbar_init(&bar_xempty[s], 1); }
-    mbar_init(bar_tmem_full, 1);
-    mbar_init(bar_act, kEpiWarps * 32);
+    mbar_init(&bar_tmem_full[0], 1);
+    mbar_init(&bar_tmem_full[1], 1);
+    mbar_init(&bar_act[0], kEpiWarps * 32);
+    mbar_init(&bar_act[1], kEpiWarps * 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -372,13 +375,20 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    uint32_t wi = 0, xi = 0, li = 0;
-    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
+    uint32_t wi = 0, xi = 0, li = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x, ++ti) {
+      const uint32_t acc = tmem_base + (ti & 1) * 256;
       for (int l = 0; l < prog.n_layers; ++l, ++li) {
         const LayerDev L = prog.layers[l];
         const uint32_t idesc = umma_idesc_f16(L.n);
-        if (li > 0) {                         // previous epilogue: H written, TMEM drained
-          mbar_wait(bar_act, (li - 1) & 1);
+        // Layer l > 0 needs the previous layer's epilogue (activations written, accumulator drained).
+        // Layer 0 reads only the input ring and writes the OTHER accumulator buffer, so it may start
+        // while the previous tile's last read-out is still running; that buffer was drained two
+        // tiles ago, which the wait of this tile's layer 1 (two phases later on the same barrier
+        // pair) transitively guarantees for every tile with >= 2 layers.
+        if (l > 0) {
+          const uint32_t pl = li - 1;         // phase index; barrier (pl & 1) completes every other layer
+          mbar_wait(&bar_act[pl & 1], (pl >> 1) & 1);
           tc_fence_after();
         }
         if (args.timeline && blockIdx.x == 0 && lane == 0 && li < 64) args.timeline[li * 4 + 0] = clock64();
@@ -395,11 +405,11 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
             const uint32_t b_base = smem_u32(sRingW + ws * w_stage_bytes);
 #pragma unroll
             for (int k = 0; k < kKB / 16; ++k)
-              tc_mma_f16(tmem_base, umma_desc(a_base + k * 32), umma_desc(b_base + k * 32), idesc,
+              tc_mma_f16(acc, umma_desc(a_base + k * 32), umma_desc(b_base + k * 32), idesc,
                          (kb | k) != 0 ? 1u : 0u);
             tc_commit(&bar_wempty[ws]);         // ring slots are released when these MMAs retire
             if (from_x) tc_commit(&bar_xempty[xs]);
-            if (kb == nkb - 1) tc_commit(bar_tmem_full);
+            if (kb == nkb - 1) tc_commit(&bar_tmem_full[li & 1]);
           }
           __syncwarp();
           if (from_x) ++xi;
@@ -412,10 +422,11 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
     const int q = warp & 3;                     // TMEM lane quarter this warp may access (warp id % 4)
     const int ch = (warp - kEpiWarp0) >> 2;     // which half of the layer's columns
     const int r = q * 32 + lane;                // row within the tile
-    uint32_t li = 0;
-    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x) {
+    uint32_t li = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < args.ntiles; tile += gridDim.x, ++ti) {
       const int64_t row = (int64_t)tile * kTileM + r;
       const bool row_ok = row < args.rows;
+      const uint32_t acc = tmem_base + (ti & 1) * 256 + ((uint32_t)(q * 32) << 16);
       for (int l = 0; l < prog.n_layers; ++l, ++li) {
         const LayerDev L = prog.layers[l];
         const bool last = (l == prog.n_layers - 1);
@@ -425,12 +436,12 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
         const int nh = L.n >> 1;
         const int cbeg = ch * nh, cend = cbeg + nh;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-        mbar_wait(bar_tmem_full, li & 1);
+        mbar_wait(&bar_tmem_full[li & 1], (li >> 1) & 1);
         tc_fence_after();
         if (args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && li < 64) args.timeline[li * 4 + 2] = clock64();
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld32(acc + (uint32_t)c0, v);
           float f[32];
           const float4* b4 = reinterpret_cast<const float4*>(sParams + L.bias_off + c0);
 #pragma unroll
@@ -514,7 +525,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
         }
         fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
         tc_fence_before();          // TMEM loads ordered before the arrive
-        mbar_arrive(bar_act);
+        mbar_arrive(&bar_act[li & 1]);
         if (args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && li < 64) args.timeline[li * 4 + 3] = clock64();
       }
     }
@@ -608,7 +619,7 @@ extern "C" {
 hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers, int n_heads,
                           const hos_mlp_head* heads) {
   if (hos::check_arch() != HOS_OK) return nullptr;
-  if (!layers || n_layers < 1 || n_layers > kMaxLayers || n_heads < 0 || n_heads > kMaxHeads || in_dim < 1) {
+  if (!layers || n_layers < 2 || n_layers > kMaxLayers || n_heads < 0 || n_heads > kMaxHeads || in_dim < 1) {
     hos::set_error("hos_mlp_create: bad layer/head count");
     return nullptr;
   }
@@ -673,7 +684,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   m->w_bytes = woff;
   m->smem_bytes = 1024 + (size_t)P.kbh * kXChunkBytes + (size_t)kStages * nmax * 128 +
                   (size_t)kStagesX * kXChunkBytes + (((size_t)poff + 3) & ~(size_t)3) * 4 +
-                  (2 * kStages + 2 * kStagesX + 2) * 8 + 16 + kTileM * 4 * sizeof(float);
+                  (2 * kStages + 2 * kStagesX + 4) * 8 + 16 + kTileM * 4 * sizeof(float);
   if (m->smem_bytes > 227 * 1024) {
     hos::set_error("hos_mlp_create: needs %zu B shared memory (> 227 KB)", m->smem_bytes);
     delete m;
