@@ -137,6 +137,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mlp-variant", type=int, default=0, help="A/B: 0 auto, 1 single-CTA MLP kernel, 2 cluster-pair kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -154,6 +155,7 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
 
+    ops.set_mlp_variant(args.mlp_variant)
     lit = LitMipNeRF360("/nonexistent", precision=args.precision, **MODEL_KW)
     synth.fill_params_(lit.model, 0)
     lit = lit.to(dev)

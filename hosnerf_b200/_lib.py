@@ -56,6 +56,7 @@ SIGNATURES = {
     "hos_mlp_set_ipe_input": (c_i, [C.c_void_p, c_i]),
     "hos_mlp_forward_ipe": (c_i, [C.c_void_p, c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_f, c_i, c_f, c_f, c_f]),
     "hos_mlp_debug_timeline": (c_i, [c_f]),
+    "hos_mlp_set_variant": (c_i, [c_i]),
     "hos_pack_rows_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f]),
     "hos_composite_mip360": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
@@ -66,7 +67,7 @@ SIGNATURES = {
 _lib = None
 LAUNCHES = 0          # kernels of this library launched so far (bench.py reports it per timed region)
 _KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_bias": 0, "hos_mlp_set_head": 0,
-                     "hos_mlp_set_ipe_input": 0}
+                     "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0}
 
 
 def load():

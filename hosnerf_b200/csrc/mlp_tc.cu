@@ -89,14 +89,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting warp sleeps in hardware until the phase completes (or the
+// hint expires) instead of spinning - a bare try_wait loop polls every few cycles and, with ~10 waiting warps per
+// SM, was taking a third of all issue slots away from the epilogue / feature warps (ncu: BRA = 33 % of samples).
+constexpr uint32_t kSuspendHintNs = 0x989680u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(kSuspendHintNs) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -129,6 +133,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- cluster-pair (cta_group::2) wrappers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Bounded waits for the pair kernel: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Each try_wait sleeps up to kSuspendHintNs in hardware, so the loop body runs a handful of times at most.
+__device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  long long t_start = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(a), "r"(parity), "r"(kSuspendHintNs) : "memory");
+    if (ok) return;
+    const long long now = clock64();
+    if (t_start == 0) t_start = now;
+    else if (now - t_start > 4000000000ll) __trap();        // ~2 s: far beyond any legitimate wait
+  }
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
 // (bit layout: cute/arch/mma_sm100_desc.hpp, SmemDescriptor).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -141,8 +205,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return d;
 }
 // Instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M=128.
-__host__ __device__ inline uint32_t umma_idesc_f16(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__host__ __device__ inline uint32_t umma_idesc_f16(int n, int m = kTileM) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 
@@ -227,8 +291,26 @@ __device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, boo
 // Produce the 8 feature chunks of one pass for row r into the X ring.  Kernel column order:
 //   col = jg*168 + l*14 + jj*2 + {0: sin, 1: cos},  j = jg*7 + jj   (3 groups of 7 directions)
 // so that a thread only carries 7 directions of recurrence state at a time.
+// kStg: ring depth.  kWarpArrive == false: every thread arrives on bar_xfull (count 128).
+// kWarpArrive == true (cluster-pair kernel): one arrival per warp, on the local bar_xfull (xfull_remote == 0)
+// or on the leader CTA's barrier at cluster address xfull_remote + 8 * stage.
+template <int kStg, bool kWarpArrive>
 __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRowGeom& G, int r, unsigned char* sRingX,
-                                                  uint64_t* bar_xfull, uint64_t* bar_xempty, uint32_t& xi) {
+                                                  uint64_t* bar_xfull, uint64_t* bar_xempty, uint32_t& xi,
+                                                  uint32_t xfull_remote = 0) {
+  auto chunk_done = [&]() {
+    fence_proxy_async();
+    if (!kWarpArrive) {
+      mbar_arrive(&bar_xfull[xi % kStg]);
+    } else {
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
+        if (xfull_remote) mbar_arrive_remote(xfull_remote + 8u * (xi % kStg));
+        else mbar_arrive(&bar_xfull[xi % kStg]);
+      }
+    }
+    ++xi;
+  };
   constexpr float kInv2Pi = 0.15915494309189535f;
   constexpr float k2PiHi = 6.2831854820251465f;           // fl32(2 pi)
   constexpr float k2PiLo = -1.7484555e-07f;               // 2 pi - fl32(2 pi)
@@ -258,8 +340,9 @@ __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRow
       for (int jj = 0; jj < kJGroup; ++jj) {
         const int p = (jg * kIpeDeg + l) * kJGroup + jj;   // pair index; columns 2p, 2p+1
         if ((p & 31) == 0) {                               // first pair of a 64-column chunk: acquire a slot
-          const int xs = xi % kStagesX;
-          mbar_wait(&bar_xempty[xs], ((xi / kStagesX) & 1) ^ 1);
+          const int xs = xi % kStg;
+          if (kWarpArrive) mbar_wait_guard(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
+          else mbar_wait(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
           slot = sRingX + xs * kXChunkBytes;
         }
         // ---- sin/cos of 2^l m_j: angle doubling, re-seeded every 4 octaves
@@ -288,19 +371,13 @@ __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRow
           const int g = (p & 31) >> 2;              // 16-byte group inside the chunk row
           *reinterpret_cast<uint4*>(slot + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        if ((p & 31) == 31) {                       // chunk complete
-          fence_proxy_async();
-          mbar_arrive(&bar_xfull[xi % kStagesX]);
-          ++xi;
-        }
+        if ((p & 31) == 31) chunk_done();           // chunk complete
       }
     }
   }
   // 252 pairs = 7 chunks + 28 pairs: groups 0..6 of the last chunk are written, zero the 8th
   *reinterpret_cast<uint4*>(slot + r * 128 + ((7 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-  fence_proxy_async();
-  mbar_arrive(&bar_xfull[xi % kStagesX]);
-  ++xi;
+  chunk_done();
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1)
@@ -539,7 +616,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
       ipe_row_setup(ipe, row, row < args.rows, G);
       for (int l = 0; l < prog.n_layers; ++l) {
         if (prog.layers[l].kb_x == 0) continue;
-        ipe_generate_pass(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi);
+        ipe_generate_pass<kStagesX, false>(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi);
       }
     }
   }
@@ -548,6 +625,351 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+  }
+}
+
+
+// ============================================================================ cluster-pair kernel
+// Two CTAs (one cluster, two SMs) run every layer as ONE tcgen05.mma.cta_group::2 of M = 256 rows:
+// CTA r owns rows [128 r, 128 r + 128) of the A operand and of the accumulator (its own TMEM) and stages
+// only output columns [N/2 r, N/2 r + N/2) of every weight chunk, so each SM pulls half the weight bytes
+// through L2 and a ring stage is 16 KB instead of 32 KB.  That is what makes room for TWO 128-row tiles
+// per CTA ("slots"), whose layers are interleaved  (s0,l) (s1,l) (s0,l+1) ...  : while the tensor core
+// runs slot 1's layer, the epilogue warps drain slot 0's accumulator and write its next A operand, so
+// the MMA pipe only idles when an epilogue is slower than the other slot's MMAs.
+//
+// Measured building blocks (scripts/ubench_tc.cu, B200): tcgen05.ld sustains ~900 B/clk/SM (a 128 x 256
+// fp32 tile drains in ~340 cycles; with bias/ReLU/fp16 pack/st.shared ~1.1 k cycles on 8 warps); M=256
+// N=256 K=16 cta_group::2 issues every 128 cycles; ONE thread's bulk copies complete one mbarrier phase
+// per ~800 cycles regardless of size, but separate warps overlap - hence one producer warp per ring stage.
+//
+// Warp roles (both CTAs unless noted): 0, 2, 3 weight producers (stage = their index; in the peer CTA
+// they also relay "my half has landed" to the leader), 1 MMA issuer (leader CTA only) + TMEM alloc,
+// 4-11 epilogue, 12-15 feature generators.  Barriers that collect arrivals from both CTAs live in the
+// leader; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
+constexpr int kPairStagesW = 3;
+constexpr int kPairStagesX = 2;
+constexpr int kPairBars = 3 * kPairStagesW + 3 * kPairStagesX + 4;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
+                const __grid_constant__ IpeArgs ipe) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int h_bytes = prog.kbh * kXChunkBytes;             // one slot's activations
+  const int w_stage_bytes = prog.n_max * 64;               // this CTA's half of an [n_max x 64] fp16 chunk
+  unsigned char* sH = smem;                                // [2 slots][kbh][16 KB]
+  unsigned char* sRingW = sH + 2 * h_bytes;                // [kPairStagesW][w_stage_bytes]
+  unsigned char* sRingX = sRingW + kPairStagesW * w_stage_bytes;   // [kPairStagesX][16 KB]
+  float* sParams = reinterpret_cast<float*>(sRingX + kPairStagesX * kXChunkBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((prog.param_floats + 3) & ~3));
+  uint64_t* bar_wfull = bars;                              // [3] this CTA's half landed (tx bytes)
+  uint64_t* bar_wpeer = bar_wfull + kPairStagesW;          // [3] leader only: the peer's half landed
+  uint64_t* bar_wempty = bar_wpeer + kPairStagesW;         // [3] multicast commit: stage consumed
+  uint64_t* bar_xfull = bar_wempty + kPairStagesW;         // [2] leader: own feature chunk written / landed
+  uint64_t* bar_xpeer = bar_xfull + kPairStagesX;          // [2] leader only: the peer's feature chunk
+  uint64_t* bar_xempty = bar_xpeer + kPairStagesX;         // [2] multicast commit
+  uint64_t* bar_tfull = bar_xempty + kPairStagesX;         // [2 slots] multicast commit: accumulator ready
+  uint64_t* bar_act = bar_tfull + 2;                       // [2 slots] leader only: 16 epilogue warps done
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kPairBars + 1);
+  float* s_headx = reinterpret_cast<float*>(s_tmem + 4);   // [128][4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool fused = args.fused_ipe != 0;
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int n_groups = (args.ntiles + 3) >> 2;             // 4 tiles per group: tile = 4 g + 2 slot + rank
+  const int n_layers = prog.n_layers;
+
+  for (int i = threadIdx.x; i < prog.param_floats; i += kMlpThreads) sParams[i] = args.params[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPairStagesW; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wpeer[s], 1); mbar_init(&bar_wempty[s], 1); }
+    for (int s = 0; s < kPairStagesX; ++s) {
+      mbar_init(&bar_xfull[s], fused ? 4 : 1);
+      mbar_init(&bar_xpeer[s], fused ? 4 : 1);
+      mbar_init(&bar_xempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_act[s], 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // both CTAs: barriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ===================== weight producers: warp p owns ring stage p =====================
+    if (lane == 0) {
+      const uint32_t p = warp == 0 ? 0u : (uint32_t)(warp - 1);
+      uint32_t wi = 0, xi = 0;
+      for (int g = cluster; g < n_groups; g += n_clusters) {
+        for (int l = 0; l < n_layers; ++l) {
+          const LayerDev L = prog.layers[l];
+          const uint32_t half_bytes = (uint32_t)L.n * 64u;
+          const int nkb = L.kb_h + L.kb_x;
+          for (int slot = 0; slot < 2; ++slot) {
+            for (int kb = 0; kb < nkb; ++kb, ++wi) {
+              const bool from_x = kb >= L.kb_h;
+              const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
+              if (from_x) ++xi;
+              if (wi % kPairStagesW != p) continue;
+              const uint32_t use = wi / kPairStagesW;
+              mbar_wait_guard(&bar_wempty[p], (use & 1) ^ 1);
+              mbar_expect_tx(&bar_wfull[p], half_bytes);
+              bulk_g2s(sRingW + p * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * (2u * half_bytes) + rank * half_bytes,
+                       half_bytes, &bar_wfull[p]);
+              const bool load_x = from_x && !fused;
+              if (load_x) {
+                int tile = 4 * g + 2 * slot + (int)rank;
+                if (tile >= args.ntiles) tile = args.ntiles - 1;          // padding tile: any valid rows, outputs masked
+                mbar_wait_guard(&bar_xempty[xs], (xuse & 1) ^ 1);
+                mbar_expect_tx(&bar_xfull[xs], kXChunkBytes);
+                bulk_g2s(sRingX + xs * kXChunkBytes, args.x_tiled + ((size_t)tile * prog.kbx + (kb - L.kb_h)) * kXChunkBytes,
+                         kXChunkBytes, &bar_xfull[xs]);
+              }
+              if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
+                mbar_wait_guard(&bar_wfull[p], use & 1);
+                mbar_arrive_remote(mapa_u32(smem_u32(&bar_wpeer[p]), 0));
+                if (load_x) {
+                  mbar_wait_guard(&bar_xfull[xs], xuse & 1);
+                  mbar_arrive_remote(mapa_u32(smem_u32(&bar_xpeer[xs]), 0));
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (rank == 0) {
+      uint32_t wi = 0, xi = 0;
+      int gi = 0;
+      for (int g = cluster; g < n_groups; g += n_clusters, ++gi) {
+        for (int l = 0; l < n_layers; ++l) {
+          const LayerDev L = prog.layers[l];
+          const uint32_t idesc = umma_idesc_f16(L.n, 2 * kTileM);
+          const int nkb = L.kb_h + L.kb_x;
+          for (int slot = 0; slot < 2; ++slot) {
+            // unit (slot, l) needs the epilogue of this slot's previous unit in BOTH CTAs: activations
+            // written (l > 0) and the accumulator drained (also across groups for l == 0)
+            const uint32_t u = (uint32_t)gi * n_layers + l;
+            const uint32_t seq = 2 * u + slot;
+            const bool tl = args.timeline && blockIdx.x == 0 && lane == 0 && seq < 64;
+            long long wsum = 0, xsum = 0;
+            if (tl) args.timeline[seq * 12 + 0] = clock64();
+            if (u > 0) mbar_wait_guard(&bar_act[slot], (u - 1) & 1);
+            tc_fence_after();
+            if (tl) args.timeline[seq * 12 + 1] = clock64();
+            const uint32_t acc = tmem_base + slot * 256;
+            for (int kb = 0; kb < nkb; ++kb, ++wi) {
+              const uint32_t ws = wi % kPairStagesW, use = wi / kPairStagesW;
+              const bool from_x = kb >= L.kb_h;
+              const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
+              long long c0 = tl ? clock64() : 0;
+              mbar_wait_guard(&bar_wfull[ws], use & 1);
+              mbar_wait_guard(&bar_wpeer[ws], use & 1);
+              long long c1 = tl ? clock64() : 0;
+              if (from_x) {
+                mbar_wait_guard(&bar_xfull[xs], xuse & 1);
+                mbar_wait_guard(&bar_xpeer[xs], xuse & 1);
+              }
+              if (tl) { wsum += c1 - c0; xsum += clock64() - c1; }
+              tc_fence_after();
+              const bool tl2 = tl && (seq == 21 || seq == 28) && kb < 12;      // chunk-level stamps of two units
+              long long* t2 = args.timeline + 768 + (seq == 28 ? 64 : 0) + kb * 5;
+              if (tl2) { t2[0] = c0; t2[1] = clock64(); }
+              if (lane == 0) {
+                const uint32_t a_base = smem_u32(from_x ? sRingX + xs * kXChunkBytes : sH + slot * h_bytes + kb * kXChunkBytes);
+                const uint32_t b_base = smem_u32(sRingW + ws * w_stage_bytes);
+#pragma unroll
+                for (int k = 0; k < kKB / 16; ++k)
+                  tc_mma_f16_pair(acc, umma_desc(a_base + k * 32), umma_desc(b_base + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                if (tl2) t2[2] = clock64();
+                tc_commit_pair(&bar_wempty[ws]);
+                if (from_x) tc_commit_pair(&bar_xempty[xs]);
+                if (kb == nkb - 1) tc_commit_pair(&bar_tfull[slot]);
+                if (tl2) t2[3] = clock64();
+              }
+              __syncwarp();
+              if (tl2) t2[4] = clock64();
+              if (from_x) ++xi;
+            }
+            if (tl) { args.timeline[seq * 12 + 2] = clock64(); args.timeline[seq * 12 + 8] = wsum; args.timeline[seq * 12 + 9] = xsum; }
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    // ===================== epilogue (8 warps): 2 warps per TMEM lane quarter, half the columns each ============
+    const int q = warp & 3;
+    const int ch = (warp - kEpiWarp0) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t act_addr0 = mapa_u32(smem_u32(&bar_act[0]), 0);
+    int gi = 0;
+    for (int g = cluster; g < n_groups; g += n_clusters, ++gi) {
+      for (int l = 0; l < n_layers; ++l) {
+        const LayerDev L = prog.layers[l];
+        const bool last = (l == n_layers - 1);
+        const bool has_head = L.head >= 0;
+        const HeadDev Hd = prog.heads[has_head ? L.head : 0];
+        const int nh = L.n >> 1;
+        const int cbeg = ch * nh, cend = cbeg + nh;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int tile = 4 * g + 2 * slot + (int)rank;
+          const int64_t row = (int64_t)tile * kTileM + r;
+          const bool row_ok = row < args.rows;
+          const uint32_t u = (uint32_t)gi * n_layers + l;
+          const uint32_t acc = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16);
+          unsigned char* sHs = sH + slot * h_bytes;
+          const float* rb = (L.rowbias && args.rowbias && row_ok) ? args.rowbias + (row / args.rowbias_div) * L.n : nullptr;
+          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+          const uint32_t seq = 2 * u + slot;
+          const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && seq < 64;
+          if (tl) args.timeline[seq * 12 + 3] = clock64();
+          mbar_wait_guard(&bar_tfull[slot], u & 1);
+          tc_fence_after();
+          if (tl) args.timeline[seq * 12 + 4] = clock64();
+
+          auto process32 = [&](uint32_t (&v)[32], int c0) {
+            float f[32];
+            const float4* b4 = reinterpret_cast<const float4*>(sParams + L.bias_off + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = b4[j];
+              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
+              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
+              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
+              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
+            }
+            if (rb) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(rb + c0) + j);
+                f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+              }
+            }
+            if (L.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (has_head) {
+#pragma unroll
+              for (int n = 0; n < 4; ++n) {
+                if (n < Hd.hn) {
+                  const float4* w4 = reinterpret_cast<const float4*>(sParams + Hd.w_off + n * L.n + c0);
+                  float a = hacc[n];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 w = w4[j];
+                    a = fmaf(f[4 * j + 0], w.x, a); a = fmaf(f[4 * j + 1], w.y, a);
+                    a = fmaf(f[4 * j + 2], w.z, a); a = fmaf(f[4 * j + 3], w.w, a);
+                  }
+                  hacc[n] = a;
+                }
+              }
+            }
+            if (!last) {
+              unsigned char* dst = sHs + (c0 >> 6) * kXChunkBytes;
+              const int kk = c0 & 63;
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                __half2 h0 = __floats2half2_rn(f[gq * 8 + 0], f[gq * 8 + 1]);
+                __half2 h1 = __floats2half2_rn(f[gq * 8 + 2], f[gq * 8 + 3]);
+                __half2 h2 = __floats2half2_rn(f[gq * 8 + 4], f[gq * 8 + 5]);
+                __half2 h3 = __floats2half2_rn(f[gq * 8 + 6], f[gq * 8 + 7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(dst + tile_byte_offset(r, kk + gq * 8)) = pk;
+              }
+            }
+          };
+
+          // two TMEM loads in flight: the next 32 columns arrive while these are converted
+          uint32_t va[32], vb[32];
+          tmem_ld32_nowait(acc + (uint32_t)cbeg, va);
+          for (int c0 = cbeg; c0 < cend; c0 += 64) {
+            tmem_wait_ld();
+            const bool more1 = c0 + 32 < cend;
+            if (more1) tmem_ld32_nowait(acc + (uint32_t)(c0 + 32), vb);
+            process32(va, c0);
+            if (more1) {
+              tmem_wait_ld();
+              if (c0 + 64 < cend) tmem_ld32_nowait(acc + (uint32_t)(c0 + 64), va);
+              process32(vb, c0 + 32);
+            }
+          }
+
+          if (has_head) {                         // combine the two column halves, then post-process
+            if (ch == 1) *reinterpret_cast<float4*>(s_headx + r * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            if (ch == 0 && row_ok) {
+              const float4 o4 = *reinterpret_cast<const float4*>(s_headx + r * 4);
+              hacc[0] += o4.x; hacc[1] += o4.y; hacc[2] += o4.z; hacc[3] += o4.w;
+              float* o = args.out[Hd.slot] + row * Hd.hn;
+#pragma unroll
+              for (int n = 0; n < 4; ++n) {
+                if (n >= Hd.hn) break;
+                float x = hacc[n] + sParams[Hd.b_off + n];
+                if (Hd.post == 1) {
+                  float z = x + Hd.shift;
+                  x = z > 20.f ? z : log1pf(expf(z));
+                } else if (Hd.post == 2) {
+                  x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * Hd.shift) - Hd.shift;
+                } else if (Hd.post == 3) {
+                  x = args.add[row * Hd.hn + n] + x;
+                } else if (Hd.post == 4) {
+                  x = (n < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+                }
+                o[n] = x;
+              }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+          }
+          fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
+          tc_fence_before();          // TMEM loads ordered before the arrive
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(act_addr0 + 8u * slot);
+          if (tl) args.timeline[seq * 12 + 5] = clock64();
+        }
+      }
+    }
+  } else if (fused && warp >= kFeatWarp0) {
+    // ===================== feature generators (warps 12..15): fused IPE prologue =====================
+    const int r = (warp - kFeatWarp0) * 32 + lane;
+    const uint32_t xremote = rank != 0 ? mapa_u32(smem_u32(&bar_xpeer[0]), 0) : 0u;
+    uint32_t xi = 0;
+    int gi = 0;
+    for (int g = cluster; g < n_groups; g += n_clusters, ++gi) {
+      for (int l = 0; l < n_layers; ++l) {
+        if (prog.layers[l].kb_x == 0) continue;
+        for (int slot = 0; slot < 2; ++slot) {
+          const int64_t row = (int64_t)(4 * g + 2 * slot + (int)rank) * kTileM + r;
+          const uint32_t seq = 2 * ((uint32_t)gi * n_layers + l) + slot;
+          const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kFeatWarp0 * 32 && seq < 64;
+          if (tl) args.timeline[seq * 12 + 6] = clock64();
+          IpeRowGeom G;
+          ipe_row_setup(ipe, row, row < args.rows, G);
+          ipe_generate_pass<kPairStagesX, true>(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi, xremote);
+          if (tl) args.timeline[seq * 12 + 7] = clock64();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                   // no CTA leaves (or frees TMEM) while its partner may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
   }
 }
 
@@ -611,8 +1033,13 @@ struct hos_mlp {
   float* d_params = nullptr;         // biases + head weights (fp32)
   size_t w_bytes = 0;
   size_t smem_bytes = 0;
+  size_t smem_pair = 0;    // shared memory of the cluster-pair kernel; 0: this program only runs on mlp_tc_kernel
+  int max_clusters = 0;    // co-resident 2-CTA clusters (persistent grid of the pair kernel)
   int ipe_perm = 0;        // weights packed for the fused-IPE column order
 };
+
+// 0: pick automatically (pair kernel when the program supports it), 1: single-CTA kernel, 2: pair kernel (error if unsupported)
+static int g_mlp_variant = 0;
 
 extern "C" {
 
@@ -689,6 +1116,31 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
     hos::set_error("hos_mlp_create: needs %zu B shared memory (> 227 KB)", m->smem_bytes);
     delete m;
     return nullptr;
+  }
+  // cluster-pair kernel: every layer width a multiple of 64 (two CTAs x two epilogue column halves x 32-column
+  // TMEM loads), two activation slots + half-width weight stages must fit
+  bool pair_ok = true;
+  for (int l = 0; l < n_layers; ++l) pair_ok = pair_ok && (layers[l].out_dim % 64) == 0;
+  const size_t smem_pair = 1024 + 2 * (size_t)P.kbh * kXChunkBytes + (size_t)kPairStagesW * nmax * 64 +
+                           (size_t)kPairStagesX * kXChunkBytes + (((size_t)poff + 3) & ~(size_t)3) * 4 +
+                           (kPairBars + 1) * 8 + 16 + kTileM * 4 * sizeof(float);
+  if (pair_ok && smem_pair <= 227 * 1024) {
+    m->smem_pair = smem_pair;
+    if (cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
+      cudaGetLastError();
+      m->smem_pair = 0;
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kNumSMs);
+      cfg.blockDim = dim3(kMlpThreads);
+      cfg.dynamicSmemBytes = m->smem_pair;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, mlp_pair_kernel, &cfg) != cudaSuccess || nc < 1) {
+        cudaGetLastError();
+        nc = kNumSMs / 2;
+      }
+      m->max_clusters = nc < kNumSMs / 2 ? nc : kNumSMs / 2;
+    }
   }
   if (cudaMalloc(&m->d_w, m->w_bytes) != cudaSuccess || cudaMalloc(&m->d_params, (size_t)poff * 4) != cudaSuccess ||
       cudaMemset(m->d_params, 0, (size_t)poff * 4) != cudaSuccess ||
@@ -767,8 +1219,17 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   a.fused_ipe = ipe != nullptr;
   a.timeline = g_timeline;
   static const IpeArgs kNoIpe = {};
-  int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
-  mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
+  HOS_REQUIRE(g_mlp_variant != 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
+  // the pair kernel walks groups of 4 tiles; tiny batches keep more SMs busy on the single-CTA kernel
+  const bool pair = m->smem_pair && g_mlp_variant == 2;      // opt-in until it beats the single-CTA kernel
+  if (pair) {
+    const int n_groups = (a.ntiles + 3) / 4;
+    const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
+    mlp_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_pair, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
+  } else {
+    int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
+    mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
+  }
   HOS_LAUNCH_CHECK();
   return HOS_OK;
 }
@@ -781,8 +1242,14 @@ int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float
   return mlp_launch(m, x_tiled, nullptr, rows, rowbias, rowbias_div, add, out0, out1, stream);
 }
 
-int hos_mlp_debug_timeline(long long* device_buf_256) {
-  g_timeline = device_buf_256;
+int hos_mlp_set_variant(int variant) {
+  HOS_REQUIRE(variant >= 0 && variant <= 2, "hos_mlp_set_variant: 0 = auto, 1 = single-CTA kernel, 2 = cluster-pair kernel");
+  g_mlp_variant = variant;
+  return HOS_OK;
+}
+
+int hos_mlp_debug_timeline(long long* device_buf_1024) {
+  g_timeline = device_buf_1024;
   return HOS_OK;
 }
 

@@ -268,6 +268,11 @@ class FusedMLP:
             pass
 
 
+def set_mlp_variant(variant: int):
+    """0 = automatic, 1 = single-CTA tcgen05 kernel, 2 = cluster-pair (cta_group::2, ping-pong) kernel."""
+    _lib.call("hos_mlp_set_variant", int(variant))
+
+
 def pack_rows_f16(x, k=None):
     _chk(x, "x")
     rows = x.shape[0]

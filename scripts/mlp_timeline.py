@@ -1,29 +1,68 @@
-"""Per-layer timeline of CTA 0 of the tcgen05 MLP kernel (debug hook hos_mlp_debug_timeline)."""
+"""Per-unit timeline of CTA 0 of the tcgen05 MLP kernels (debug hook hos_mlp_debug_timeline).
+usage: python scripts/mlp_timeline.py [variant: 1 single-CTA | 2 cluster pair] [prop|nerf]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from hosnerf_b200 import MipNeRF360, synth, _lib
+from hosnerf_b200 import MipNeRF360, synth, _lib, ops
 
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+which = sys.argv[2] if len(sys.argv) > 2 else "nerf"
 dev = "cuda:0"
+ops.set_mlp_variant(variant)
 net = MipNeRF360("/nonexistent", num_levels=2, num_prop_samples=128, num_nerf_samples=128, nerf_netwidth=256,
                  opaque_background=True, precision="fp16")
 synth.fill_params_(net, 0)
 net = net.to(dev)
 b = {k: v.to(dev) for k, v in synth.make_bkg_batch(4096, seed=1).items()}
+lib = _lib.load()
 with torch.no_grad():
     for _ in range(3):
         net(b, 1.0, False, False, 0.1, 1e6)
-    buf = torch.zeros(256, dtype=torch.int64, device=dev)
-    lib = _lib.load()
-    lib.hos_mlp_debug_timeline(buf.data_ptr())
-    # run only the NeRF level's MLP last so its stamps remain: do a full forward, stamps of the last launch (nerf) stay
-    net(b, 1.0, False, False, 0.1, 1e6)
+    buf = torch.zeros(1024, dtype=torch.int64, device=dev)
+    if which == "nerf":
+        lib.hos_mlp_debug_timeline(buf.data_ptr())      # stamps of the last launch (NeRF MLP) remain
+        net(b, 1.0, False, False, 0.1, 1e6)
+    else:
+        mlp = net.mlps[0]
+        _, hist = net(b, 1.0, False, False, 0.1, 1e6)
+        lib.hos_mlp_debug_timeline(buf.data_ptr())
+        sd = hist[0]["sdist"]
+        td = (1.0 / (sd / 1e6 + (1.0 - sd) / 0.1)).contiguous()
+        mlp.eval_samples(td, b["rays_o"], b["rays_d"], b["radii"].reshape(-1).contiguous(), b["viewdirs"], 0.0, "fp16")
     torch.cuda.synchronize()
     lib.hos_mlp_debug_timeline(None)
-t = buf.cpu().view(64, 4)
-t0 = int(t[0, 0])
-print("layer-iter: mma_start  mma_issued  epi_start  epi_end   (cycles, relative) | mma_issue_span  mma->epi_start  epi_span  epi_end->next_mma")
-for i in range(24):
-    a, bb, c, d = [int(x) - t0 for x in t[i]]
-    nxt = int(t[i + 1, 0]) - t0
-    print(f"{i:3d}: {a:8d} {bb:8d} {c:8d} {d:8d} | {bb - a:6d} {c - bb:6d} {d - c:6d} {nxt - d:6d}")
+if variant == 1:
+    t = buf.cpu()[:256].view(64, 4)
+    t0 = int(t[0, 0])
+    print("layer-iter: mma_start  mma_issued  epi_start  epi_end | mma_issue_span  mma->epi_start  epi_span  epi_end->next_mma")
+    for i in range(24):
+        a, bb, c, d = [int(x) - t0 for x in t[i]]
+        nxt = int(t[i + 1, 0]) - t0
+        print(f"{i:3d}: {a:8d} {bb:8d} {c:8d} {d:8d} | {bb - a:6d} {c - bb:6d} {d - c:6d} {nxt - d:6d}")
+else:
+    t = buf.cpu()[:768].view(64, 12)
+    t0 = int(t[0, 0])
+    nl = 4 if which == "prop" else len(net.mlps[-1]._cache["f16"].layers)
+    print("unit(g,l,slot): mma_enter acc_free issued | epi_enter acc_ready epi_done | feat_start feat_end | "
+          "act_wait issue_span w_wait x_wait | epi_wait epi_span | feat_span")
+    for i in range(64):
+        r = [int(x) for x in t[i]]
+        if r[0] == 0:
+            break
+        u, slot = i // 2, i % 2
+        rel = [x - t0 if x else 0 for x in r[:8]]
+        print(f"{i:3d} (g{u // nl} l{u % nl} s{slot}): {rel[0]:8d} {rel[1]:8d} {rel[2]:8d} | {rel[3]:8d} {rel[4]:8d} {rel[5]:8d} | "
+              f"{rel[6]:8d} {rel[7]:8d} | {r[1] - r[0]:6d} {r[2] - r[1]:6d} {r[8]:6d} {r[9]:6d} | {r[4] - r[3]:6d} {r[5] - r[4]:6d} | "
+              f"{(r[7] - r[6]) if r[6] else 0:6d}")
+
+    for base, name in ((768, "unit 21"), (832, "unit 28")):
+        c = buf.cpu()[base:base + 60].view(12, 5)
+        print(name, "chunk: wait_start waited mma4_issued commits_done syncwarp_done (deltas) | period")
+        prev = None
+        for kb in range(12):
+            r = [int(x) for x in c[kb]]
+            if r[0] == 0:
+                break
+            print(f"  kb{kb}: wait {r[1] - r[0]:5d}  mma4 {r[2] - r[1]:5d}  commits {r[3] - r[2]:5d}  sync {r[4] - r[3]:5d} | "
+                  f"{(r[0] - prev) if prev else 0:6d}")
+            prev = r[0]

@@ -227,9 +227,19 @@ def _emulate_fp16_mlp(x, layers, head_w, head_b):
     return h.double() @ head_w.double().T + head_b.double()
 
 
+@pytest.fixture
+def mlp_variant(request):
+    """Forces one of the two tcgen05 MLP kernels (1 = single CTA, 2 = cluster pair) for a test."""
+    ops.set_mlp_variant(request.param)
+    yield request.param
+    ops.set_mlp_variant(0)
+
+
+@pytest.mark.parametrize("mlp_variant", [1, 2], indirect=True)
 @pytest.mark.parametrize("width,depth,in_dim,skip,rows", [(256, 4, 504, None, 1000), (256, 8, 504, 5, 777),
-                                                          (128, 6, 36, 4, 300), (256, 8, 63, 5, 128 * 149 + 5)])
-def test_fused_mlp_tcgen05_vs_emulation(width, depth, in_dim, skip, rows):
+                                                          (128, 6, 36, 4, 300), (256, 8, 63, 5, 128 * 149 + 5),
+                                                          (256, 8, 127, 5, 128 * 600 + 77)])
+def test_fused_mlp_tcgen05_vs_emulation(width, depth, in_dim, skip, rows, mlp_variant):
     gen = torch.Generator().manual_seed(width + depth)
     x = torch.randn(rows, in_dim, generator=gen)
     layers, desc = [], []
@@ -258,6 +268,29 @@ def test_fused_mlp_tcgen05_vs_emulation(width, depth, in_dim, skip, rows):
     for (W, b, sk) in layers:
         h = torch.relu((h if not sk else torch.cat([h, full], -1)) @ W.T + b)
     assert rel_err(out.cpu(), h @ hw.T + hb) < 3e-2
+
+
+def test_pair_kernel_matches_single_cta_kernel_fused_ipe():
+    """The cluster-pair kernel (cta_group::2, two row tiles per SM in ping-pong) and the single-CTA kernel run
+    the same fp16 program: C2 shape with the fused IPE prologue, ray count not a multiple of a 4-tile group."""
+    b = {k: cu(v) for k, v in synth.make_bkg_batch(1031, seed=5).items()}
+    outs = []
+    for variant in (1, 2):
+        ops.set_mlp_variant(variant)
+        try:
+            net = _bkg(num_levels=2, num_prop_samples=128, num_nerf_samples=128, nerf_netwidth=256, precision="fp16")
+            with torch.no_grad():
+                rend, hist = net(b, 1.0, False, False, 0.1, 1e6)
+            torch.cuda.synchronize()
+            outs.append((rend, hist))
+        finally:
+            ops.set_mlp_variant(0)
+    (ra, ha), (rb, hb) = outs
+    d0 = rel_err(hb[0]["density"].cpu(), ha[0]["density"].cpu())
+    print("pair vs single: L0 density rel", d0, "final rgb abs", max_abs(ra[-1]["rgb"].cpu(), rb[-1]["rgb"].cpu()))
+    assert torch.isfinite(hb[-1]["rgb"]).all()
+    assert d0 < 1e-5                       # same operands, same K order: fp32 accumulation-order noise at most
+    assert max_abs(ra[-1]["rgb"].cpu(), rb[-1]["rgb"].cpu()) < 1e-4
 
 
 # ----------------------------------------------------------------------------- human branch
