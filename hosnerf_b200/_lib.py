@@ -66,7 +66,7 @@ SIGNATURES = {
 
 _lib = None
 LAUNCHES = 0          # kernels of this library launched so far (bench.py reports it per timed region)
-_KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_bias": 0, "hos_mlp_set_head": 0,
+_KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_layer": 2, "hos_mlp_set_bias": 1, "hos_mlp_set_head": 0,
                      "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0}
 
 

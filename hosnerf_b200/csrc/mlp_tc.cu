@@ -151,20 +151,55 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Bounded waits for the pair kernel: a protocol bug traps (launch failure) instead of hanging the GPU.
-// Each try_wait sleeps up to kSuspendHintNs in hardware, so the loop body runs a handful of times at most.
+// try_wait returns within a few tens of cycles whether or not a suspend-time hint is given (ncu: 57 % of all
+// executed instructions were polling loops), and every poll takes an issue slot from the epilogue / feature
+// warps on the same scheduler - so waits that are not on the MMA warp's critical path back off with
+// nanosleep between polls.  kSleepNs == 0: pure spin (MMA issuer only).
+template <int kSleepNs>
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  long long t_start = 0;
+  uint32_t polls = 0;
   for (;;) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(a), "r"(parity), "r"(kSuspendHintNs) : "memory");
+        : "=r"(ok) : "r"(a), "r"(parity) : "memory");
     if (ok) return;
-    const long long now = clock64();
-    if (t_start == 0) t_start = now;
-    else if (now - t_start > 4000000000ll) __trap();        // ~2 s: far beyond any legitimate wait
+    if (kSleepNs > 0) asm volatile("nanosleep.u32 %0;" ::"r"((uint32_t)kSleepNs));
+    if (++polls > (kSleepNs > 0 ? (1u << 24) : (1u << 28))) __trap();     // seconds: far beyond any legitimate wait
+  }
+}
+__device__ __forceinline__ void mbar_wait2_spin(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1) {
+  uint32_t polls = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "and.pred p, p, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(a0), "r"(p0), "r"(a1), "r"(p1) : "memory");
+    if (ok) return;
+    if (++polls > (1u << 28)) __trap();
+  }
+}
+// wait until up to three phases have all completed: the polls overlap instead of paying three latencies in a row
+__device__ __forceinline__ void mbar_wait3_spin(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2) {
+  uint32_t polls = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q, r;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 r, [%5], %6;\n\t"
+        "and.pred p, p, q;\n\tand.pred p, p, r;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2) : "memory");
+    if (ok) return;
+    if (++polls > (1u << 28)) __trap();
   }
 }
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {     // arrives on `bar` in BOTH CTAs of the pair
@@ -190,6 +225,25 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {      // explicit ld.shared (a generic LD costs far more latency)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// two fp32 (bit patterns) -> packed fp16x2 (lo = first), optionally with ReLU fused into the conversion
+__device__ __forceinline__ uint32_t cvt_f16x2(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_relu_f16x2(uint32_t lo, uint32_t hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return d;
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -341,7 +395,7 @@ __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRow
         const int p = (jg * kIpeDeg + l) * kJGroup + jj;   // pair index; columns 2p, 2p+1
         if ((p & 31) == 0) {                               // first pair of a 64-column chunk: acquire a slot
           const int xs = xi % kStg;
-          if (kWarpArrive) mbar_wait_guard(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
+          if (kWarpArrive) mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
           else mbar_wait(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
           slot = sRingX + xs * kXChunkBytes;
         }
@@ -632,64 +686,84 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
 // ============================================================================ cluster-pair kernel
 // Two CTAs (one cluster, two SMs) run every layer as ONE tcgen05.mma.cta_group::2 of M = 256 rows:
 // CTA r owns rows [128 r, 128 r + 128) of the A operand and of the accumulator (its own TMEM) and stages
-// only output columns [N/2 r, N/2 r + N/2) of every weight chunk, so each SM pulls half the weight bytes
-// through L2 and a ring stage is 16 KB instead of 32 KB.  That is what makes room for TWO 128-row tiles
-// per CTA ("slots"), whose layers are interleaved  (s0,l) (s1,l) (s0,l+1) ...  : while the tensor core
-// runs slot 1's layer, the epilogue warps drain slot 0's accumulator and write its next A operand, so
-// the MMA pipe only idles when an epilogue is slower than the other slot's MMAs.
+// only output columns [N/2 r, N/2 r + N/2) of every weight chunk.  Each SM therefore pulls half the
+// weight bytes through L2 and a ring stage is 16 KB instead of 32 KB, which buys a 7-deep weight ring:
+// the refill latency of a stage (MMA retire -> producer wake -> L2 -> peer relay) is ~2.5-3.5 k cycles,
+// several times the 512 cycles a chunk lasts on the tensor core, so a 3-deep ring left the MMA warp
+// waiting ~400 cycles per chunk (timeline in profiles/).
 //
-// Measured building blocks (scripts/ubench_tc.cu, B200): tcgen05.ld sustains ~900 B/clk/SM (a 128 x 256
-// fp32 tile drains in ~340 cycles; with bias/ReLU/fp16 pack/st.shared ~1.1 k cycles on 8 warps); M=256
-// N=256 K=16 cta_group::2 issues every 128 cycles; ONE thread's bulk copies complete one mbarrier phase
-// per ~800 cycles regardless of size, but separate warps overlap - hence one producer warp per ring stage.
+// Layers of one tile are dependent, so MMA and epilogue overlap at CHUNK granularity instead: the
+// accumulator is double-buffered in TMEM (layer u -> columns 256 (u & 1)), the epilogue drains it 64
+// columns at a time and signals each finished K-chunk of the next A operand separately; the MMA warp
+// starts layer u + 1 on chunk 0 while the epilogue is still converting chunks 1..3 of layer u.  The
+// first layer of a tile reads only generated features, so it also overlaps the previous tile's last
+// epilogue.
 //
-// Warp roles (both CTAs unless noted): 0, 2, 3 weight producers (stage = their index; in the peer CTA
-// they also relay "my half has landed" to the leader), 1 MMA issuer (leader CTA only) + TMEM alloc,
-// 4-11 epilogue, 12-15 feature generators.  Barriers that collect arrivals from both CTAs live in the
-// leader; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
-constexpr int kPairStagesW = 3;
+// Measured building blocks (scripts/ubench_tc.cu, B200): tcgen05.ld sustains ~900 B/clk/SM; M=256 N=256
+// K=16 cta_group::2 issues every 128 cycles (issue blocks while the pipe is busy: anything the MMA warp
+// does between MMAs - waits, commits - idles the tensor core); ONE thread's bulk copies complete one
+// mbarrier phase per ~800 cycles regardless of size while separate warps overlap - hence three producer
+// warps.
+//
+// Warp roles (both CTAs unless noted): 0, 2, 3 weight producers (chunk i -> producer i % 3, stage i % S;
+// in the peer CTA they also relay "my half has landed" to the leader), 1 MMA issuer (leader CTA only)
+// + TMEM alloc, 4-11 epilogue, 12-15 feature generators.  Barriers that collect arrivals from both CTAs
+// live in the leader; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
+constexpr int kPairMaxStagesW = 8;
 constexpr int kPairStagesX = 2;
-constexpr int kPairBars = 3 * kPairStagesW + 3 * kPairStagesX + 4;
+constexpr int kPairProducers = 3;
+constexpr int kPairMaxKbh = 4;
+constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 2 + kPairMaxKbh;
+static_assert(kPairBars % 2 == 0, "s_headx behind the barriers is read as float4");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
-                const __grid_constant__ IpeArgs ipe) {
+                const __grid_constant__ IpeArgs ipe, const int stages_w) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int h_bytes = prog.kbh * kXChunkBytes;             // one slot's activations
   const int w_stage_bytes = prog.n_max * 64;               // this CTA's half of an [n_max x 64] fp16 chunk
-  unsigned char* sH = smem;                                // [2 slots][kbh][16 KB]
-  unsigned char* sRingW = sH + 2 * h_bytes;                // [kPairStagesW][w_stage_bytes]
-  unsigned char* sRingX = sRingW + kPairStagesW * w_stage_bytes;   // [kPairStagesX][16 KB]
+  unsigned char* sH = smem;                                // [kbh][16 KB] activations (A operand of the next layer)
+  unsigned char* sOnes = sH + prog.kbh * kXChunkBytes;     // [16 KB] constant A chunk: columns 0, 1 = 1.0 (bias as a rank-2 update)
+  unsigned char* sRingW = sOnes + kXChunkBytes;            // [stages_w][w_stage_bytes]
+  unsigned char* sRingX = sRingW + stages_w * w_stage_bytes;       // [kPairStagesX][16 KB]
   float* sParams = reinterpret_cast<float*>(sRingX + kPairStagesX * kXChunkBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((prog.param_floats + 3) & ~3));
-  uint64_t* bar_wfull = bars;                              // [3] this CTA's half landed (tx bytes)
-  uint64_t* bar_wpeer = bar_wfull + kPairStagesW;          // [3] leader only: the peer's half landed
-  uint64_t* bar_wempty = bar_wpeer + kPairStagesW;         // [3] multicast commit: stage consumed
-  uint64_t* bar_xfull = bar_wempty + kPairStagesW;         // [2] leader: own feature chunk written / landed
-  uint64_t* bar_xpeer = bar_xfull + kPairStagesX;          // [2] leader only: the peer's feature chunk
-  uint64_t* bar_xempty = bar_xpeer + kPairStagesX;         // [2] multicast commit
-  uint64_t* bar_tfull = bar_xempty + kPairStagesX;         // [2 slots] multicast commit: accumulator ready
-  uint64_t* bar_act = bar_tfull + 2;                       // [2 slots] leader only: 16 epilogue warps done
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kPairBars + 1);
-  float* s_headx = reinterpret_cast<float*>(s_tmem + 4);   // [128][4]
+  uint64_t* bar_wfull = bars;                              // [S] leader: both halves landed (own tx bytes + the peer's relay
+                                                           //     arrive); peer: its own half landed
+  uint64_t* bar_wempty = bar_wfull + kPairMaxStagesW;      // [S] multicast commit: stage consumed
+  uint64_t* bar_xfull = bar_wempty + kPairMaxStagesW;      // [2] leader: feature chunk complete in BOTH CTAs (fused: one arrive
+                                                           //     per feature warp of the pair; else own tx bytes + relay)
+  uint64_t* bar_xempty = bar_xfull + kPairStagesX;         // [2] multicast commit
+  uint64_t* bar_tfull = bar_xempty + kPairStagesX;         // [2 accumulator buffers] multicast commit
+  uint64_t* bar_hready = bar_tfull + 2;                    // [kbh] leader only: K-chunk c of the next A operand written by
+                                                           //       the 16 epilogue warps of the pair
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kPairBars);       // kPairBars is even: 16-byte aligned
+  float* s_headx = reinterpret_cast<float*>(s_tmem + 4);   // [128][4], read as float4
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool fused = args.fused_ipe != 0;
   const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int n_groups = (args.ntiles + 3) >> 2;             // 4 tiles per group: tile = 4 g + 2 slot + rank
+  const int n_groups = (args.ntiles + 1) >> 1;             // 2 tiles per group: tile = 2 g + rank
   const int n_layers = prog.n_layers;
+  const uint32_t S = (uint32_t)stages_w;
 
   for (int i = threadIdx.x; i < prog.param_floats; i += kMlpThreads) sParams[i] = args.params[i];
+  // Bias: every layer's weight stream ends with one extra chunk whose K-columns 0 / 1 hold fp16 hi / lo parts of
+  // the bias; multiplied by this constant operand it lands in the accumulator, so the epilogue adds nothing.
+  for (int i = threadIdx.x; i < kXChunkBytes / 16; i += kMlpThreads) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x < kTileM) *reinterpret_cast<uint32_t*>(sOnes + tile_byte_offset(threadIdx.x, 0)) = 0x3c003c00u;   // (1.0h, 1.0h)
+  fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kPairStagesW; ++s) { mbar_init(&bar_wfull[s], 1); mbar_init(&bar_wpeer[s], 1); mbar_init(&bar_wempty[s], 1); }
+    const uint32_t both = rank == 0 ? 2u : 1u;             // the leader's barriers also count the peer
+    for (int s = 0; s < kPairMaxStagesW; ++s) { mbar_init(&bar_wfull[s], both); mbar_init(&bar_wempty[s], 1); }
     for (int s = 0; s < kPairStagesX; ++s) {
-      mbar_init(&bar_xfull[s], fused ? 4 : 1);
-      mbar_init(&bar_xpeer[s], fused ? 4 : 1);
+      mbar_init(&bar_xfull[s], fused ? 8 : both);
       mbar_init(&bar_xempty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_act[s], 2 * kEpiWarps); }
+    for (int s = 0; s < 2; ++s) mbar_init(&bar_tfull[s], 1);
+    for (int s = 0; s < kPairMaxKbh; ++s) mbar_init(&bar_hready[s], 2 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -703,42 +777,46 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == 0 || warp == 2 || warp == 3) {
-    // ===================== weight producers: warp p owns ring stage p =====================
+    // ===================== weight producers: chunk i -> producer i % 3, ring stage i % S =====================
     if (lane == 0) {
       const uint32_t p = warp == 0 ? 0u : (uint32_t)(warp - 1);
       uint32_t wi = 0, xi = 0;
       for (int g = cluster; g < n_groups; g += n_clusters) {
+        int tile = 2 * g + (int)rank;
+        if (tile >= args.ntiles) tile = args.ntiles - 1;            // padding tile: any valid rows, outputs masked
         for (int l = 0; l < n_layers; ++l) {
           const LayerDev L = prog.layers[l];
           const uint32_t half_bytes = (uint32_t)L.n * 64u;
           const int nkb = L.kb_h + L.kb_x;
-          for (int slot = 0; slot < 2; ++slot) {
-            for (int kb = 0; kb < nkb; ++kb, ++wi) {
-              const bool from_x = kb >= L.kb_h;
-              const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
-              if (from_x) ++xi;
-              if (wi % kPairStagesW != p) continue;
-              const uint32_t use = wi / kPairStagesW;
-              mbar_wait_guard(&bar_wempty[p], (use & 1) ^ 1);
-              mbar_expect_tx(&bar_wfull[p], half_bytes);
-              bulk_g2s(sRingW + p * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * (2u * half_bytes) + rank * half_bytes,
-                       half_bytes, &bar_wfull[p]);
-              const bool load_x = from_x && !fused;
+          for (int kb = 0; kb <= nkb; ++kb, ++wi) {            // chunk nkb: the bias chunk
+            const bool from_x = kb >= L.kb_h && kb < nkb;
+            const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
+            if (from_x) ++xi;
+            // un-fused input: the 2-deep X ring is filled by ONE thread in order (a barrier waiter must never
+            // be two phases ahead, which independent producers on a 2-stage ring could be)
+            const bool load_x = from_x && !fused && p == 0;
+            if (load_x) {
+              mbar_wait_guard<100>(&bar_xempty[xs], (xuse & 1) ^ 1);
+              mbar_expect_tx(&bar_xfull[xs], kXChunkBytes);
+              bulk_g2s(sRingX + xs * kXChunkBytes, args.x_tiled + ((size_t)tile * prog.kbx + (kb - L.kb_h)) * kXChunkBytes,
+                       kXChunkBytes, &bar_xfull[xs]);
+            }
+            const bool load_w = wi % kPairProducers == p;
+            const uint32_t ws = wi % S, use = wi / S;
+            if (load_w) {
+              mbar_wait_guard<100>(&bar_wempty[ws], (use & 1) ^ 1);
+              mbar_expect_tx(&bar_wfull[ws], half_bytes);
+              bulk_g2s(sRingW + ws * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * (2u * half_bytes) + rank * half_bytes,
+                       half_bytes, &bar_wfull[ws]);
+            }
+            if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
               if (load_x) {
-                int tile = 4 * g + 2 * slot + (int)rank;
-                if (tile >= args.ntiles) tile = args.ntiles - 1;          // padding tile: any valid rows, outputs masked
-                mbar_wait_guard(&bar_xempty[xs], (xuse & 1) ^ 1);
-                mbar_expect_tx(&bar_xfull[xs], kXChunkBytes);
-                bulk_g2s(sRingX + xs * kXChunkBytes, args.x_tiled + ((size_t)tile * prog.kbx + (kb - L.kb_h)) * kXChunkBytes,
-                         kXChunkBytes, &bar_xfull[xs]);
+                mbar_wait_guard<100>(&bar_xfull[xs], xuse & 1);
+                mbar_arrive_remote(mapa_u32(smem_u32(&bar_xfull[xs]), 0));
               }
-              if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
-                mbar_wait_guard(&bar_wfull[p], use & 1);
-                mbar_arrive_remote(mapa_u32(smem_u32(&bar_wpeer[p]), 0));
-                if (load_x) {
-                  mbar_wait_guard(&bar_xfull[xs], xuse & 1);
-                  mbar_arrive_remote(mapa_u32(smem_u32(&bar_xpeer[xs]), 0));
-                }
+              if (load_w) {
+                mbar_wait_guard<100>(&bar_wfull[ws], use & 1);
+                mbar_arrive_remote(mapa_u32(smem_u32(&bar_wfull[ws]), 0));
               }
             }
           }
@@ -746,107 +824,153 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA) =====================
-    if (rank == 0) {
-      uint32_t wi = 0, xi = 0;
-      int gi = 0;
-      for (int g = cluster; g < n_groups; g += n_clusters, ++gi) {
-        for (int l = 0; l < n_layers; ++l) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    // tcgen05.mma issue blocks while the pipe is busy (queue depth ~1), so every cycle this thread spends between
+    // MMAs is a cycle the tensor core idles: one lane, both barriers of a chunk polled together, descriptors
+    // advanced by integer adds, no instrumentation inside the chunk loop.
+    if (rank == 0 && lane == 0) {
+      uint32_t wi = 0, xi = 0, u = 0, hq = 0;        // chunk / feature-chunk / unit counters; hq = units that read H so far
+      const uint64_t desc_hi = umma_desc(0);
+      for (int g = cluster; g < n_groups; g += n_clusters) {
+        for (int l = 0; l < n_layers; ++l, ++u) {
           const LayerDev L = prog.layers[l];
           const uint32_t idesc = umma_idesc_f16(L.n, 2 * kTileM);
           const int nkb = L.kb_h + L.kb_x;
-          for (int slot = 0; slot < 2; ++slot) {
-            // unit (slot, l) needs the epilogue of this slot's previous unit in BOTH CTAs: activations
-            // written (l > 0) and the accumulator drained (also across groups for l == 0)
-            const uint32_t u = (uint32_t)gi * n_layers + l;
-            const uint32_t seq = 2 * u + slot;
-            const bool tl = args.timeline && blockIdx.x == 0 && lane == 0 && seq < 64;
-            long long wsum = 0, xsum = 0;
-            if (tl) args.timeline[seq * 12 + 0] = clock64();
-            if (u > 0) mbar_wait_guard(&bar_act[slot], (u - 1) & 1);
-            tc_fence_after();
-            if (tl) args.timeline[seq * 12 + 1] = clock64();
-            const uint32_t acc = tmem_base + slot * 256;
-            for (int kb = 0; kb < nkb; ++kb, ++wi) {
-              const uint32_t ws = wi % kPairStagesW, use = wi / kPairStagesW;
-              const bool from_x = kb >= L.kb_h;
-              const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
-              long long c0 = tl ? clock64() : 0;
-              mbar_wait_guard(&bar_wfull[ws], use & 1);
-              mbar_wait_guard(&bar_wpeer[ws], use & 1);
-              long long c1 = tl ? clock64() : 0;
-              if (from_x) {
-                mbar_wait_guard(&bar_xfull[xs], xuse & 1);
-                mbar_wait_guard(&bar_xpeer[xs], xuse & 1);
-              }
-              if (tl) { wsum += c1 - c0; xsum += clock64() - c1; }
-              tc_fence_after();
-              const bool tl2 = tl && (seq == 21 || seq == 28) && kb < 12;      // chunk-level stamps of two units
-              long long* t2 = args.timeline + 768 + (seq == 28 ? 64 : 0) + kb * 5;
-              if (tl2) { t2[0] = c0; t2[1] = clock64(); }
-              if (lane == 0) {
-                const uint32_t a_base = smem_u32(from_x ? sRingX + xs * kXChunkBytes : sH + slot * h_bytes + kb * kXChunkBytes);
-                const uint32_t b_base = smem_u32(sRingW + ws * w_stage_bytes);
-#pragma unroll
-                for (int k = 0; k < kKB / 16; ++k)
-                  tc_mma_f16_pair(acc, umma_desc(a_base + k * 32), umma_desc(b_base + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
-                if (tl2) t2[2] = clock64();
-                tc_commit_pair(&bar_wempty[ws]);
-                if (from_x) tc_commit_pair(&bar_xempty[xs]);
-                if (kb == nkb - 1) tc_commit_pair(&bar_tfull[slot]);
-                if (tl2) t2[3] = clock64();
-              }
-              __syncwarp();
-              if (tl2) t2[4] = clock64();
-              if (from_x) ++xi;
+          const uint32_t acc = tmem_base + (u & 1) * 256;
+          const bool tl = args.timeline && blockIdx.x == 0 && u < 64;
+          long long wsum = 0, osum = 0;
+          if (tl) args.timeline[u * 12 + 0] = clock64();
+          // Accumulator buffer (u & 1) was last read by the epilogue of unit u - 2, which finished before it
+          // signalled the last H chunk that unit u - 1 waited for; H chunk kb is overwritten by the epilogue of
+          // unit u only after all MMAs of unit u retired (tfull).
+          for (int kb = 0; kb < nkb; ++kb, ++wi) {
+            const uint32_t ws = wi % S, use = wi / S;
+            const bool from_x = kb >= L.kb_h;
+            const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
+            // weights of both halves + (features of both CTAs | the previous layer's K-chunk kb)
+            if (tl) {       // instrumented CTA only: split the wait into weights / operand
+              const long long c0 = clock64();
+              mbar_wait_guard<0>(&bar_wfull[ws], use & 1);
+              const long long c1 = clock64();
+              mbar_wait_guard<0>(from_x ? &bar_xfull[xs] : &bar_hready[kb], from_x ? (xuse & 1) : (hq & 1));
+              wsum += c1 - c0; osum += clock64() - c1;
+            } else {
+              mbar_wait2_spin(smem_u32(&bar_wfull[ws]), use & 1,
+                              smem_u32(from_x ? &bar_xfull[xs] : &bar_hready[kb]), from_x ? (xuse & 1) : (hq & 1));
             }
-            if (tl) { args.timeline[seq * 12 + 2] = clock64(); args.timeline[seq * 12 + 8] = wsum; args.timeline[seq * 12 + 9] = xsum; }
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(from_x ? sRingX + xs * kXChunkBytes : sH + kb * kXChunkBytes);
+            const uint32_t b_base = smem_u32(sRingW + ws * w_stage_bytes);
+            const uint64_t adesc = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
+            const uint64_t bdesc = desc_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
+#pragma unroll
+            for (int k = 0; k < kKB / 16; ++k)
+              tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_pair(&bar_wempty[ws]);
+            if (from_x) { tc_commit_pair(&bar_xempty[xs]); ++xi; }
           }
+          {   // bias chunk: ones (columns 0, 1 of the constant operand) x (hi, lo) -> one K = 16 MMA
+            const uint32_t ws = wi % S, use = wi / S;
+            mbar_wait_guard<0>(&bar_wfull[ws], use & 1);
+            tc_fence_after();
+            const uint64_t adesc = desc_hi | (uint64_t)((smem_u32(sOnes) >> 4) & 0x3FFF);
+            const uint64_t bdesc = desc_hi | (uint64_t)((smem_u32(sRingW + ws * w_stage_bytes) >> 4) & 0x3FFF);
+            tc_mma_f16_pair(acc, adesc, bdesc, idesc, 1u);
+            tc_commit_pair(&bar_wempty[ws]);
+            tc_commit_pair(&bar_tfull[u & 1]);
+            ++wi;
+          }
+          if (L.kb_h) ++hq;
+          if (tl) { args.timeline[u * 12 + 1] = clock64(); args.timeline[u * 12 + 8] = wsum; args.timeline[u * 12 + 9] = osum; }
         }
       }
     }
   } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
-    // ===================== epilogue (8 warps): 2 warps per TMEM lane quarter, half the columns each ============
+    // ===================== epilogue (8 warps): 2 warps per TMEM lane quarter; K-chunk c of the output is columns
+    // [64 c, 64 c + 64): warp half `ch` converts its 32 of them, then signals the chunk ============
     const int q = warp & 3;
     const int ch = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
-    const uint32_t act_addr0 = mapa_u32(smem_u32(&bar_act[0]), 0);
-    int gi = 0;
-    for (int g = cluster; g < n_groups; g += n_clusters, ++gi) {
-      for (int l = 0; l < n_layers; ++l) {
+    const uint32_t hready0 = mapa_u32(smem_u32(&bar_hready[0]), 0);
+    const uint32_t sparams_u32 = smem_u32(sParams);
+    const uint32_t headx_u32 = smem_u32(s_headx) + 16u * r;
+    // this thread's 16-byte slots in a K-chunk of H: row r, 16-byte groups 4 ch .. 4 ch + 3 (128B swizzle)
+    const uint32_t h_row = smem_u32(sH) + 128u * r;
+    uint32_t h_off[4];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) h_off[gq] = h_row + ((uint32_t)((4 * ch + gq) ^ (r & 7)) << 4);
+    uint32_t u = 0;
+    for (int g = cluster; g < n_groups; g += n_clusters) {
+      const int tile = 2 * g + (int)rank;
+      const int64_t row = (int64_t)tile * kTileM + r;
+      const bool row_ok = row < args.rows;
+      for (int l = 0; l < n_layers; ++l, ++u) {
         const LayerDev L = prog.layers[l];
         const bool last = (l == n_layers - 1);
         const bool has_head = L.head >= 0;
-        const HeadDev Hd = prog.heads[has_head ? L.head : 0];
-        const int nh = L.n >> 1;
-        const int cbeg = ch * nh, cend = cbeg + nh;
-        for (int slot = 0; slot < 2; ++slot) {
-          const int tile = 4 * g + 2 * slot + (int)rank;
-          const int64_t row = (int64_t)tile * kTileM + r;
-          const bool row_ok = row < args.rows;
-          const uint32_t u = (uint32_t)gi * n_layers + l;
-          const uint32_t acc = tmem_base + slot * 256 + ((uint32_t)(q * 32) << 16);
-          unsigned char* sHs = sH + slot * h_bytes;
+        const bool relu = L.relu != 0;
+        const int nchunks = L.n >> 6;
+        const uint32_t acc = tmem_base + (u & 1) * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && u < 64;
+        if (tl) args.timeline[u * 12 + 3] = clock64();
+        mbar_wait_guard<20>(&bar_tfull[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        if (tl) args.timeline[u * 12 + 4] = clock64();
+
+        // chunk c done: its 32 columns of this warp are in shared memory -> tell the MMA warp (leader CTA)
+        auto chunk_ready = [&](int c) {
+          fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
+          tc_fence_before();          // TMEM loads of this chunk ordered before the arrive
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(hready0 + 8u * c);
+        };
+
+        if (!has_head && !last && !(L.rowbias && args.rowbias)) {
+          // ---------- plain hidden layer (bias already in the accumulator): convert (+ ReLU) and store, nothing else.
+          // Two TMEM loads in flight: the next chunk's 32 columns arrive while these are converted.
+          auto store32 = [&](const uint32_t (&v)[32], int c) {
+            const uint32_t cb = (uint32_t)c * kXChunkBytes;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint32_t p0, p1, p2, p3;
+              if (relu) {
+                p0 = cvt_relu_f16x2(v[gq * 8 + 0], v[gq * 8 + 1]); p1 = cvt_relu_f16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                p2 = cvt_relu_f16x2(v[gq * 8 + 4], v[gq * 8 + 5]); p3 = cvt_relu_f16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
+              } else {
+                p0 = cvt_f16x2(v[gq * 8 + 0], v[gq * 8 + 1]); p1 = cvt_f16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                p2 = cvt_f16x2(v[gq * 8 + 4], v[gq * 8 + 5]); p3 = cvt_f16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
+              }
+              sts128(h_off[gq] + cb, p0, p1, p2, p3);
+            }
+          };
+          uint32_t va[32], vb[32];
+          tmem_ld32_nowait(acc, va);
+          for (int c = 0; c < nchunks; c += 2) {
+            tmem_wait_ld();
+            const bool more1 = c + 1 < nchunks;
+            if (more1) tmem_ld32_nowait(acc + (uint32_t)((c + 1) * 64), vb);
+            store32(va, c);
+            chunk_ready(c);
+            if (more1) {
+              tmem_wait_ld();
+              if (c + 2 < nchunks) tmem_ld32_nowait(acc + (uint32_t)((c + 2) * 64), va);
+              store32(vb, c + 1);
+              chunk_ready(c + 1);
+            }
+          }
+        } else {
+          // ---------- general layer: per-row bias, fp32 output head, last layer (no activations stored)
+          const HeadDev Hd = prog.heads[has_head ? L.head : 0];
           const float* rb = (L.rowbias && args.rowbias && row_ok) ? args.rowbias + (row / args.rowbias_div) * L.n : nullptr;
           float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-          const uint32_t seq = 2 * u + slot;
-          const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && seq < 64;
-          if (tl) args.timeline[seq * 12 + 3] = clock64();
-          mbar_wait_guard(&bar_tfull[slot], u & 1);
-          tc_fence_after();
-          if (tl) args.timeline[seq * 12 + 4] = clock64();
-
-          auto process32 = [&](uint32_t (&v)[32], int c0) {
+          for (int c = 0; c < nchunks; ++c) {
+            const int c0 = c * 64 + ch * 32;
+            uint32_t v[32];
+            tmem_ld32_nowait(acc + (uint32_t)(c * 64), v);
+            tmem_wait_ld();
             float f[32];
-            const float4* b4 = reinterpret_cast<const float4*>(sParams + L.bias_off + c0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = b4[j];
-              f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bb.x;
-              f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bb.y;
-              f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bb.z;
-              f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bb.w;
-            }
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             if (rb) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -854,7 +978,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                 f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
               }
             }
-            if (L.relu) {
+            if (relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
@@ -862,11 +986,11 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
 #pragma unroll
               for (int n = 0; n < 4; ++n) {
                 if (n < Hd.hn) {
-                  const float4* w4 = reinterpret_cast<const float4*>(sParams + Hd.w_off + n * L.n + c0);
+                  const uint32_t w4 = sparams_u32 + 4u * (uint32_t)(Hd.w_off + n * L.n + c0);
                   float a = hacc[n];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
-                    const float4 w = w4[j];
+                    const float4 w = lds128(w4 + 16u * j);
                     a = fmaf(f[4 * j + 0], w.x, a); a = fmaf(f[4 * j + 1], w.y, a);
                     a = fmaf(f[4 * j + 2], w.z, a); a = fmaf(f[4 * j + 3], w.w, a);
                   }
@@ -875,50 +999,30 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
               }
             }
             if (!last) {
-              unsigned char* dst = sHs + (c0 >> 6) * kXChunkBytes;
-              const int kk = c0 & 63;
+              const uint32_t cb = (uint32_t)c * kXChunkBytes;
 #pragma unroll
-              for (int gq = 0; gq < 4; ++gq) {
-                __half2 h0 = __floats2half2_rn(f[gq * 8 + 0], f[gq * 8 + 1]);
-                __half2 h1 = __floats2half2_rn(f[gq * 8 + 2], f[gq * 8 + 3]);
-                __half2 h2 = __floats2half2_rn(f[gq * 8 + 4], f[gq * 8 + 5]);
-                __half2 h3 = __floats2half2_rn(f[gq * 8 + 6], f[gq * 8 + 7]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(dst + tile_byte_offset(r, kk + gq * 8)) = pk;
-              }
-            }
-          };
-
-          // two TMEM loads in flight: the next 32 columns arrive while these are converted
-          uint32_t va[32], vb[32];
-          tmem_ld32_nowait(acc + (uint32_t)cbeg, va);
-          for (int c0 = cbeg; c0 < cend; c0 += 64) {
-            tmem_wait_ld();
-            const bool more1 = c0 + 32 < cend;
-            if (more1) tmem_ld32_nowait(acc + (uint32_t)(c0 + 32), vb);
-            process32(va, c0);
-            if (more1) {
-              tmem_wait_ld();
-              if (c0 + 64 < cend) tmem_ld32_nowait(acc + (uint32_t)(c0 + 64), va);
-              process32(vb, c0 + 32);
+              for (int gq = 0; gq < 4; ++gq)
+                sts128(h_off[gq] + cb, cvt_f16x2(__float_as_uint(f[gq * 8 + 0]), __float_as_uint(f[gq * 8 + 1])),
+                       cvt_f16x2(__float_as_uint(f[gq * 8 + 2]), __float_as_uint(f[gq * 8 + 3])),
+                       cvt_f16x2(__float_as_uint(f[gq * 8 + 4]), __float_as_uint(f[gq * 8 + 5])),
+                       cvt_f16x2(__float_as_uint(f[gq * 8 + 6]), __float_as_uint(f[gq * 8 + 7])));
+              chunk_ready(c);
             }
           }
-
+          if (last) tc_fence_before();
           if (has_head) {                         // combine the two column halves, then post-process
-            if (ch == 1) *reinterpret_cast<float4*>(s_headx + r * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+            if (ch == 1) sts128(headx_u32, __float_as_uint(hacc[0]), __float_as_uint(hacc[1]), __float_as_uint(hacc[2]), __float_as_uint(hacc[3]));
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
             if (ch == 0 && row_ok) {
-              const float4 o4 = *reinterpret_cast<const float4*>(s_headx + r * 4);
+              const float4 o4 = lds128(headx_u32);
               hacc[0] += o4.x; hacc[1] += o4.y; hacc[2] += o4.z; hacc[3] += o4.w;
+              const float4 hb = lds128(sparams_u32 + 4u * Hd.b_off);
+              const float hbias[4] = {hb.x, hb.y, hb.z, hb.w};
               float* o = args.out[Hd.slot] + row * Hd.hn;
 #pragma unroll
               for (int n = 0; n < 4; ++n) {
                 if (n >= Hd.hn) break;
-                float x = hacc[n] + sParams[Hd.b_off + n];
+                float x = hacc[n] + hbias[n];
                 if (Hd.post == 1) {
                   float z = x + Hd.shift;
                   x = z > 20.f ? z : log1pf(expf(z));
@@ -934,33 +1038,25 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
           }
-          fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
-          tc_fence_before();          // TMEM loads ordered before the arrive
-          __syncwarp();
-          if (lane == 0) mbar_arrive_remote(act_addr0 + 8u * slot);
-          if (tl) args.timeline[seq * 12 + 5] = clock64();
         }
+        if (tl) args.timeline[u * 12 + 5] = clock64();
       }
     }
   } else if (fused && warp >= kFeatWarp0) {
     // ===================== feature generators (warps 12..15): fused IPE prologue =====================
     const int r = (warp - kFeatWarp0) * 32 + lane;
-    const uint32_t xremote = rank != 0 ? mapa_u32(smem_u32(&bar_xpeer[0]), 0) : 0u;
-    uint32_t xi = 0;
-    int gi = 0;
-    for (int g = cluster; g < n_groups; g += n_clusters, ++gi) {
-      for (int l = 0; l < n_layers; ++l) {
+    const uint32_t xremote = rank != 0 ? mapa_u32(smem_u32(&bar_xfull[0]), 0) : 0u;
+    uint32_t xi = 0, u = 0;
+    for (int g = cluster; g < n_groups; g += n_clusters) {
+      const int64_t row = (int64_t)(2 * g + (int)rank) * kTileM + r;
+      for (int l = 0; l < n_layers; ++l, ++u) {
         if (prog.layers[l].kb_x == 0) continue;
-        for (int slot = 0; slot < 2; ++slot) {
-          const int64_t row = (int64_t)(4 * g + 2 * slot + (int)rank) * kTileM + r;
-          const uint32_t seq = 2 * ((uint32_t)gi * n_layers + l) + slot;
-          const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kFeatWarp0 * 32 && seq < 64;
-          if (tl) args.timeline[seq * 12 + 6] = clock64();
-          IpeRowGeom G;
-          ipe_row_setup(ipe, row, row < args.rows, G);
-          ipe_generate_pass<kPairStagesX, true>(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi, xremote);
-          if (tl) args.timeline[seq * 12 + 7] = clock64();
-        }
+        const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kFeatWarp0 * 32 && u < 64;
+        if (tl) args.timeline[u * 12 + 6] = clock64();
+        IpeRowGeom G;
+        ipe_row_setup(ipe, row, row < args.rows, G);
+        ipe_generate_pass<kPairStagesX, true>(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi, xremote);
+        if (tl) args.timeline[u * 12 + 7] = clock64();
       }
     }
   }
@@ -1006,6 +1102,21 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h,
   *reinterpret_cast<__half*>(dst + (size_t)kb * N * 128 + tile_byte_offset(n, kk)) = __float2half_rn(v);
 }
 
+// Bias chunk of a layer (cluster-pair kernel): an [N x 64] fp16 chunk whose K-columns 0 / 1 hold the fp16 hi / lo
+// parts of b[n] (hi + lo reproduces the fp32 bias to ~2^-22); b == nullptr: all zero.
+__global__ void pack_bias_chunk_kernel(const float* __restrict__ b, int N, unsigned char* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * kKB) return;
+  const int n = i / kKB, kk = i % kKB;
+  __half v = __float2half_rn(0.f);
+  if (b && kk < 2) {
+    const float x = b[n];
+    const __half hi = __float2half_rn(x);
+    v = kk == 0 ? hi : __float2half_rn(x - __half2float(hi));
+  }
+  *reinterpret_cast<__half*>(dst + tile_byte_offset(n, kk)) = v;
+}
+
 // X fp32 [rows, ld] (first K columns) -> tiled fp16 [ntiles][kbx][16 KB], zero padded.
 __global__ void pack_rows_kernel(const float* __restrict__ X, int64_t rows, int ld, int K, int kbx,
                                  unsigned char* __restrict__ dst, int64_t total) {
@@ -1034,6 +1145,7 @@ struct hos_mlp {
   size_t w_bytes = 0;
   size_t smem_bytes = 0;
   size_t smem_pair = 0;    // shared memory of the cluster-pair kernel; 0: this program only runs on mlp_tc_kernel
+  int pair_stages = 0;     // depth of its weight ring
   int max_clusters = 0;    // co-resident 2-CTA clusters (persistent grid of the pair kernel)
   int ipe_perm = 0;        // weights packed for the fused-IPE column order
 };
@@ -1080,7 +1192,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
     D.head = (int8_t)L.head;
     D.w_off = woff;
     D.bias_off = poff;                      // multiples of 16 floats: the epilogue reads float4
-    woff += (uint32_t)(D.kb_h + D.kb_x) * D.n * 128u;
+    woff += (uint32_t)(D.kb_h + D.kb_x + 1) * D.n * 128u;   // + the bias chunk read by the cluster-pair kernel
     poff += D.n;
     if (l < n_layers - 1 && L.out_dim > width) width = L.out_dim;
     if (L.out_dim > nmax) nmax = L.out_dim;
@@ -1121,9 +1233,15 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   // TMEM loads), two activation slots + half-width weight stages must fit
   bool pair_ok = true;
   for (int l = 0; l < n_layers; ++l) pair_ok = pair_ok && (layers[l].out_dim % 64) == 0;
-  const size_t smem_pair = 1024 + 2 * (size_t)P.kbh * kXChunkBytes + (size_t)kPairStagesW * nmax * 64 +
-                           (size_t)kPairStagesX * kXChunkBytes + (((size_t)poff + 3) & ~(size_t)3) * 4 +
-                           (kPairBars + 1) * 8 + 16 + kTileM * 4 * sizeof(float);
+  for (int l = 0; l + 1 < n_layers; ++l) pair_ok = pair_ok && layers[l].out_dim == P.kbh * kKB;   // one hready phase count
+  pair_ok = pair_ok && P.kbh <= kPairMaxKbh;
+  const size_t pair_fixed = 1024 + (size_t)(P.kbh + 1) * kXChunkBytes + (size_t)kPairStagesX * kXChunkBytes +
+                            (((size_t)poff + 3) & ~(size_t)3) * 4 + (kPairBars + 1) * 8 + 16 + kTileM * 4 * sizeof(float);
+  int pair_stages = pair_fixed < 227 * 1024 ? (int)((227 * 1024 - pair_fixed) / ((size_t)nmax * 64)) : 0;
+  if (pair_stages > kPairMaxStagesW) pair_stages = kPairMaxStagesW;
+  pair_ok = pair_ok && pair_stages >= 3;
+  const size_t smem_pair = pair_fixed + (size_t)pair_stages * nmax * 64;
+  m->pair_stages = pair_stages;
   if (pair_ok && smem_pair <= 227 * 1024) {
     m->smem_pair = smem_pair;
     if (cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
@@ -1169,6 +1287,8 @@ int hos_mlp_set_layer(hos_mlp_t* m, int layer, const float* W, const float* b, v
   pack_weight_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(W, D.n, L.in_h, L.in_x, L.x_first, D.kb_h, D.kb_x,
                                                                    m->ipe_perm, m->d_w + D.w_off);
   HOS_LAUNCH_CHECK();
+  pack_bias_chunk_kernel<<<(D.n * kKB + 255) / 256, 256, 0, st>>>(b, D.n, m->d_w + D.w_off + (size_t)(D.kb_h + D.kb_x) * D.n * 128);
+  HOS_LAUNCH_CHECK();
   if (b) HOS_CUDA(cudaMemcpyAsync(m->d_params + D.bias_off, b, (size_t)D.n * 4, cudaMemcpyDeviceToDevice, st));
   else HOS_CUDA(cudaMemsetAsync(m->d_params + D.bias_off, 0, (size_t)D.n * 4, st));
   return HOS_OK;
@@ -1178,6 +1298,9 @@ int hos_mlp_set_bias(hos_mlp_t* m, int layer, const float* b, void* stream) {
   HOS_ARCH_GUARD();
   HOS_REQUIRE(m && b && layer >= 0 && layer < m->prog.n_layers, "hos_mlp_set_bias: bad handle/layer");
   const LayerDev& D = m->prog.layers[layer];
+  pack_bias_chunk_kernel<<<(D.n * kKB + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      b, D.n, m->d_w + D.w_off + (size_t)(D.kb_h + D.kb_x) * D.n * 128);
+  HOS_LAUNCH_CHECK();
   HOS_CUDA(cudaMemcpyAsync(m->d_params + D.bias_off, b, (size_t)D.n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return HOS_OK;
 }
@@ -1223,9 +1346,10 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   // the pair kernel walks groups of 4 tiles; tiny batches keep more SMs busy on the single-CTA kernel
   const bool pair = m->smem_pair && g_mlp_variant == 2;      // opt-in until it beats the single-CTA kernel
   if (pair) {
-    const int n_groups = (a.ntiles + 3) / 4;
+    const int n_groups = (a.ntiles + 1) / 2;
     const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
-    mlp_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_pair, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
+    mlp_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_pair, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe,
+                                                                                      m->pair_stages);
   } else {
     int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
     mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);

@@ -43,26 +43,20 @@ else:
     t = buf.cpu()[:768].view(64, 12)
     t0 = int(t[0, 0])
     nl = 4 if which == "prop" else len(net.mlps[-1]._cache["f16"].layers)
-    print("unit(g,l,slot): mma_enter acc_free issued | epi_enter acc_ready epi_done | feat_start feat_end | "
-          "act_wait issue_span w_wait x_wait | epi_wait epi_span | feat_span")
-    for i in range(64):
+    print("unit(tile,layer): mma_enter issued | epi_enter acc_ready epi_done | feat_start feat_end | "
+          "issue_span w_wait operand_wait | epi_wait epi_span | feat_span | mma_enter->next")
+    for i in range(63):
         r = [int(x) for x in t[i]]
         if r[0] == 0:
             break
-        u, slot = i // 2, i % 2
         rel = [x - t0 if x else 0 for x in r[:8]]
-        print(f"{i:3d} (g{u // nl} l{u % nl} s{slot}): {rel[0]:8d} {rel[1]:8d} {rel[2]:8d} | {rel[3]:8d} {rel[4]:8d} {rel[5]:8d} | "
-              f"{rel[6]:8d} {rel[7]:8d} | {r[1] - r[0]:6d} {r[2] - r[1]:6d} {r[8]:6d} {r[9]:6d} | {r[4] - r[3]:6d} {r[5] - r[4]:6d} | "
-              f"{(r[7] - r[6]) if r[6] else 0:6d}")
-
-    for base, name in ((768, "unit 21"), (832, "unit 28")):
-        c = buf.cpu()[base:base + 60].view(12, 5)
-        print(name, "chunk: wait_start waited mma4_issued commits_done syncwarp_done (deltas) | period")
-        prev = None
-        for kb in range(12):
-            r = [int(x) for x in c[kb]]
-            if r[0] == 0:
-                break
-            print(f"  kb{kb}: wait {r[1] - r[0]:5d}  mma4 {r[2] - r[1]:5d}  commits {r[3] - r[2]:5d}  sync {r[4] - r[3]:5d} | "
-                  f"{(r[0] - prev) if prev else 0:6d}")
-            prev = r[0]
+        nxt = int(t[i + 1, 0])
+        print(f"{i:3d} (t{i // nl} l{i % nl}): {rel[0]:8d} {rel[1]:8d} | {rel[3]:8d} {rel[4]:8d} {rel[5]:8d} | "
+              f"{rel[6]:8d} {rel[7]:8d} | {r[1] - r[0]:6d} {r[8]:6d} {r[9]:6d} | {r[4] - r[3]:6d} {r[5] - r[4]:6d} | "
+              f"{(r[7] - r[6]) if r[6] else 0:6d} | {(nxt - r[0]) if nxt else 0:6d}")
+if variant == 2:
+    for base, name in ((768, "unit 11"), (800, "unit 12")):
+        c = [int(x) for x in buf.cpu()[base:base + 12]]
+        if c[0]:
+            print(name, "epilogue warp 4, per 64-column chunk: (ld ready -> processed, -> signalled, -> next ld ready)",
+                  [(c[i * 3 + 1] - c[i * 3], c[i * 3 + 2] - c[i * 3 + 1], (c[i * 3 + 3] - c[i * 3 + 2]) if i < 3 else 0) for i in range(4)])

@@ -289,7 +289,9 @@ def test_pair_kernel_matches_single_cta_kernel_fused_ipe():
     d0 = rel_err(hb[0]["density"].cpu(), ha[0]["density"].cpu())
     print("pair vs single: L0 density rel", d0, "final rgb abs", max_abs(ra[-1]["rgb"].cpu(), rb[-1]["rgb"].cpu()))
     assert torch.isfinite(hb[-1]["rgb"]).all()
-    assert d0 < 1e-5                       # same operands, same K order: fp32 accumulation-order noise at most
+    # same fp16 operands; the pair kernel adds the bias inside the GEMM (fp16 hi + lo parts, ~2^-22) instead of in the
+    # epilogue, so an activation can land on the other side of an fp16 rounding boundary: a few fp16 ulps at most
+    assert d0 < 5e-3
     assert max_abs(ra[-1]["rgb"].cpu(), rb[-1]["rgb"].cpu()) < 1e-4
 
 
