@@ -185,6 +185,34 @@ __device__ __forceinline__ void mbar_wait2_spin(uint32_t a0, uint32_t p0, uint32
     if (++polls > (1u << 28)) __trap();
   }
 }
+__device__ __forceinline__ void mbar_wait4_spin(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2,
+                                                uint32_t a3, uint32_t p3) {
+  uint32_t polls = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p, q, r, s;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 r, [%5], %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 s, [%7], %8;\n\t"
+        "and.pred p, p, q;\n\tand.pred r, r, s;\n\tand.pred p, p, r;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(a3), "r"(p3) : "memory");
+    if (ok) return;
+    if (++polls > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ bool elect_one() {      // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_commit_pair_addr(uint32_t bar_saddr) {     // arrives on the barrier in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_saddr),
+               "h"((uint16_t)3)
+               : "memory");
+}
 // wait until up to three phases have all completed: the polls overlap instead of paying three latencies in a row
 __device__ __forceinline__ void mbar_wait3_spin(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2) {
   uint32_t polls = 0;
@@ -825,63 +853,97 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread of the leader CTA) =====================
-    // tcgen05.mma issue blocks while the pipe is busy (queue depth ~1), so every cycle this thread spends between
-    // MMAs is a cycle the tensor core idles: one lane, both barriers of a chunk polled together, descriptors
-    // advanced by integer adds, no instrumentation inside the chunk loop.
-    if (rank == 0 && lane == 0) {
-      uint32_t wi = 0, xi = 0, u = 0, hq = 0;        // chunk / feature-chunk / unit counters; hq = units that read H so far
+    // A single thread runs ~5 cycles per dependent instruction and every try_wait / commit costs 60-180 cycles
+    // (scripts/ubench_tc.cu, test 8), while a K = 64 chunk lasts only 512 cycles on the tensor core: the loop
+    // therefore works on GROUPS of up to three chunks - all their barriers polled in one parallel try_wait,
+    // MMAs and commits issued back to back, ring state advanced by increments (no division).  Grouping of a
+    // layer with kb_h activation chunks: [h0] [h1 h2] [h3 ...] (the first alone so that the layer starts as soon
+    // as the previous epilogue has produced one K-chunk), feature chunks alone (their ring is 2 deep), and the
+    // bias chunk rides with the last group.
+    // The loop runs on ALL lanes of the warp with warp-uniform values and only the tcgen05 instructions sit under
+    // elect.sync: tcgen05.mma takes its descriptors from uniform registers, and when the issue code ran on one lane of
+    // a divergent branch the compiler had to move 7 values per MMA through R2UR in a wait-loop (~130 cycles per MMA).
+    if (rank == 0) {
+      uint32_t u = 0, hpar = 0;                      // unit counter; parity of the hready phase the next H-reading unit waits for
+      uint32_t ws = 0, wpar = 0, xs = 0, xpar = 0;   // weight / feature ring cursors + phase parities
       const uint64_t desc_hi = umma_desc(0);
+      const uint32_t wfull0 = smem_u32(&bar_wfull[0]), wempty0 = smem_u32(&bar_wempty[0]);
+      const uint32_t xfull0 = smem_u32(&bar_xfull[0]), xempty0 = smem_u32(&bar_xempty[0]);
+      const uint32_t hready_a = smem_u32(&bar_hready[0]), tfull0 = smem_u32(&bar_tfull[0]);
+      const uint32_t h16 = (smem_u32(sH) >> 4) & 0x3FFF, x16 = (smem_u32(sRingX) >> 4) & 0x3FFF;
+      const uint32_t w16 = (smem_u32(sRingW) >> 4) & 0x3FFF, ones16 = (smem_u32(sOnes) >> 4) & 0x3FFF;
+      const uint32_t wstage16 = (uint32_t)w_stage_bytes >> 4;
       for (int g = cluster; g < n_groups; g += n_clusters) {
         for (int l = 0; l < n_layers; ++l, ++u) {
           const LayerDev L = prog.layers[l];
           const uint32_t idesc = umma_idesc_f16(L.n, 2 * kTileM);
-          const int nkb = L.kb_h + L.kb_x;
+          const int kb_h = L.kb_h, nkb = L.kb_h + L.kb_x;
           const uint32_t acc = tmem_base + (u & 1) * 256;
-          const bool tl = args.timeline && blockIdx.x == 0 && u < 64;
-          long long wsum = 0, osum = 0;
+          const bool tl = args.timeline && blockIdx.x == 0 && u < 64 && lane == 0;
+          long long wait_sum = 0;
           if (tl) args.timeline[u * 12 + 0] = clock64();
           // Accumulator buffer (u & 1) was last read by the epilogue of unit u - 2, which finished before it
           // signalled the last H chunk that unit u - 1 waited for; H chunk kb is overwritten by the epilogue of
           // unit u only after all MMAs of unit u retired (tfull).
-          for (int kb = 0; kb < nkb; ++kb, ++wi) {
-            const uint32_t ws = wi % S, use = wi / S;
-            const bool from_x = kb >= L.kb_h;
-            const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
-            // weights of both halves + (features of both CTAs | the previous layer's K-chunk kb)
-            if (tl) {       // instrumented CTA only: split the wait into weights / operand
-              const long long c0 = clock64();
-              mbar_wait_guard<0>(&bar_wfull[ws], use & 1);
+          int kb = 0, gi3 = 0;
+          while (kb < nkb) {
+            const bool is_h = kb < kb_h;
+            const int cnt = (is_h && kb > 0 && kb + 1 < kb_h) ? 2 : 1;
+            const bool with_bias = kb + cnt == nkb;
+            const int nst = cnt + (with_bias ? 1 : 0);           // ring stages consumed by this group (<= 3)
+            // ---- one parallel poll: the weight stages + the newest operand chunk (earlier ones are implied)
+            uint32_t wb[3], wp[3];
+            {
+              uint32_t s_ = ws, p_ = wpar;
+#pragma unroll
+              for (int i = 0; i < 3; ++i) {
+                wb[i] = wfull0 + 8u * s_; wp[i] = p_;
+                if (i + 1 < nst) { if (++s_ == S) { s_ = 0; p_ ^= 1; } }
+              }
+            }
+            const uint32_t ob = is_h ? hready_a + 8u * (uint32_t)(kb + cnt - 1) : xfull0 + 8u * xs;
+            const uint32_t op = is_h ? hpar : xpar;
+            const long long c0 = tl ? clock64() : 0;
+            mbar_wait4_spin(wb[0], wp[0], wb[1], wp[1], wb[2], wp[2], ob, op);
+            const bool tl3 = tl && (u == 11 || u == 12) && gi3 < 5;
+            if (tl) {
               const long long c1 = clock64();
-              mbar_wait_guard<0>(from_x ? &bar_xfull[xs] : &bar_hready[kb], from_x ? (xuse & 1) : (hq & 1));
-              wsum += c1 - c0; osum += clock64() - c1;
-            } else {
-              mbar_wait2_spin(smem_u32(&bar_wfull[ws]), use & 1,
-                              smem_u32(from_x ? &bar_xfull[xs] : &bar_hready[kb]), from_x ? (xuse & 1) : (hq & 1));
+              wait_sum += c1 - c0;
+              if (tl3) { args.timeline[840 + (u - 11) * 16 + gi3 * 3 + 0] = c0; args.timeline[840 + (u - 11) * 16 + gi3 * 3 + 1] = c1; }
             }
             tc_fence_after();
-            const uint32_t a_base = smem_u32(from_x ? sRingX + xs * kXChunkBytes : sH + kb * kXChunkBytes);
-            const uint32_t b_base = smem_u32(sRingW + ws * w_stage_bytes);
-            const uint64_t adesc = desc_hi | (uint64_t)((a_base >> 4) & 0x3FFF);
-            const uint64_t bdesc = desc_hi | (uint64_t)((b_base >> 4) & 0x3FFF);
+            // ---- issue
+            const bool leader_lane = elect_one();
+#pragma unroll 1
+            for (int i = 0; i < cnt; ++i) {
+              const uint32_t a16 = is_h ? h16 + (uint32_t)(kb + i) * (kXChunkBytes >> 4) : x16 + xs * (kXChunkBytes >> 4);
+              const uint64_t adesc = desc_hi | (uint64_t)a16;
+              const uint64_t bdesc = desc_hi | (uint64_t)(w16 + ws * wstage16);
+              if (leader_lane) {
 #pragma unroll
-            for (int k = 0; k < kKB / 16; ++k)
-              tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            tc_commit_pair(&bar_wempty[ws]);
-            if (from_x) { tc_commit_pair(&bar_xempty[xs]); ++xi; }
+                for (int k = 0; k < kKB / 16; ++k)
+                  tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb + i) != 0 || k != 0 ? 1u : 0u);
+                tc_commit_pair_addr(wempty0 + 8u * ws);
+                if (!is_h) tc_commit_pair_addr(xempty0 + 8u * xs);
+              }
+              if (++ws == S) { ws = 0; wpar ^= 1; }
+              if (!is_h) { if (++xs == kPairStagesX) { xs = 0; xpar ^= 1; } }
+            }
+            if (with_bias) {   // ones (columns 0, 1 of the constant operand) x (hi, lo) -> one K = 16 MMA
+              if (leader_lane) {
+                tc_mma_f16_pair(acc, desc_hi | (uint64_t)ones16, desc_hi | (uint64_t)(w16 + ws * wstage16), idesc, 1u);
+                tc_commit_pair_addr(wempty0 + 8u * ws);
+                tc_commit_pair_addr(tfull0 + 8u * (u & 1));
+              }
+              if (++ws == S) { ws = 0; wpar ^= 1; }
+            }
+            __syncwarp();
+            if (tl3) args.timeline[840 + (u - 11) * 16 + gi3 * 3 + 2] = clock64();
+            ++gi3;
+            kb += cnt;
           }
-          {   // bias chunk: ones (columns 0, 1 of the constant operand) x (hi, lo) -> one K = 16 MMA
-            const uint32_t ws = wi % S, use = wi / S;
-            mbar_wait_guard<0>(&bar_wfull[ws], use & 1);
-            tc_fence_after();
-            const uint64_t adesc = desc_hi | (uint64_t)((smem_u32(sOnes) >> 4) & 0x3FFF);
-            const uint64_t bdesc = desc_hi | (uint64_t)((smem_u32(sRingW + ws * w_stage_bytes) >> 4) & 0x3FFF);
-            tc_mma_f16_pair(acc, adesc, bdesc, idesc, 1u);
-            tc_commit_pair(&bar_wempty[ws]);
-            tc_commit_pair(&bar_tfull[u & 1]);
-            ++wi;
-          }
-          if (L.kb_h) ++hq;
-          if (tl) { args.timeline[u * 12 + 1] = clock64(); args.timeline[u * 12 + 8] = wsum; args.timeline[u * 12 + 9] = osum; }
+          if (kb_h) hpar ^= 1;
+          if (tl) { args.timeline[u * 12 + 1] = clock64(); args.timeline[u * 12 + 8] = wait_sum; }
         }
       }
     }
@@ -1344,7 +1406,7 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   static const IpeArgs kNoIpe = {};
   HOS_REQUIRE(g_mlp_variant != 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
   // the pair kernel walks groups of 4 tiles; tiny batches keep more SMs busy on the single-CTA kernel
-  const bool pair = m->smem_pair && g_mlp_variant == 2;      // opt-in until it beats the single-CTA kernel
+  const bool pair = m->smem_pair && g_mlp_variant != 1 && (g_mlp_variant == 2 || a.ntiles >= 2);
   if (pair) {
     const int n_groups = (a.ntiles + 1) / 2;
     const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;

@@ -44,7 +44,7 @@ else:
     t0 = int(t[0, 0])
     nl = 4 if which == "prop" else len(net.mlps[-1]._cache["f16"].layers)
     print("unit(tile,layer): mma_enter issued | epi_enter acc_ready epi_done | feat_start feat_end | "
-          "issue_span w_wait operand_wait | epi_wait epi_span | feat_span | mma_enter->next")
+          "issue_span wait | epi_wait epi_span | feat_span | mma_enter->next")
     for i in range(63):
         r = [int(x) for x in t[i]]
         if r[0] == 0:
@@ -52,7 +52,7 @@ else:
         rel = [x - t0 if x else 0 for x in r[:8]]
         nxt = int(t[i + 1, 0])
         print(f"{i:3d} (t{i // nl} l{i % nl}): {rel[0]:8d} {rel[1]:8d} | {rel[3]:8d} {rel[4]:8d} {rel[5]:8d} | "
-              f"{rel[6]:8d} {rel[7]:8d} | {r[1] - r[0]:6d} {r[8]:6d} {r[9]:6d} | {r[4] - r[3]:6d} {r[5] - r[4]:6d} | "
+              f"{rel[6]:8d} {rel[7]:8d} | {r[1] - r[0]:6d} {r[8]:6d} | {r[4] - r[3]:6d} {r[5] - r[4]:6d} | "
               f"{(r[7] - r[6]) if r[6] else 0:6d} | {(nxt - r[0]) if nxt else 0:6d}")
 if variant == 2:
     for base, name in ((768, "unit 11"), (800, "unit 12")):
@@ -60,3 +60,14 @@ if variant == 2:
         if c[0]:
             print(name, "epilogue warp 4, per 64-column chunk: (ld ready -> processed, -> signalled, -> next ld ready)",
                   [(c[i * 3 + 1] - c[i * 3], c[i * 3 + 2] - c[i * 3 + 1], (c[i * 3 + 3] - c[i * 3 + 2]) if i < 3 else 0) for i in range(4)])
+
+if variant == 2:
+    tt = buf.cpu()
+    for uu in (11, 12):
+        base = 840 + (uu - 11) * 16
+        c = [int(x) for x in tt[base:base + 15]]
+        ref = int(tt[uu * 12 + 0])
+        if c[0]:
+            print(f"unit {uu} MMA thread groups (rel. to mma_enter): [wait_start, wait_end, issued]",
+                  [(c[i * 3] - ref, c[i * 3 + 1] - ref, c[i * 3 + 2] - ref) for i in range(5) if c[i * 3]],
+                  "| epilogue acc_ready/epi_done of previous unit:", int(tt[(uu - 1) * 12 + 4]) - ref, int(tt[(uu - 1) * 12 + 5]) - ref)

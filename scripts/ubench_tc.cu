@@ -628,6 +628,108 @@ static void run_trace(const unsigned char* d_src, int chunk, int stages, int var
   CK(cudaFree(d_st));
 }
 
+// Test 8: issue cost of every tcgen05.mma / tcgen05.commit in a (4 MMA + commit) x n_chunks stream, plus the cost
+// of a try_wait on an already-completed barrier placed between chunks (what the MLP kernel's MMA thread does).
+template <int CG>
+__global__ void __launch_bounds__(128, 1) k_issue_trace(int n_chunks, int with_wait, long long* stamps) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kBStage = CG == 1 ? 32768 : 16384;
+  unsigned char* sA = smem;
+  unsigned char* sB = sA + 4 * 16384;
+  __shared__ uint64_t bar_done, bar_ready, bar_stage[4];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0;
+  for (int i = threadIdx.x; i < (4 * 16384 + 3 * kBStage) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_done, 1);
+    mbar_init(&bar_ready, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_stage[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_ready)) : "memory");   // phase 0 complete
+  }
+  if (warp == 1) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  if (warp == 1 && rank == 0 && lane == 0) {
+    const uint32_t idesc = umma_idesc_f16(CG == 1 ? 128 : 256, 256);
+    long long t0 = clock64();
+    for (int c = 0; c < n_chunks; ++c) {
+      const uint32_t a_base = smem_u32(sA + (c & 3) * 16384);
+      const uint32_t b_base = smem_u32(sB + (c % 3) * kBStage);
+      long long* st = stamps + c * 8;
+      if (with_wait) mbar_wait(&bar_ready, 0);
+      const long long w = clock64();
+      tc_mma<CG>(tmem_base, umma_desc(a_base), umma_desc(b_base), idesc, c != 0);
+      const long long m0 = clock64();
+      tc_mma<CG>(tmem_base, umma_desc(a_base + 32), umma_desc(b_base + 32), idesc, 1);
+      const long long m1 = clock64();
+      tc_mma<CG>(tmem_base, umma_desc(a_base + 64), umma_desc(b_base + 64), idesc, 1);
+      const long long m2 = clock64();
+      tc_mma<CG>(tmem_base, umma_desc(a_base + 96), umma_desc(b_base + 96), idesc, 1);
+      const long long m3 = clock64();
+      tc_commit<CG>(&bar_stage[c & 3]);
+      const long long cm = clock64();
+      if (blockIdx.x == 0 && c < 32) { st[0] = w - t0; st[1] = m0 - t0; st[2] = m1 - t0; st[3] = m2 - t0; st[4] = m3 - t0; st[5] = cm - t0; }
+    }
+    tc_commit<CG>(&bar_done);
+    mbar_wait(&bar_done, 0);
+    if (blockIdx.x == 0) stamps[32 * 8] = clock64() - t0;
+  }
+  if (CG == 2 && warp == 1 && rank == 1 && lane == 0) mbar_wait(&bar_done, 0);
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+template <int CG>
+static void run_issue_trace(int with_wait) {
+  long long* d;
+  CK(cudaMalloc(&d, 300 * 8));
+  CK(cudaMemset(d, 0, 300 * 8));
+  const int smem = 1024 + 4 * 16384 + 3 * 32768;
+  CK(cudaFuncSetAttribute(k_issue_trace<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(148);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, k_issue_trace<CG>, 24, with_wait, d));
+  CK(cudaDeviceSynchronize());
+  long long h[300];
+  CK(cudaMemcpy(h, d, 300 * 8, cudaMemcpyDeviceToHost));
+  printf("issue trace cg=%d with_wait=%d: total %lld cyc for 24 chunks (96 MMAs)\n  per chunk [wait-or-loop, mma0, mma1, mma2, mma3, commit]:", CG, with_wait, h[256]);
+  for (int c = 1; c < 12; ++c) {
+    long long* st = h + c * 8;
+    printf(" [%lld %lld %lld %lld %lld %lld]", st[0] - h[(c - 1) * 8 + 5], st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4]);
+  }
+  printf("\n");
+  CK(cudaFree(d));
+}
+
 template <int CG>
 static void run_mma(int n_chunks, int epi_tiles, int epi_sts, long long* d_cyc, const char* label) {
   const int smem = 1024 + 4 * 16384 + 3 * (CG == 1 ? 32768 : 16384) + 65536;
@@ -664,6 +766,10 @@ static void run_mma(int n_chunks, int epi_tiles, int epi_sts, long long* d_cyc, 
 int main() {
   long long* d_cyc;
   CK(cudaMalloc(&d_cyc, 64));
+  if (getenv("UB_ISSUE")) {
+    run_issue_trace<1>(0); run_issue_trace<1>(1); run_issue_trace<2>(0); run_issue_trace<2>(1);
+    return 0;
+  }
   // ---- test 4: L2 streaming
   {
     unsigned char* d_src;
