@@ -741,6 +741,7 @@ constexpr int kPairMaxStagesW = 8;
 constexpr int kPairStagesX = 2;
 constexpr int kPairProducers = 3;
 constexpr int kPairMaxKbh = 4;
+constexpr int kRowBiasVecs = 4;
 constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 2 + kPairMaxKbh;
 static_assert(kPairBars % 2 == 0, "s_headx behind the barriers is read as float4");
 
@@ -767,6 +768,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                                                            //       the 16 epilogue warps of the pair
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kPairBars);       // kPairBars is even: 16-byte aligned
   float* s_headx = reinterpret_cast<float*>(s_tmem + 4);   // [128][4], read as float4
+  float* s_rowbias = s_headx + kTileM * 4;                 // [kRowBiasVecs][128] per-ray bias vectors of the current tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -891,7 +893,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             const int cnt = (is_h && kb > 0 && kb + 1 < kb_h) ? 2 : 1;
             const bool with_bias = kb + cnt == nkb;
             const int nst = cnt + (with_bias ? 1 : 0);           // ring stages consumed by this group (<= 3)
-            // ---- one parallel poll: the weight stages + the newest operand chunk (earlier ones are implied)
+            // ---- one parallel poll (four try_waits in flight together cost ~220 cycles, four separate phase checks
+            // ~150 each): the weight stages + the newest operand chunk (earlier ones are implied)
             uint32_t wb[3], wp[3];
             {
               uint32_t s_ = ws, p_ = wpar;
@@ -974,6 +977,26 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         const int nchunks = L.n >> 6;
         const uint32_t acc = tmem_base + (u & 1) * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
         const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && u < 64;
+        // Per-ray bias (view-direction term): when a tile spans a whole number of rays (or one ray spans whole tiles) its
+        // <= 4 bias vectors are fetched into shared memory BEFORE the wait for the accumulator, so the L2 latency is
+        // hidden and the 8 loads per 32 columns become broadcast ld.shared; otherwise each row reads global memory.
+        uint32_t rb_s = 0;
+        const float* rb_g = nullptr;
+        if (L.rowbias && args.rowbias) {
+          const int div = args.rowbias_div;
+          const int nr = (div % kTileM == 0) ? 1 : ((kTileM % div == 0 && kTileM / div <= kRowBiasVecs && L.n <= 128) ? kTileM / div : 0);
+          if (nr > 0 && nr * L.n <= kRowBiasVecs * 128) {
+            const int te = threadIdx.x - kEpiWarp0 * 32;
+            for (int i = te; i < nr * L.n; i += kEpiWarps * 32) {
+              const int64_t row0 = (int64_t)tile * kTileM + (int64_t)(i / L.n) * div;
+              s_rowbias[i] = row0 < args.rows ? __ldg(args.rowbias + (row0 / div) * L.n + (i % L.n)) : 0.f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            rb_s = smem_u32(s_rowbias) + 4u * (uint32_t)((nr == 1 ? 0 : r / div) * L.n);
+          } else if (row_ok) {
+            rb_g = args.rowbias + (row / div) * L.n;
+          }
+        }
         if (tl) args.timeline[u * 12 + 3] = clock64();
         mbar_wait_guard<20>(&bar_tfull[u & 1], (u >> 1) & 1);
         tc_fence_after();
@@ -987,7 +1010,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           if (lane == 0) mbar_arrive_remote(hready0 + 8u * c);
         };
 
-        if (!has_head && !last && !(L.rowbias && args.rowbias)) {
+        if (!has_head && !last && !rb_s && !rb_g) {
           // ---------- plain hidden layer (bias already in the accumulator): convert (+ ReLU) and store, nothing else.
           // Two TMEM loads in flight: the next chunk's 32 columns arrive while these are converted.
           auto store32 = [&](const uint32_t (&v)[32], int c) {
@@ -1023,20 +1046,22 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         } else {
           // ---------- general layer: per-row bias, fp32 output head, last layer (no activations stored)
           const HeadDev Hd = prog.heads[has_head ? L.head : 0];
-          const float* rb = (L.rowbias && args.rowbias && row_ok) ? args.rowbias + (row / args.rowbias_div) * L.n : nullptr;
           float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int c = 0; c < nchunks; ++c) {
+          auto process_general = [&](uint32_t (&v)[32], int c) {
             const int c0 = c * 64 + ch * 32;
-            uint32_t v[32];
-            tmem_ld32_nowait(acc + (uint32_t)(c * 64), v);
-            tmem_wait_ld();
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (rb) {
+            if (rb_s) {                         // per-ray bias staged in shared memory (see above)
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(rb + c0) + j);
+                const float4 bb = lds128(rb_s + 4u * (uint32_t)c0 + 16u * j);
+                f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+              }
+            } else if (rb_g) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(rb_g + c0) + j);
                 f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
               }
             }
@@ -1070,6 +1095,12 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                        cvt_f16x2(__float_as_uint(f[gq * 8 + 6]), __float_as_uint(f[gq * 8 + 7])));
               chunk_ready(c);
             }
+          };
+          for (int c = 0; c < nchunks; ++c) {       // single-buffered: this path also carries the head accumulators
+            uint32_t v[32];
+            tmem_ld32_nowait(acc + (uint32_t)(c * 64), v);
+            tmem_wait_ld();
+            process_general(v, c);
           }
           if (last) tc_fence_before();
           if (has_head) {                         // combine the two column halves, then post-process
@@ -1298,7 +1329,8 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   for (int l = 0; l + 1 < n_layers; ++l) pair_ok = pair_ok && layers[l].out_dim == P.kbh * kKB;   // one hready phase count
   pair_ok = pair_ok && P.kbh <= kPairMaxKbh;
   const size_t pair_fixed = 1024 + (size_t)(P.kbh + 1) * kXChunkBytes + (size_t)kPairStagesX * kXChunkBytes +
-                            (((size_t)poff + 3) & ~(size_t)3) * 4 + (kPairBars + 1) * 8 + 16 + kTileM * 4 * sizeof(float);
+                            (((size_t)poff + 3) & ~(size_t)3) * 4 + (kPairBars + 1) * 8 + 16 + kTileM * 4 * sizeof(float) +
+                            kRowBiasVecs * 128 * sizeof(float);
   int pair_stages = pair_fixed < 227 * 1024 ? (int)((227 * 1024 - pair_fixed) / ((size_t)nmax * 64)) : 0;
   if (pair_stages > kPairMaxStagesW) pair_stages = kPairMaxStagesW;
   pair_ok = pair_ok && pair_stages >= 3;

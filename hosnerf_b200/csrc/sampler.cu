@@ -95,11 +95,54 @@ __device__ void dilate_ray(SamplerSmem& sm, const float* __restrict__ t, const f
     sm.knots[2 * M + 1 + j] = r;
   }
   if (threadIdx.x == 0) sm.knots[M] = t[M];
-  for (int i = K + threadIdx.x; i < n2; i += blockDim.x) sm.knots[i] = CUDART_INF_F;
-  __syncthreads();
-  bitonic_sort(sm.knots, n2);
-  for (int i = threadIdx.x; i < K; i += blockDim.x) sm.knots[i] = fminf(fmaxf(sm.knots[i], lo), hi);
-  __syncthreads();
+  if (sorted_input) {
+    // t ascending => the three lists A = t[0..M], B = t[:-1] - d, C = t[1:] + d are each ascending: the sorted
+    // union is a 3-way merge, done by rank: position of an element = its own index + how many elements of the other
+    // two lists precede it (ties broken by list order A < B < C, so every position is hit exactly once).  The
+    // result is the same ascending array of VALUES that torch.sort produces - one pass instead of 45 bitonic steps.
+    __syncthreads();
+    for (int e = threadIdx.x; e < K; e += blockDim.x) {
+      float x;
+      int pos;
+      if (e <= M) {                      // from A: count B < x and C < x
+        x = sm.knots[e];
+        int a = 0, b = M;
+        while (a < b) { int m = (a + b) >> 1; if (sm.t0[m] < x) a = m + 1; else b = m; }
+        pos = e + a;
+        a = 0; b = M;
+        while (a < b) { int m = (a + b) >> 1; if (sm.t1[m] < x) a = m + 1; else b = m; }
+        pos += a;
+      } else if (e <= 2 * M) {           // from B: count A <= x and C < x
+        const int j = e - (M + 1);
+        x = sm.t0[j];
+        int a = 0, b = M + 1;
+        while (a < b) { int m = (a + b) >> 1; if (sm.knots[m] <= x) a = m + 1; else b = m; }
+        pos = j + a;
+        a = 0; b = M;
+        while (a < b) { int m = (a + b) >> 1; if (sm.t1[m] < x) a = m + 1; else b = m; }
+        pos += a;
+      } else {                           // from C: count A <= x and B <= x
+        const int j = e - (2 * M + 1);
+        x = sm.t1[j];
+        int a = 0, b = M + 1;
+        while (a < b) { int m = (a + b) >> 1; if (sm.knots[m] <= x) a = m + 1; else b = m; }
+        pos = j + a;
+        a = 0; b = M;
+        while (a < b) { int m = (a + b) >> 1; if (sm.t0[m] <= x) a = m + 1; else b = m; }
+        pos += a;
+      }
+      sm.cw[pos] = fminf(fmaxf(x, lo), hi);          // cw is free until cdf_ray: staging for the merged knots
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sm.knots[i] = sm.cw[i];
+    __syncthreads();
+  } else {
+    for (int i = K + threadIdx.x; i < n2; i += blockDim.x) sm.knots[i] = CUDART_INF_F;
+    __syncthreads();
+    bitonic_sort(sm.knots, n2);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sm.knots[i] = fminf(fmaxf(sm.knots[i], lo), hi);
+    __syncthreads();
+  }
   float part = 0.f;
   for (int k = threadIdx.x; k < K - 1; k += blockDim.x) {
     float x = sm.knots[k];
@@ -165,7 +208,8 @@ __device__ void cdf_ray(SamplerSmem& sm, int M) {
 __device__ void invert_ray(SamplerSmem& sm, int off, int M, const float* __restrict__ u_base,
                            const float* __restrict__ jitter, int jitter_cols, float max_jitter, int S,
                            float lo, float hi, float* __restrict__ out, float* __restrict__ centers_out,
-                           int32_t* __restrict__ idx_out) {
+                           int32_t* __restrict__ idx_out, float* __restrict__ tdist_out = nullptr, float s_near = 0.f,
+                           float s_far = 0.f) {
   const float* t = sm.knots + off;
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     float u = u_base[s];
@@ -200,6 +244,7 @@ __device__ void invert_ray(SamplerSmem& sm, int off, int M, const float* __restr
       v = (sm.centers[i] + sm.centers[i - 1]) / 2.f;
     }
     out[i] = v;
+    if (tdist_out) tdist_out[i] = 1.f / (v * s_far + (1.f - v) * s_near);    // s_to_t (helper.py:146-150)
   }
 }
 
@@ -278,14 +323,7 @@ resample_level_kernel(const float* __restrict__ sdist, const float* __restrict__
   cdf_ray(sm, M);
   float* so = sdist_out + (size_t)ray * (S + 1);
   invert_ray(sm, off, M, u_base, jitter ? jitter + (size_t)ray * jitter_cols : nullptr, jitter_cols,
-             max_jitter, S, lo, hi, so, nullptr, nullptr);
-  __syncthreads();
-  // s_to_t: 1 / (s*s_far + (1-s)*s_near)   (helper.py:146-150); each thread re-reads what it wrote
-  float* to = tdist_out + (size_t)ray * (S + 1);
-  for (int i = threadIdx.x; i <= S; i += blockDim.x) {
-    float s = so[i];
-    to[i] = 1.f / (s * s_far + (1.f - s) * s_near);
-  }
+             max_jitter, S, lo, hi, so, nullptr, nullptr, tdist_out + (size_t)ray * (S + 1), s_near, s_far);
 }
 
 // Human branch samples: z = near*(1-t) + far*t (+ stratified jitter), pts = o + d*z.
