@@ -36,12 +36,13 @@ NEAR, FAR = 0.1, 1e6
 # algorithmic MLP work per sample: 2 * MACs of the reference layers
 FLOP_PROP = 2 * 342272
 FLOP_NERF = 2 * 851968
+MLP_KERNEL = {0: "mlp_pair_kernel", 1: "mlp_tc_kernel", 2: "mlp_pair_kernel"}
 WORKLOAD = "C2: stage-1 bkg render_rays, 4096 rays x (128 prop + 128 nerf) samples, PropMLP 4x256 + NeRFMLP 8x256"
 
 
 def ncu_traffic():
     """DRAM bytes of the dominant kernel (both MLP launches of a step) from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r1_mlp_ncu.json")
+    p = os.path.join(ROOT, "profiles", "r1_mlp_pair_ncu.json")
     try:
         return json.load(open(p))["dram_bytes_per_step"]
     except Exception:
@@ -236,10 +237,10 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / K,
                     "api": "LitMipNeRF360.render_rays(batch) with pinned host tensors in, rgb.cpu() out"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "mlp_tc_kernel (tcgen05 fused MLP, 2 launches/step)",
+            "roofline": {"bound": "tensor", "kernel": MLP_KERNEL[args.mlp_variant] + " (tcgen05 fused MLP, 2 launches/step)",
                          "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                          "peak_source": f"{src} bf16_tflops (burst)", "traffic": ncu_traffic(),
-                         "traffic_note": "DRAM read+write bytes of the two MLP launches of one step, ncu --set full (profiles/r1_mlp_ncu.json)",
+                         "traffic_note": "DRAM read+write bytes of the two MLP launches of one step, ncu --set full (profiles/r1_mlp_pair_ncu.json)",
                          "kernel_share_of_step": mlp_ms / dev_ms if dev_ms > 0 else None,
                          "flop_per_launch": [N_RAYS * S_PROP * FLOP_PROP, N_RAYS * S_NERF * FLOP_NERF]},
             "clocks": sampler.summary(),

@@ -1,7 +1,12 @@
 // Fused multi-layer MLP on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
 // SURVEY 8a rows a9 (Prop/NeRF MLP), a17 (non-rigid MLP), a19 (canonical MLP).
 //
-// One persistent CTA per SM walks 128-row tiles of the flattened (rays x samples) batch.
+// Two kernels share the program format, the packed weights and the fused IPE prologue:
+//   mlp_pair_kernel  (default)  2-CTA clusters, tcgen05.mma.cta_group::2, deep weight ring, TMEM double-buffered
+//                               accumulator, chunk-pipelined epilogue - see the comment above that kernel;
+//   mlp_tc_kernel    (fallback) the single-CTA kernel described next.
+//
+// mlp_tc_kernel: one persistent CTA per SM walks 128-row tiles of the flattened (rays x samples) batch.
 // For every tile the whole layer stack runs without touching HBM in between:
 //
 //   warp 0  (producer)  1-D bulk copies (cp.async.bulk -> UBLKCP) of pre-tiled, pre-swizzled
@@ -39,7 +44,6 @@ constexpr int kStages = 3;       // weight ring depth
 constexpr int kStagesX = 3;      // input-feature ring depth
 constexpr int kMlpThreads = 512; // warp 0 producer, 1 MMA, (2-3 idle), 4-11 epilogue, 12-15 feature generators
 constexpr int kEpiWarp0 = 4, kEpiWarps = 8, kFeatWarp0 = 12;
-constexpr int kJGroup = 7;       // basis directions per feature-generation group (3 groups of 7)
 constexpr int kTmemCols = 512;   // two accumulator buffers: consecutive tiles alternate, so the first layer of
                                  // tile t+1 (input = features, no dependence on tile t) overlaps tile t's last read-out
 constexpr int kIpeB = 21;        // geodesic basis directions (icosahedron, 2 subdivisions)
@@ -370,17 +374,81 @@ __device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, boo
   G.xd = G.x[0] * G.d[0] + G.x[1] * G.d[1] + G.x[2] * G.d[2];
 }
 
-// Produce the 8 feature chunks of one pass for row r into the X ring.  Kernel column order:
-//   col = jg*168 + l*14 + jj*2 + {0: sin, 1: cos},  j = jg*7 + jj   (3 groups of 7 directions)
-// so that a thread only carries 7 directions of recurrence state at a time.
+// One group of GS basis directions (JBASE .. JBASE + GS - 1), all 12 octaves, two directions per packed fp32x2
+// instruction (sm_100 FMUL2 / FFMA2 / FADD2): per direction pair and octave 8 packed instructions instead of 16
+// scalar ones.  emit(p, e sin, e cos) receives the pair index p = PBASE + l * GS + jj (columns 2p, 2p + 1).
+template <int GS, int JBASE, int PBASE, class Emit>
+__device__ __forceinline__ void ipe_group(const IpeArgs& A, const IpeRowGeom& G, Emit&& emit) {
+  constexpr float kInv2Pi = 0.15915494309189535f;
+  constexpr float k2PiHi = 6.2831854820251465f;           // fl32(2 pi)
+  constexpr float k2PiLo = -1.7484555e-07f;               // 2 pi - fl32(2 pi)
+  constexpr float kHalfLog2e = 0.72134752044448170f;      // 0.5 * log2(e)
+  constexpr int NP = (GS + 1) / 2;                        // packed pairs (an odd group pads with a copy of its last direction)
+  float2 s[NP], c[NP], e[NP], lv[NP], lm[NP];
+  // lifted mean  m_j = z.b_j  and variance  b_j^T J cov J^T b_j  with cov = t_var d d^T + r_var (I - d d^T/|d|^2):
+  //   v = J b_j = a b_j + bq (x.b_j) x ;  var = t_var (d.v)^2 + r_var (|v|^2 - (d.v)^2 / |d|^2)
+#pragma unroll
+  for (int jj = 0; jj < 2 * NP; ++jj) {
+    const int j = JBASE + (jj < GS ? jj : GS - 1);
+    const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
+    const float xb = G.x[0] * b0 + G.x[1] * b1 + G.x[2] * b2;
+    const float db = G.d[0] * b0 + G.d[1] * b1 + G.d[2] * b2;
+    const float k = G.bq * xb;
+    const float dv = fmaf(k, G.xd, G.a * db);
+    const float vv = G.a * G.a + k * (2.f * G.a * xb + k * G.m);        // |b_j| = 1
+    const float var = fmaxf(fmaf(G.t_var, dv * dv, G.r_var * (vv - dv * dv * G.inv_dsq)), 0.f);
+    const float mean = G.a * xb;
+    if (jj & 1) { lv[jj >> 1].y = var; lm[jj >> 1].y = mean; } else { lv[jj >> 1].x = var; lm[jj >> 1].x = mean; }
+  }
+  const float2 kNeg2 = make_float2(-2.f, -2.f), kOne = make_float2(1.f, 1.f);
+#pragma unroll
+  for (int l = 0; l < kIpeDeg; ++l) {
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      // ---- sin/cos of 2^l m_j: angle doubling, re-seeded from MUFU after Cody-Waite reduction every 4 octaves
+      if ((l & 3) == 0) {
+        const float ax = lm[q].x * (float)(1 << l), ay = lm[q].y * (float)(1 << l);
+        const float kx = rintf(ax * kInv2Pi), ky = rintf(ay * kInv2Pi);
+        const float rx = fmaf(-kx, k2PiLo, fmaf(-kx, k2PiHi, ax)), ry = fmaf(-ky, k2PiLo, fmaf(-ky, k2PiHi, ay));
+        s[q] = make_float2(__sinf(rx), __sinf(ry));
+        c[q] = make_float2(__cosf(rx), __cosf(ry));
+      } else {
+        const float2 nt = __fmul2_rn(s[q], kNeg2);         // -2 sin
+        const float2 sc = __fmul2_rn(s[q], c[q]);
+        c[q] = __ffma2_rn(nt, s[q], kOne);                 // 1 - 2 sin^2
+        s[q] = __fadd2_rn(sc, sc);                         // 2 sin cos
+      }
+      // ---- exp(-0.5 * 4^l * var_j): ex2 every 3rd octave, fourth powers in between
+      if ((l % 3) == 0) {
+        const float sc4 = -kHalfLog2e * (float)(1 << (2 * l));
+        e[q] = make_float2(exp2f(sc4 * lv[q].x), exp2f(sc4 * lv[q].y));
+      } else {
+        const float2 e2 = __fmul2_rn(e[q], e[q]);
+        e[q] = __fmul2_rn(e2, e2);
+      }
+      const float2 es = __fmul2_rn(e[q], s[q]), ec = __fmul2_rn(e[q], c[q]);
+      emit(PBASE + l * GS + 2 * q, es.x, ec.x);
+      if (2 * q + 1 < GS) emit(PBASE + l * GS + 2 * q + 1, es.y, ec.y);
+    }
+  }
+}
+
+// Produce the 8 feature chunks of one pass for row r into the X ring.  Kernel column order (the weight columns are
+// permuted to match at upload time, pack_weight_kernel): three groups of 8, 8 and 5 basis directions,
+//   col = 2 * (pbase_g + l * gs_g + jj) + {0: sin, 1: cos},  j = jbase_g + jj,  (pbase, jbase, gs) = (0,0,8) (96,8,8) (192,16,5)
+// so that a thread only carries one group's recurrence state at a time and the K-chunks come out in order.
+//   sin/cos(2^l m): angle doubling, re-seeded from MUFU sin/cos after Cody-Waite reduction every 4
+//                   octaves (error <= ~1e-5, below the fp16 resolution of the operand);
+//   exp(-.5 4^l v): ex2.approx every 3rd octave, e_{l+1} = e_l^4 in between.
 // kStg: ring depth.  kWarpArrive == false: every thread arrives on bar_xfull (count 128).
 // kWarpArrive == true (cluster-pair kernel): one arrival per warp, on the local bar_xfull (xfull_remote == 0)
 // or on the leader CTA's barrier at cluster address xfull_remote + 8 * stage.
 template <int kStg, bool kWarpArrive>
 __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRowGeom& G, int r, unsigned char* sRingX,
                                                   uint64_t* bar_xfull, uint64_t* bar_xempty, uint32_t& xi,
-                                                  uint32_t xfull_remote = 0) {
+                                                  uint32_t xfull_remote = 0, long long* tstamp = nullptr) {
   auto chunk_done = [&]() {
+    if (tstamp) *tstamp++ = clock64();
     fence_proxy_async();
     if (!kWarpArrive) {
       mbar_arrive(&bar_xfull[xi % kStg]);
@@ -393,72 +461,25 @@ __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRow
     }
     ++xi;
   };
-  constexpr float kInv2Pi = 0.15915494309189535f;
-  constexpr float k2PiHi = 6.2831854820251465f;           // fl32(2 pi)
-  constexpr float k2PiLo = -1.7484555e-07f;               // 2 pi - fl32(2 pi)
-  constexpr float kHalfLog2e = 0.72134752044448170f;      // 0.5 * log2(e)
   uint32_t pk[4];
-  unsigned char* slot = nullptr;
-#pragma unroll
-  for (int jg = 0; jg < kIpeB / kJGroup; ++jg) {
-    float s[kJGroup], c[kJGroup], e[kJGroup], lv[kJGroup], lm[kJGroup];
-    // lifted mean  m_j = z.b_j  and variance  b_j^T J cov J^T b_j  with cov = t_var d d^T + r_var (I - d d^T/|d|^2):
-    //   v = J b_j = a b_j + bq (x.b_j) x ;  var = t_var (d.v)^2 + r_var (|v|^2 - (d.v)^2 / |d|^2)
-#pragma unroll
-    for (int jj = 0; jj < kJGroup; ++jj) {
-      const int j = jg * kJGroup + jj;
-      const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
-      const float xb = G.x[0] * b0 + G.x[1] * b1 + G.x[2] * b2;
-      const float db = G.d[0] * b0 + G.d[1] * b1 + G.d[2] * b2;
-      const float k = G.bq * xb;
-      const float dv = fmaf(k, G.xd, G.a * db);
-      const float vv = G.a * G.a + k * (2.f * G.a * xb + k * G.m);        // |b_j| = 1
-      lv[jj] = fmaxf(fmaf(G.t_var, dv * dv, G.r_var * (vv - dv * dv * G.inv_dsq)), 0.f);
-      lm[jj] = G.a * xb;
+  const uint32_t row_u32 = smem_u32(sRingX) + 128u * (uint32_t)r, r7 = (uint32_t)(r & 7);
+  uint32_t slot = 0;                                       // shared-space address of row r in the current ring slot
+  auto emit = [&](int p, float sv, float cv) {             // p is a compile-time constant after unrolling
+    if ((p & 31) == 0) {                                   // first pair of a 64-column chunk: acquire a slot
+      const int xs = xi % kStg;
+      if (kWarpArrive) { mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1); if (tstamp) *tstamp++ = clock64(); }
+      else mbar_wait(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
+      slot = row_u32 + (uint32_t)xs * kXChunkBytes;
     }
-#pragma unroll
-    for (int l = 0; l < kIpeDeg; ++l) {
-#pragma unroll
-      for (int jj = 0; jj < kJGroup; ++jj) {
-        const int p = (jg * kIpeDeg + l) * kJGroup + jj;   // pair index; columns 2p, 2p+1
-        if ((p & 31) == 0) {                               // first pair of a 64-column chunk: acquire a slot
-          const int xs = xi % kStg;
-          if (kWarpArrive) mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
-          else mbar_wait(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
-          slot = sRingX + xs * kXChunkBytes;
-        }
-        // ---- sin/cos of 2^l m_j: angle doubling, re-seeded every 4 octaves
-        if ((l & 3) == 0) {
-          const float arg = lm[jj] * (float)(1 << l);
-          const float kq = rintf(arg * kInv2Pi);
-          float xr = fmaf(-kq, k2PiHi, arg);
-          xr = fmaf(-kq, k2PiLo, xr);
-          s[jj] = __sinf(xr);
-          c[jj] = __cosf(xr);
-        } else {
-          const float s2 = s[jj] * c[jj];
-          c[jj] = fmaf(-2.f * s[jj], s[jj], 1.f);
-          s[jj] = s2 + s2;
-        }
-        // ---- exp(-0.5 * 4^l * var_j): ex2 every 3rd octave, fourth powers in between
-        if ((l % 3) == 0) {
-          e[jj] = exp2f(-kHalfLog2e * (float)(1 << (2 * l)) * lv[jj]);
-        } else {
-          const float e2 = e[jj] * e[jj];
-          e[jj] = e2 * e2;
-        }
-        __half2 h = __floats2half2_rn(e[jj] * s[jj], e[jj] * c[jj]);
-        pk[p & 3] = *reinterpret_cast<uint32_t*>(&h);
-        if ((p & 3) == 3) {
-          const int g = (p & 31) >> 2;              // 16-byte group inside the chunk row
-          *reinterpret_cast<uint4*>(slot + r * 128 + ((g ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        }
-        if ((p & 31) == 31) chunk_done();           // chunk complete
-      }
-    }
-  }
+    pk[p & 3] = cvt_f16x2(__float_as_uint(sv), __float_as_uint(cv));
+    if ((p & 3) == 3) sts128(slot + ((((uint32_t)(p & 31) >> 2) ^ r7) << 4), pk[0], pk[1], pk[2], pk[3]);
+    if ((p & 31) == 31) chunk_done();                      // chunk complete
+  };
+  ipe_group<8, 0, 0>(A, G, emit);
+  ipe_group<8, 8, 96>(A, G, emit);
+  ipe_group<5, 16, 192>(A, G, emit);
   // 252 pairs = 7 chunks + 28 pairs: groups 0..6 of the last chunk are written, zero the 8th
-  *reinterpret_cast<uint4*>(slot + r * 128 + ((7 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+  sts128(slot + ((7u ^ r7) << 4), 0u, 0u, 0u, 0u);
   chunk_done();
 }
 
@@ -738,7 +759,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
 // + TMEM alloc, 4-11 epilogue, 12-15 feature generators.  Barriers that collect arrivals from both CTAs
 // live in the leader; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
 constexpr int kPairMaxStagesW = 8;
-constexpr int kPairStagesX = 2;
+constexpr int kPairStagesX = 3;
 constexpr int kPairProducers = 3;
 constexpr int kPairMaxKbh = 4;
 constexpr int kRowBiasVecs = 4;
@@ -1065,11 +1086,32 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                 f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
               }
             }
-            if (relu) {
+            if (!last) {
+              // store + signal FIRST: the next layer's MMAs start while this warp is still busy with the head
+              const uint32_t cb = (uint32_t)c * kXChunkBytes;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              for (int gq = 0; gq < 4; ++gq) {
+                uint32_t p0, p1, p2, p3;
+                if (relu) {
+                  p0 = cvt_relu_f16x2(__float_as_uint(f[gq * 8 + 0]), __float_as_uint(f[gq * 8 + 1]));
+                  p1 = cvt_relu_f16x2(__float_as_uint(f[gq * 8 + 2]), __float_as_uint(f[gq * 8 + 3]));
+                  p2 = cvt_relu_f16x2(__float_as_uint(f[gq * 8 + 4]), __float_as_uint(f[gq * 8 + 5]));
+                  p3 = cvt_relu_f16x2(__float_as_uint(f[gq * 8 + 6]), __float_as_uint(f[gq * 8 + 7]));
+                } else {
+                  p0 = cvt_f16x2(__float_as_uint(f[gq * 8 + 0]), __float_as_uint(f[gq * 8 + 1]));
+                  p1 = cvt_f16x2(__float_as_uint(f[gq * 8 + 2]), __float_as_uint(f[gq * 8 + 3]));
+                  p2 = cvt_f16x2(__float_as_uint(f[gq * 8 + 4]), __float_as_uint(f[gq * 8 + 5]));
+                  p3 = cvt_f16x2(__float_as_uint(f[gq * 8 + 6]), __float_as_uint(f[gq * 8 + 7]));
+                }
+                sts128(h_off[gq] + cb, p0, p1, p2, p3);
+              }
+              chunk_ready(c);
             }
             if (has_head) {
+              if (relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
 #pragma unroll
               for (int n = 0; n < 4; ++n) {
                 if (n < Hd.hn) {
@@ -1084,16 +1126,6 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                   hacc[n] = a;
                 }
               }
-            }
-            if (!last) {
-              const uint32_t cb = (uint32_t)c * kXChunkBytes;
-#pragma unroll
-              for (int gq = 0; gq < 4; ++gq)
-                sts128(h_off[gq] + cb, cvt_f16x2(__float_as_uint(f[gq * 8 + 0]), __float_as_uint(f[gq * 8 + 1])),
-                       cvt_f16x2(__float_as_uint(f[gq * 8 + 2]), __float_as_uint(f[gq * 8 + 3])),
-                       cvt_f16x2(__float_as_uint(f[gq * 8 + 4]), __float_as_uint(f[gq * 8 + 5])),
-                       cvt_f16x2(__float_as_uint(f[gq * 8 + 6]), __float_as_uint(f[gq * 8 + 7])));
-              chunk_ready(c);
             }
           };
           for (int c = 0; c < nchunks; ++c) {       // single-buffered: this path also carries the head accumulators
@@ -1148,7 +1180,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         if (tl) args.timeline[u * 12 + 6] = clock64();
         IpeRowGeom G;
         ipe_row_setup(ipe, row, row < args.rows, G);
-        ipe_generate_pass<kPairStagesX, true>(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi, xremote);
+        ipe_generate_pass<kPairStagesX, true>(ipe, G, r, sRingX, bar_xfull, bar_xempty, xi, xremote,
+                                              (tl && (u == 9 || u == 14)) ? args.timeline + 900 + (u == 14 ? 20 : 0) : nullptr);
         if (tl) args.timeline[u * 12 + 7] = clock64();
       }
     }
@@ -1167,7 +1200,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
 // -> fp16 chunks in kernel K order: kb_h chunks of h columns, then kb_x chunks of x columns.
 // ipe_perm != 0: the x columns are re-ordered from the reference's IPE layout
 // f = half*252 + l*21 + j  to the kernel's generation order
-// col = jg*168 + l*14 + jj*2 + half  with j = jg*7 + jj.
+// col = 2 * (pbase_g + l * gs_g + jj) + half,  j = jbase_g + jj  (groups of 8, 8, 5 directions; see ipe_generate_pass).
 __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h, int in_x, int x_first, int kb_h,
                                    int kb_x, int ipe_perm, unsigned char* __restrict__ dst) {
   const int nkb = kb_h + kb_x;
@@ -1186,8 +1219,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h,
     if (c < in_x) {
       if (ipe_perm) {
         const int half = c & 1, pr = c >> 1;
-        const int jg = pr / (kIpeDeg * kJGroup), l = (pr / kJGroup) % kIpeDeg, jj = pr % kJGroup;
-        c = half * (kIpeDeg * kIpeB) + l * kIpeB + jg * kJGroup + jj;
+        const int gs = pr < 192 ? 8 : 5, pb = pr < 96 ? 0 : (pr < 192 ? 96 : 192), jb = pr < 96 ? 0 : (pr < 192 ? 8 : 16);
+        const int l = (pr - pb) / gs, jj = (pr - pb) % gs;
+        c = half * (kIpeDeg * kIpeB) + l * kIpeB + jb + jj;
       }
       v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
     }

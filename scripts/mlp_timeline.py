@@ -71,3 +71,10 @@ if variant == 2:
             print(f"unit {uu} MMA thread groups (rel. to mma_enter): [wait_start, wait_end, issued]",
                   [(c[i * 3] - ref, c[i * 3 + 1] - ref, c[i * 3 + 2] - ref) for i in range(5) if c[i * 3]],
                   "| epilogue acc_ready/epi_done of previous unit:", int(tt[(uu - 1) * 12 + 4]) - ref, int(tt[(uu - 1) * 12 + 5]) - ref)
+
+if variant == 2:
+    for base, name in ((900, "unit 9 (l0)"), (920, "unit 14 (skip)")):
+        c = [int(x) for x in buf.cpu()[base:base + 17]]
+        if c[0]:
+            print(name, "feature warp 12: per chunk (slot acquired -> chunk done = compute), then (chunk done -> next slot acquired = blocked):",
+                  [(c[2 * i + 1] - c[2 * i], (c[2 * i + 2] - c[2 * i + 1]) if i < 7 else 0) for i in range(8)])
