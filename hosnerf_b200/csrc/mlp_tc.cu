@@ -1031,9 +1031,31 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           if (lane == 0) mbar_arrive_remote(hready0 + 8u * c);
         };
 
-        if (!has_head && !last && !rb_s && !rb_g) {
-          // ---------- plain hidden layer (bias already in the accumulator): convert (+ ReLU) and store, nothing else.
+        const HeadDev Hd = prog.heads[has_head ? L.head : 0];
+        float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!last && !rb_s && !rb_g) {
+          // ---------- hidden layer (bias already in the accumulator): convert (+ ReLU), store, signal; a layer that also
+          // feeds an fp32 head (density) accumulates it AFTER the signal, so the next layer's MMAs are not held up.
           // Two TMEM loads in flight: the next chunk's 32 columns arrive while these are converted.
+          auto head32 = [&](const uint32_t (&v)[32], int c) {
+            const int c0 = c * 64 + ch * 32;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              if (n < Hd.hn) {
+                const uint32_t w4 = sparams_u32 + 4u * (uint32_t)(Hd.w_off + n * L.n + c0);
+                float a = hacc[n];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w = lds128(w4 + 16u * j);
+                  const float f0 = __uint_as_float(v[4 * j + 0]), f1 = __uint_as_float(v[4 * j + 1]);
+                  const float f2 = __uint_as_float(v[4 * j + 2]), f3 = __uint_as_float(v[4 * j + 3]);
+                  a = fmaf(relu ? fmaxf(f0, 0.f) : f0, w.x, a); a = fmaf(relu ? fmaxf(f1, 0.f) : f1, w.y, a);
+                  a = fmaf(relu ? fmaxf(f2, 0.f) : f2, w.z, a); a = fmaf(relu ? fmaxf(f3, 0.f) : f3, w.w, a);
+                }
+                hacc[n] = a;
+              }
+            }
+          };
           auto store32 = [&](const uint32_t (&v)[32], int c) {
             const uint32_t cb = (uint32_t)c * kXChunkBytes;
 #pragma unroll
@@ -1057,17 +1079,17 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             if (more1) tmem_ld32_nowait(acc + (uint32_t)((c + 1) * 64), vb);
             store32(va, c);
             chunk_ready(c);
+            if (has_head) head32(va, c);
             if (more1) {
               tmem_wait_ld();
               if (c + 2 < nchunks) tmem_ld32_nowait(acc + (uint32_t)((c + 2) * 64), va);
               store32(vb, c + 1);
               chunk_ready(c + 1);
+              if (has_head) head32(vb, c + 1);
             }
           }
         } else {
           // ---------- general layer: per-row bias, fp32 output head, last layer (no activations stored)
-          const HeadDev Hd = prog.heads[has_head ? L.head : 0];
-          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
           auto process_general = [&](uint32_t (&v)[32], int c) {
             const int c0 = c * 64 + ch * 32;
             float f[32];
@@ -1134,6 +1156,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             tmem_wait_ld();
             process_general(v, c);
           }
+        }
+        {
           if (last) tc_fence_before();
           if (has_head) {                         // combine the two column halves, then post-process
             if (ch == 1) sts128(headx_u32, __float_as_uint(hacc[0]), __float_as_uint(hacc[1]), __float_as_uint(hacc[2]), __float_as_uint(hacc[3]));
