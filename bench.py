@@ -58,36 +58,64 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML (a few ms per sample) when
+    nvidia_ml_py is importable, else nvidia-smi (one sample per ~100 ms)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and all(x.strip().isdigit() for x in visible.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = get(self.handle)
+        flags = [bool(r & n.nvmlClocksEventReasonHwSlowdown), bool(r & n.nvmlClocksEventReasonHwThermalSlowdown),
+                 bool(r & n.nvmlClocksEventReasonSwThermalSlowdown), bool(r & n.nvmlClocksEventReasonSwPowerCap)]
+        return [str(mhz), str(self.max_mhz)] + ["Active" if f else "Not Active" for f in flags]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    time.sleep(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
             except Exception:
-                pass
+                if self.nvml is not None:
+                    self.nvml = None       # fall back to nvidia-smi
+                    continue
             time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "n_samples": len(self.samples)}
+                "reasons": reasons, "n_samples": len(self.samples),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_steps(n_rays, steps, warmup, threads):
@@ -133,7 +161,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])

@@ -447,9 +447,33 @@ template <int kStg, bool kWarpArrive>
 __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRowGeom& G, int r, unsigned char* sRingX,
                                                   uint64_t* bar_xfull, uint64_t* bar_xempty, uint32_t& xi,
                                                   uint32_t xfull_remote = 0, long long* tstamp = nullptr) {
-  auto chunk_done = [&]() {
+  const uint32_t xempty_u32 = smem_u32(bar_xempty);
+  uint32_t pk[4];
+  const uint32_t row_u32 = smem_u32(sRingX) + 128u * (uint32_t)r, r7 = (uint32_t)(r & 7);
+  uint32_t slot = 0;                                       // shared-space address of row r in the current ring slot
+  auto acquire = [&]() {                                   // wait until ring slot xi % kStg has been consumed
+    const int xs = xi % kStg;
+    if (kWarpArrive) mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
+    else mbar_wait(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
     if (tstamp) *tstamp++ = clock64();
-    fence_proxy_async();
+    slot = row_u32 + (uint32_t)xs * kXChunkBytes;
+  };
+  // Publish chunk xi.  with_next: also poll the NEXT slot's "consumed" barrier - the phase check is issued before the
+  // proxy fence so that its ~150-cycle latency hides behind the fence instead of following it.
+  auto chunk_done = [&](bool with_next) {
+    if (tstamp) *tstamp++ = clock64();
+    uint32_t next_free = 0;
+    if (with_next) {
+      const uint32_t nx = (xi + 1) % kStg, npar = (((xi + 1) / kStg) & 1) ^ 1;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "fence.proxy.async.shared::cta;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(next_free) : "r"(xempty_u32 + 8u * nx), "r"(npar) : "memory");
+    } else {
+      fence_proxy_async();
+    }
     if (!kWarpArrive) {
       mbar_arrive(&bar_xfull[xi % kStg]);
     } else {
@@ -460,27 +484,27 @@ __device__ __forceinline__ void ipe_generate_pass(const IpeArgs& A, const IpeRow
       }
     }
     ++xi;
-  };
-  uint32_t pk[4];
-  const uint32_t row_u32 = smem_u32(sRingX) + 128u * (uint32_t)r, r7 = (uint32_t)(r & 7);
-  uint32_t slot = 0;                                       // shared-space address of row r in the current ring slot
-  auto emit = [&](int p, float sv, float cv) {             // p is a compile-time constant after unrolling
-    if ((p & 31) == 0) {                                   // first pair of a 64-column chunk: acquire a slot
-      const int xs = xi % kStg;
-      if (kWarpArrive) { mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1); if (tstamp) *tstamp++ = clock64(); }
-      else mbar_wait(&bar_xempty[xs], ((xi / kStg) & 1) ^ 1);
-      slot = row_u32 + (uint32_t)xs * kXChunkBytes;
+    if (with_next) {
+      if (next_free) {
+        if (tstamp) *tstamp++ = clock64();
+        slot = row_u32 + (uint32_t)(xi % kStg) * kXChunkBytes;
+      } else {
+        acquire();
+      }
     }
+  };
+  auto emit = [&](int p, float sv, float cv) {             // p is a compile-time constant after unrolling
+    if (p == 0) acquire();                                 // first chunk of the pass; later slots come from chunk_done(true)
     pk[p & 3] = cvt_f16x2(__float_as_uint(sv), __float_as_uint(cv));
     if ((p & 3) == 3) sts128(slot + ((((uint32_t)(p & 31) >> 2) ^ r7) << 4), pk[0], pk[1], pk[2], pk[3]);
-    if ((p & 31) == 31) chunk_done();                      // chunk complete
+    if ((p & 31) == 31) chunk_done(true);                  // chunk complete, more follow in this pass
   };
   ipe_group<8, 0, 0>(A, G, emit);
   ipe_group<8, 8, 96>(A, G, emit);
   ipe_group<5, 16, 192>(A, G, emit);
   // 252 pairs = 7 chunks + 28 pairs: groups 0..6 of the last chunk are written, zero the 8th
   sts128(slot + ((7u ^ r7) << 4), 0u, 0u, 0u, 0u);
-  chunk_done();
+  chunk_done(false);
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1)
