@@ -270,6 +270,53 @@ def test_fused_mlp_tcgen05_vs_emulation(width, depth, in_dim, skip, rows, mlp_va
     assert rel_err(out.cpu(), h @ hw.T + hb) < 3e-2
 
 
+@pytest.mark.parametrize("mlp_variant", [1, 2], indirect=True)
+@pytest.mark.parametrize("rows,div", [(128 * 5 + 17, 128), (128 * 4, 64), (128 * 3 + 1, 32), (700, 200), (128 * 6, 256), (100, 7)])
+def test_fused_mlp_rowbias_heads_and_ragged_tiles(rows, div, mlp_variant):
+    """The NeRF-MLP shape of the program: hidden ReLU layers, an fp32 head on a hidden layer (density, softplus), a
+    narrower last layer with a per-ray bias (view term) and a second head (rgb, padded sigmoid) - for ray lengths
+    that divide a 128-row tile, span several tiles, or do neither (per-row global bias path), and for batches that
+    end in a partial tile / an odd number of tiles (the pair kernel pads its second CTA)."""
+    gen = torch.Generator().manual_seed(rows + div)
+    width, in_dim, nlast = 256, 63, 128
+    x = torch.randn(rows, in_dim, generator=gen)
+
+    def mk(o, i):
+        return (torch.rand(o, i, generator=gen) * 2 - 1) * (6.0 / i) ** 0.5, (torch.rand(o, generator=gen) * 2 - 1) * 0.1
+
+    Ws = [mk(width, in_dim), mk(width, width), mk(width, width), mk(nlast, width)]
+    hd_w, hd_b = torch.randn(1, width, generator=gen) / width ** 0.5, torch.randn(1, generator=gen) * 0.1
+    hr_w, hr_b = torch.randn(3, nlast, generator=gen) / nlast ** 0.5, torch.randn(3, generator=gen) * 0.1
+    n_rays = (rows + div - 1) // div
+    rowbias = torch.randn(n_rays, nlast, generator=gen) * 0.3
+    desc = [dict(out_dim=width, in_h=0, in_x=in_dim, x_first=0, relu=1, rowbias=0, head=-1),
+            dict(out_dim=width, in_h=width, in_x=0, x_first=0, relu=1, rowbias=0, head=-1),
+            dict(out_dim=width, in_h=width, in_x=0, x_first=0, relu=1, rowbias=0, head=0),
+            dict(out_dim=nlast, in_h=width, in_x=0, x_first=0, relu=1, rowbias=1, head=1)]
+    heads = [dict(out_dim=1, post=1, shift=-1.0, out_slot=0), dict(out_dim=3, post=2, shift=0.001, out_slot=1)]
+    fm = ops.FusedMLP(in_dim, desc, heads)
+    for i, (W, b) in enumerate(Ws):
+        fm.set_layer(i, cu(W), cu(b) if i < 3 else None)       # the last layer's bias travels in the per-ray term
+    fm.set_head(0, cu(hd_w), cu(hd_b))
+    fm.set_head(1, cu(hr_w), cu(hr_b))
+    dens, rgb = fm.forward(ops.pack_rows_f16(cu(x)), rows, rowbias=cu(rowbias), rowbias_div=div)
+    torch.cuda.synchronize()
+    # emulation: fp16 operands, fp32 accumulate, activations rounded to fp16 between layers, heads in fp32
+    h16 = x.half().float()
+    h = None
+    for i, (W, b) in enumerate(Ws):
+        pre = h16.double() @ W.half().double().T
+        pre = pre + (b.double() if i < 3 else rowbias.double()[torch.arange(rows) // div])
+        h = torch.relu(pre).float()
+        if i == 2:
+            d_ref = torch.nn.functional.softplus(h.double() @ hd_w.double().T + hd_b.double() - 1.0).float()
+        h16 = h.half().float()
+    r_ref = (torch.sigmoid(h.double() @ hr_w.double().T + hr_b.double()) * 1.002 - 0.001).float()
+    assert dens.shape == (rows, 1) and rgb.shape == (rows, 3)
+    assert rel_err(dens.cpu(), d_ref) < 1e-2, rel_err(dens.cpu(), d_ref)
+    assert max_abs(rgb.cpu(), r_ref) < 5e-3, max_abs(rgb.cpu(), r_ref)
+
+
 def test_pair_kernel_matches_single_cta_kernel_fused_ipe():
     """The cluster-pair kernel (cta_group::2, two row tiles per SM in ping-pong) and the single-CTA kernel run
     the same fp16 program: C2 shape with the fused IPE prologue, ray count not a multiple of a 4-tile group."""
