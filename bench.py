@@ -276,10 +276,10 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            n = 1024
-            sec = cpu_reference_steps(n, 1, 1, threads)
+            n = 2048
+            sec = cpu_reference_steps(n, 2, 1, threads)
             line["cpu_baseline"] = {"value": n * SAMPLES_PER_RAY / sec, "unit": "ray-samples/s", "cores": threads,
-                                    "kind": "port", "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 1 timed pass, torch CPU fp32 oracle"}
+                                    "kind": "port", "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 2 timed passes, torch CPU fp32 oracle"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
