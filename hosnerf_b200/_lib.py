@@ -58,6 +58,11 @@ SIGNATURES = {
     "hos_mlp_debug_timeline": (c_i, [c_f]),
     "hos_mlp_set_variant": (c_i, [c_i]),
     "hos_pack_rows_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f]),
+    "hos_gemm_create": (C.c_void_p, [c_i, c_i, c_i, c_i]),
+    "hos_gemm_destroy": (None, [C.c_void_p]),
+    "hos_gemm_set_weight": (c_i, [C.c_void_p, c_f, c_f, c_f]),
+    "hos_gemm_set_head": (c_i, [C.c_void_p, c_i, c_f, c_f, c_f]),
+    "hos_gemm_forward": (c_i, [C.c_void_p, c_f, c_f, c_l, c_i, c_f, c_f, c_i, c_fl, c_f]),
     "hos_composite_mip360": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "hos_composite_s3": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_hp, c_f, c_f, c_i, c_i, c_i, c_fl,
@@ -67,7 +72,7 @@ SIGNATURES = {
 _lib = None
 LAUNCHES = 0          # kernels of this library launched so far (bench.py reports it per timed region)
 _KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_layer": 2, "hos_mlp_set_bias": 1, "hos_mlp_set_head": 0,
-                     "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0}
+                     "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0, "hos_gemm_set_head": 0}
 
 
 def load():

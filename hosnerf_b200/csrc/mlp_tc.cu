@@ -1306,6 +1306,265 @@ __global__ void pack_rows_kernel(const float* __restrict__ X, int64_t rows, int 
       __float2half_rn(v);
 }
 
+// ============================================================================ wide-layer GEMM (cluster pair)
+// Layers wider than 256 (the reference's default NeRFMLP is 1024 wide) cannot keep a tile's activations on chip
+// (128 rows x 1024 fp16 = 256 KB), so they run layer by layer through L2/HBM:
+//     Y[rows, N] = act([A0 | A1][rows, K0 + K1] * W^T + b)         A0, A1, Y in the tiled fp16 layout
+// with the same building blocks as mlp_pair_kernel: tcgen05.mma.cta_group::2 (M = 256 rows per cluster, N = 256 per
+// unit), half of every weight chunk per CTA, mbarrier rings fed by several bulk-copy producer warps per operand
+// (one thread's copies serialise), accumulator double-buffered in TMEM.  Units (tile pair, 256-column block) are
+// independent, so the epilogue of unit u (bias, ReLU, optional fp32 head, 16-byte stores of the tiled output)
+// simply overlaps the MMAs of unit u + 1 - no per-layer dead time here.
+constexpr int kGemmStages = 6;          // per operand ring (A: 16 KB stages, W: 16 KB = this CTA's 128 of 256 rows)
+constexpr int kGemmNB = 256;            // output columns per unit
+constexpr int kGemmBars = 2 * kGemmStages + 4;
+constexpr int kGemmWProducers = 3;      // warps 0, 2, 3
+constexpr int kGemmAProducers = 4;      // warps 12..15
+
+struct GemmArgs {
+  const unsigned char* a0;     // tiled fp16 [ntiles][kb0][16 KB]
+  const unsigned char* a1;     // optional second input (skip connection), [ntiles][kb1][16 KB]
+  const unsigned char* w;      // packed [N / 256][kb0 + kb1][256 x 128 B]
+  const float* params;         // [N] bias, then [hn][N] head weights, then [4] head bias
+  unsigned char* y;            // tiled fp16 [ntiles][N / 64][16 KB], or null
+  float* head_out;             // [rows][hn] or null
+  int64_t rows;
+  int ntiles, kb0, kb1, n, relu;
+  int hn, head_post;
+  float head_shift;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kWStage = kGemmNB * 64;                     // 16 KB: this CTA's half of a [256 x 64] weight chunk
+  unsigned char* sRingA = smem;                             // [kGemmStages][16 KB]
+  unsigned char* sRingW = sRingA + kGemmStages * kXChunkBytes;
+  float* sParams = reinterpret_cast<float*>(sRingW + kGemmStages * kWStage);
+  const int param_floats = args.n * (1 + args.hn) + 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((param_floats + 3) & ~3));
+  // The A and W rings move in lock step, so stage s of both shares one pair of barriers:
+  uint64_t* bar_full = bars;                                // leader: A + W of both CTAs landed (2 tx arrivals + 2 relays); peer: its own two
+  uint64_t* bar_empty = bar_full + kGemmStages;             // multicast commit: stage s of both rings consumed
+  uint64_t* bar_tfull = bar_empty + kGemmStages;            // [2] multicast commit: accumulator buffer complete
+  uint64_t* bar_tempty = bar_tfull + 2;                     // [2] leader only: drained by the 16 epilogue warps of the pair
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kGemmBars);
+  float* s_headx = reinterpret_cast<float*>(s_tmem + 4);    // [128][4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int n_groups = (args.ntiles + 1) >> 1;              // 2 tiles per group: tile = 2 g + rank
+  const int KB = args.kb0 + args.kb1;
+  const int nblk = args.n / kGemmNB;
+
+  for (int i = threadIdx.x; i < param_floats; i += kMlpThreads) sParams[i] = args.params[i];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const bool w_producer = warp == 0 || warp == 2 || warp == 3;
+  const bool a_producer = warp >= kFeatWarp0;
+  if (w_producer || a_producer) {
+    // ===================== producers: chunk i of the flat stream -> producer i % P, ring stage i % kGemmStages ========
+    if (lane == 0) {
+      const uint32_t P = w_producer ? kGemmWProducers : kGemmAProducers;
+      const uint32_t p = w_producer ? (warp == 0 ? 0u : (uint32_t)(warp - 1)) : (uint32_t)(warp - kFeatWarp0);
+      uint64_t* full = bar_full;
+      uint64_t* empty = bar_empty;
+      unsigned char* ring = w_producer ? sRingW : sRingA;
+      uint32_t ci = 0;
+      for (int g = cluster; g < n_groups; g += n_clusters) {
+        int tile = 2 * g + (int)rank;
+        if (tile >= args.ntiles) tile = args.ntiles - 1;           // padding tile: any valid rows, nothing is stored
+        for (int j = 0; j < nblk; ++j) {
+          for (int kb = 0; kb < KB; ++kb, ++ci) {
+            if (ci % P != p) continue;
+            const uint32_t st = ci % kGemmStages, use = ci / kGemmStages;
+            mbar_wait_guard<100>(&empty[st], (use & 1) ^ 1);
+            mbar_expect_tx(&full[st], kXChunkBytes);
+            const unsigned char* src;
+            if (w_producer) {
+              src = args.w + ((size_t)j * KB + kb) * (2u * kWStage) + rank * kWStage;
+            } else {
+              src = kb < args.kb0 ? args.a0 + ((size_t)tile * args.kb0 + kb) * kXChunkBytes
+                                  : args.a1 + ((size_t)tile * args.kb1 + (kb - args.kb0)) * kXChunkBytes;
+            }
+            bulk_g2s(ring + st * kXChunkBytes, src, kXChunkBytes, &full[st]);
+            if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
+              mbar_wait_guard<100>(&full[st], use & 1);
+              mbar_arrive_remote(mapa_u32(smem_u32(&full[st]), 0));
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform loop, tcgen05 instructions under elect.sync =====================
+    if (rank == 0) {
+      uint32_t u = 0, st = 0, par = 0;                 // unit counter; ring cursor + phase parity (A and W rings move in lock step)
+      const uint64_t desc_hi = umma_desc(0);
+      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      const uint32_t tfull0 = smem_u32(&bar_tfull[0]);
+      const uint32_t a16 = (smem_u32(sRingA) >> 4) & 0x3FFF, w16 = (smem_u32(sRingW) >> 4) & 0x3FFF;
+      const uint32_t idesc = umma_idesc_f16(kGemmNB, 2 * kTileM);
+      for (int g = cluster; g < n_groups; g += n_clusters) {
+        for (int j = 0; j < nblk; ++j, ++u) {
+          const uint32_t acc = tmem_base + (u & 1) * 256;
+          if (u >= 2) mbar_wait_guard<0>(&bar_tempty[u & 1], ((u >> 1) - 1) & 1);     // buffer drained by unit u - 2
+          int kb = 0;
+          while (kb < KB) {
+            // up to four chunks per group: one parallel poll (~220 cycles) and the issue overhead amortised over 2048
+            // cycles of tensor work
+            const int cnt = KB - kb < 4 ? KB - kb : 4;
+            uint32_t fb[4], fp[4];
+            {
+              uint32_t s_ = st, p_ = par;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                fb[i] = full0 + 8u * s_; fp[i] = p_;
+                if (i + 1 < cnt) { if (++s_ == kGemmStages) { s_ = 0; p_ ^= 1; } }
+              }
+            }
+            mbar_wait4_spin(fb[0], fp[0], fb[1], fp[1], fb[2], fp[2], fb[3], fp[3]);
+            tc_fence_after();
+            const bool leader_lane = elect_one();
+#pragma unroll 1
+            for (int i = 0; i < cnt; ++i) {
+              if (leader_lane) {
+                const uint64_t adesc = desc_hi | (uint64_t)(a16 + st * (kXChunkBytes >> 4));
+                const uint64_t bdesc = desc_hi | (uint64_t)(w16 + st * (kWStage >> 4));
+#pragma unroll
+                for (int k = 0; k < kKB / 16; ++k)
+                  tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb + i) != 0 || k != 0 ? 1u : 0u);
+                tc_commit_pair_addr(empty0 + 8u * st);
+                if (kb + i == KB - 1) tc_commit_pair_addr(tfull0 + 8u * (u & 1));
+              }
+              if (++st == kGemmStages) { st = 0; par ^= 1; }
+            }
+            __syncwarp();
+            kb += cnt;
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    // ===================== epilogue (8 warps): bias, ReLU, optional fp32 head, tiled fp16 store =====================
+    const int q = warp & 3;
+    const int ch = (warp - kEpiWarp0) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
+    const uint32_t sparams_u32 = smem_u32(sParams);
+    const uint32_t headx_u32 = smem_u32(s_headx) + 16u * r;
+    const bool has_head = args.hn > 0 && args.head_out != nullptr;
+    uint32_t u = 0;
+    for (int g = cluster; g < n_groups; g += n_clusters) {
+      const int tile = 2 * g + (int)rank;
+      const int64_t row = (int64_t)tile * kTileM + r;
+      const bool row_ok = row < args.rows, tile_ok = tile < args.ntiles;
+      float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < nblk; ++j, ++u) {
+        const uint32_t acc = tmem_base + (u & 1) * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        mbar_wait_guard<20>(&bar_tfull[u & 1], (u >> 1) & 1);
+        tc_fence_after();
+        for (int c = 0; c < kGemmNB / 64; ++c) {
+          const int n0 = j * kGemmNB + c * 64 + ch * 32;           // first of this thread's 32 output columns
+          uint32_t v[32];
+          tmem_ld32_nowait(acc + (uint32_t)(c * 64), v);
+          tmem_wait_ld();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = lds128(sparams_u32 + 4u * (uint32_t)n0 + 16u * i);
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+          }
+          if (args.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (args.y && tile_ok) {
+            unsigned char* dst = args.y + ((size_t)tile * (args.n >> 6) + (size_t)(j * (kGemmNB / 64) + c)) * kXChunkBytes;
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              uint4 pk;
+              pk.x = cvt_f16x2(__float_as_uint(f[gq * 8 + 0]), __float_as_uint(f[gq * 8 + 1]));
+              pk.y = cvt_f16x2(__float_as_uint(f[gq * 8 + 2]), __float_as_uint(f[gq * 8 + 3]));
+              pk.z = cvt_f16x2(__float_as_uint(f[gq * 8 + 4]), __float_as_uint(f[gq * 8 + 5]));
+              pk.w = cvt_f16x2(__float_as_uint(f[gq * 8 + 6]), __float_as_uint(f[gq * 8 + 7]));
+              *reinterpret_cast<uint4*>(dst + tile_byte_offset(r, ch * 32 + gq * 8)) = pk;
+            }
+          }
+          if (has_head) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              if (h < args.hn) {
+                const uint32_t w4 = sparams_u32 + 4u * (uint32_t)(args.n * (1 + h) + n0);
+                float a = hacc[h];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 w = lds128(w4 + 16u * i);
+                  a = fmaf(f[4 * i + 0], w.x, a); a = fmaf(f[4 * i + 1], w.y, a);
+                  a = fmaf(f[4 * i + 2], w.z, a); a = fmaf(f[4 * i + 3], w.w, a);
+                }
+                hacc[h] = a;
+              }
+            }
+          }
+        }
+        tc_fence_before();          // TMEM loads ordered before the arrive
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(tempty0 + 8u * (u & 1));
+      }
+      if (has_head) {                           // combine the two column halves of this tile's rows, then post-process
+        if (ch == 1) sts128(headx_u32, __float_as_uint(hacc[0]), __float_as_uint(hacc[1]), __float_as_uint(hacc[2]), __float_as_uint(hacc[3]));
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (ch == 0 && row_ok) {
+          const float4 o4 = lds128(headx_u32);
+          hacc[0] += o4.x; hacc[1] += o4.y; hacc[2] += o4.z; hacc[3] += o4.w;
+          const float4 hb = lds128(sparams_u32 + 4u * (uint32_t)(args.n * (1 + args.hn)));
+          const float hbias[4] = {hb.x, hb.y, hb.z, hb.w};
+          float* o = args.head_out + row * args.hn;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h >= args.hn) break;
+            float x = hacc[h] + hbias[h];
+            if (args.head_post == 1) {
+              float z = x + args.head_shift;
+              x = z > 20.f ? z : log1pf(expf(z));
+            } else if (args.head_post == 2) {
+              x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * args.head_shift) - args.head_shift;
+            } else if (args.head_post == 4) {
+              x = (h < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+            }
+            o[h] = x;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
+  }
+}
+
 }  // namespace hos
 
 using namespace hos;
@@ -1586,6 +1845,121 @@ int hos_pack_rows_f16(const float* X, int64_t rows, int ld, int K, void* dst_til
   int64_t total = ntiles * kTileM * (int64_t)kbx * kKB;
   pack_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       X, rows, ld, K, kbx, (unsigned char*)dst_tiled, total);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}
+
+// ----------------------------------------------------------------------------- wide-layer GEMM handle
+struct hos_gemm {
+  int n = 0, k0 = 0, k1 = 0, kb0 = 0, kb1 = 0, x_first = 0, hn = 0;
+  unsigned char* d_w = nullptr;     // packed fp16 [n / 256][kb0 + kb1][256 x 128 B]
+  float* d_params = nullptr;        // [n] bias | [4][n] head weights | [4] head bias
+  size_t smem_bytes = 0;
+  int max_clusters = 0;
+};
+
+hos_gemm_t* hos_gemm_create(int n_out, int k0, int k1, int x_first) {
+  if (hos::check_arch() != HOS_OK) return nullptr;
+  if (n_out < kGemmNB || (n_out % kGemmNB) != 0 || n_out > 4096 || k0 < 1 || k1 < 0) {
+    hos::set_error("hos_gemm_create: n_out must be a multiple of %d (got %d), k0 >= 1, k1 >= 0", kGemmNB, n_out);
+    return nullptr;
+  }
+  hos_gemm* m = new hos_gemm();
+  m->n = n_out; m->k0 = k0; m->k1 = k1; m->x_first = x_first;
+  m->kb0 = (k0 + kKB - 1) / kKB;
+  m->kb1 = (k1 + kKB - 1) / kKB;
+  const size_t wbytes = (size_t)(n_out / kGemmNB) * (m->kb0 + m->kb1) * kGemmNB * 128;
+  const size_t pfloats = (size_t)n_out * 5 + 4;
+  m->smem_bytes = 1024 + (size_t)kGemmStages * (kXChunkBytes + kGemmNB * 64) + ((pfloats + 3) & ~(size_t)3) * 4 +
+                  kGemmBars * 8 + 16 + kTileM * 4 * sizeof(float);
+  if (m->smem_bytes > 227 * 1024) {
+    hos::set_error("hos_gemm_create: needs %zu B shared memory (> 227 KB)", m->smem_bytes);
+    delete m;
+    return nullptr;
+  }
+  if (cudaMalloc(&m->d_w, wbytes) != cudaSuccess || cudaMalloc(&m->d_params, pfloats * 4) != cudaSuccess ||
+      cudaMemset(m->d_params, 0, pfloats * 4) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
+    hos::set_error("hos_gemm_create: CUDA allocation/attribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    hos_gemm_destroy(m);
+    return nullptr;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kNumSMs);
+  cfg.blockDim = dim3(kMlpThreads);
+  cfg.dynamicSmemBytes = m->smem_bytes;
+  int nc = 0;
+  if (cudaOccupancyMaxActiveClusters(&nc, gemm_pair_kernel, &cfg) != cudaSuccess || nc < 1) {
+    cudaGetLastError();
+    nc = kNumSMs / 2;
+  }
+  m->max_clusters = nc < kNumSMs / 2 ? nc : kNumSMs / 2;
+  return m;
+}
+
+void hos_gemm_destroy(hos_gemm_t* m) {
+  if (!m) return;
+  if (m->d_w) cudaFree(m->d_w);
+  if (m->d_params) cudaFree(m->d_params);
+  delete m;
+}
+
+int hos_gemm_set_weight(hos_gemm_t* m, const float* W, const float* b, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && W, "hos_gemm_set_weight: bad handle/weights");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KB = m->kb0 + m->kb1;
+  for (int j = 0; j < m->n / kGemmNB; ++j) {
+    const int64_t tot = (int64_t)KB * kGemmNB * kKB;
+    // rows [256 j, 256 j + 256) of W [n, k0 + k1]; the first input's columns become chunks 0 .. kb0 - 1
+    pack_weight_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(W + (size_t)j * kGemmNB * (m->k0 + m->k1), kGemmNB, m->k0, m->k1,
+                                                                     m->x_first, m->kb0, m->kb1, 0,
+                                                                     m->d_w + (size_t)j * KB * kGemmNB * 128);
+    HOS_LAUNCH_CHECK();
+  }
+  if (b) HOS_CUDA(cudaMemcpyAsync(m->d_params, b, (size_t)m->n * 4, cudaMemcpyDeviceToDevice, st));
+  else HOS_CUDA(cudaMemsetAsync(m->d_params, 0, (size_t)m->n * 4, st));
+  return HOS_OK;
+}
+
+int hos_gemm_set_head(hos_gemm_t* m, int hn, const float* W, const float* b, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && W && hn >= 1 && hn <= 4, "hos_gemm_set_head: 1 <= hn <= 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  m->hn = hn;
+  HOS_CUDA(cudaMemcpyAsync(m->d_params + m->n, W, (size_t)hn * m->n * 4, cudaMemcpyDeviceToDevice, st));
+  if (b) HOS_CUDA(cudaMemcpyAsync(m->d_params + (size_t)m->n * (1 + hn), b, (size_t)hn * 4, cudaMemcpyDeviceToDevice, st));
+  else HOS_CUDA(cudaMemsetAsync(m->d_params + (size_t)m->n * (1 + hn), 0, 16, st));
+  return HOS_OK;
+}
+
+int hos_gemm_forward(hos_gemm_t* m, const void* a0_tiled, const void* a1_tiled, int64_t rows, int relu, void* y_tiled,
+                     float* head_out, int head_post, float head_shift, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && a0_tiled && rows >= 0 && (m->kb1 == 0 || a1_tiled), "hos_gemm_forward: bad handle/inputs");
+  HOS_REQUIRE(y_tiled || (head_out && m->hn > 0), "hos_gemm_forward: nothing to write");
+  HOS_REQUIRE(!head_out || m->hn > 0, "hos_gemm_forward: call hos_gemm_set_head first");
+  if (rows == 0) return HOS_OK;
+  GemmArgs a;
+  a.a0 = (const unsigned char*)a0_tiled;
+  a.a1 = (const unsigned char*)a1_tiled;
+  a.w = m->d_w;
+  a.params = m->d_params;
+  a.y = (unsigned char*)y_tiled;
+  a.head_out = head_out;
+  a.rows = rows;
+  a.ntiles = (int)((rows + kTileM - 1) / kTileM);
+  a.kb0 = m->kb0;
+  a.kb1 = m->kb1;
+  a.n = m->n;
+  a.relu = relu;
+  a.hn = head_out ? m->hn : 0;
+  a.head_post = head_post;
+  a.head_shift = head_shift;
+  const int n_groups = (a.ntiles + 1) / 2;
+  const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
+  // parameter block in shared memory: bias + the heads actually used
+  gemm_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(a);
   HOS_LAUNCH_CHECK();
   return HOS_OK;
 }

@@ -182,8 +182,8 @@ class MipNeRF360MLP(nn.Module):
             return self._cache["f16"]
         if self.netwidth > 256 or self.netwidth % 64 != 0:
             raise NotImplementedError(
-                f"hosnerf_b200: the tcgen05 MLP kernel supports widths <= 256 (got {self.netwidth}); "
-                "use precision='fp32' for this network")
+                f"hosnerf_b200: the fused tcgen05 MLP kernel supports widths <= 256 (got {self.netwidth}); "
+                "wide networks run layer by layer (_wide)")
         f = self._folded(state_idx)
         F, nw = self.ipe_size, self.netwidth
         layers, heads = [], []
@@ -228,6 +228,43 @@ class MipNeRF360MLP(nn.Module):
         self._cache["f16_key"], self._cache["f16"] = key, mlp
         return mlp
 
+    def _wide(self, state_idx: int):
+        """Wide networks (netwidth a multiple of 256 above 256 - the reference default NeRFMLP is 1024 wide,
+        S1 model.py:267-275): every pts_linear layer is one tensor-core GEMM over tiled fp16 activations
+        (``ops.TiledLinear``), the density head rides in the last one's epilogue, and the narrow bottleneck + view
+        layers run on the fused kernel."""
+        key = ("wide", state_idx, self._versions())
+        if self._cache.get("wide_key") == key:
+            return self._cache["wide"]
+        if self.netwidth % 256 != 0:
+            raise NotImplementedError(f"hosnerf_b200: fp16 mode needs netwidth <= 256 or a multiple of 256 (got {self.netwidth}); "
+                                      "use precision='fp32' for this network")
+        f = self._folded(state_idx)
+        F, nw = self.ipe_size, self.netwidth
+        lins = []
+        for i in range(self.netdepth):
+            W, b, skip = f["layers"][i]
+            lin = ops.TiledLinear(nw, F if i == 0 else nw, F if skip else 0)     # _folded orders skip weights [h | x]
+            lin.set_weight(W, b)
+            lins.append((lin, skip))
+        lins[-1][0].set_head(*f["density"])
+        tail = None
+        if not self.disable_rgb:
+            bw, cw = self.bottleneck_width, self.netwidth_condition
+            if bw % 64 != 0 or bw > 256 or cw % 64 != 0 or cw > 256:
+                raise NotImplementedError("hosnerf_b200: bottleneck / condition widths must be multiples of 64 up to 256")
+            layers = [dict(out_dim=bw, in_h=0, in_x=nw, x_first=0, relu=0, rowbias=0, head=-1),
+                      dict(out_dim=cw, in_h=bw, in_x=0, x_first=0, relu=1, rowbias=1, head=0)]
+            heads = [dict(out_dim=self.num_rgb_channels, post=2, shift=float(self.rgb_padding), out_slot=0)]
+            tail = ops.FusedMLP(nw, layers, heads)
+            tail.set_layer(0, *f["bottleneck"])
+            tail.set_layer(1, f["views"][2], None)
+            tail.set_head(0, *f["rgb"])
+            tail.view_bias = f["views"][1]
+        out = {"lins": lins, "tail": tail}
+        self._cache["wide_key"], self._cache["wide"] = key, out
+        return out
+
     # ------------------------------------------------------------------ evaluation
     def eval_samples(self, tdist, rays_o, rays_d, radii, viewdirs, time, precision: str):
         """tdist [N,S+1] -> density [N,S], rgb [N,S,3] (zeros for proposal MLPs).  Covers
@@ -236,6 +273,27 @@ class MipNeRF360MLP(nn.Module):
         st = self._state_index(time)
         f = self._folded(st)
         basis = self.pos_basis_t
+        if precision == "fp16" and self.netwidth > 256:
+            wide = self._wide(st)
+            rows = n * s
+            feat = ops.ipe_features(tdist, rays_o, rays_d, radii, basis, self.min_deg_point, self.max_deg_point, "tiled")
+            x = feat
+            dens = None
+            for i, (lin, skip) in enumerate(wide["lins"]):
+                last = i == len(wide["lins"]) - 1
+                x, head = lin.forward(x, rows, x2_tiled=feat if skip else None, relu=True,
+                                      want_y=not (last and self.disable_rgb),
+                                      head_post=1 if last else None, head_shift=float(self.density_bias))
+                if last:
+                    dens = head
+            density = dens.view(n, s)
+            if self.disable_rgb:
+                return density, torch.zeros(n, s, 3, device=tdist.device)
+            tail = wide["tail"]
+            de = ops.pos_enc(viewdirs, 0, self.deg_view, True)
+            rowbias = ops.linear_f32(de, f["views"][3], tail.view_bias)            # per-ray view term + bias
+            rgb = tail.forward(x, rows, rowbias=rowbias, rowbias_div=s)[0]
+            return density, rgb.view(n, s, 3)
         if precision == "fp16":
             mlp = self._fused(st)
             rowbias = None

@@ -268,6 +268,55 @@ class FusedMLP:
             pass
 
 
+class TiledLinear:
+    """One wide nn.Linear (n_out a multiple of 256) on the tensor cores: tiled fp16 in, tiled fp16 out
+    (``hos_gemm_*``).  ``x2`` is the skip-connection input whose columns follow (or, ``x_first``, precede) x1's in W."""
+
+    def __init__(self, n_out, k1, k2=0, x_first=False):
+        lib = _lib.load()
+        self.n_out, self.k1, self.k2 = n_out, k1, k2
+        self._h = lib.hos_gemm_create(n_out, k1, k2, int(x_first))
+        if not self._h:
+            raise RuntimeError("hos_gemm_create failed: " + lib.hos_last_error().decode())
+        self.head_dim = 0
+
+    def set_weight(self, w, b):
+        _chk(w, "w"), _chk(b, "b")
+        assert tuple(w.shape) == (self.n_out, self.k1 + self.k2), (w.shape, self.n_out, self.k1, self.k2)
+        _lib.call("hos_gemm_set_weight", self._h, _p(w), _p(b), _stream())
+
+    def set_head(self, w, b):
+        _chk(w, "w"), _chk(b, "b")
+        assert w.shape[1] == self.n_out and w.shape[0] <= 4
+        self.head_dim = w.shape[0]
+        _lib.call("hos_gemm_set_head", self._h, self.head_dim, _p(w), _p(b), _stream())
+
+    def forward(self, x1_tiled, rows, x2_tiled=None, relu=True, want_y=True, head_post=None, head_shift=0.0):
+        _chk(x1_tiled, "x1_tiled", torch.uint8), _chk(x2_tiled, "x2_tiled", torch.uint8)
+        assert x1_tiled.numel() >= tiled_bytes(rows, self.k1)
+        assert (self.k2 == 0) == (x2_tiled is None)
+        dev = x1_tiled.device
+        y = torch.empty(tiled_bytes(rows, self.n_out), device=dev, dtype=torch.uint8) if want_y else None
+        head = torch.empty(rows, self.head_dim, device=dev, dtype=_F32) if head_post is not None else None
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.call_unless_empty(rows, "hos_gemm_forward", self._h, _p(x1_tiled), _p(x2_tiled), rows, int(relu), _p(y), _p(head),
+                               0 if head_post is None else int(head_post), float(head_shift), _stream())
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.append((("gemm", self.n_out, self.k1 + self.k2), rows, e0, e1))
+        return y, head
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().hos_gemm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 def set_mlp_variant(variant: int):
     """0 = automatic, 1 = single-CTA tcgen05 kernel, 2 = cluster-pair (cta_group::2, ping-pong) kernel."""
     _lib.call("hos_mlp_set_variant", int(variant))

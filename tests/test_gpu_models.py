@@ -317,6 +317,57 @@ def test_fused_mlp_rowbias_heads_and_ragged_tiles(rows, div, mlp_variant):
     assert max_abs(rgb.cpu(), r_ref) < 5e-3, max_abs(rgb.cpu(), r_ref)
 
 
+def _untile_f16(buf, rows, k):
+    """Decode the tiled fp16 layout (include/hosnerf_b200.h) on the host: -> float32 [rows, k]."""
+    kb = (k + 63) // 64
+    ntiles = (rows + 127) // 128
+    raw = buf.cpu().view(torch.float16).view(ntiles, kb, 128 * 64)
+    r = torch.arange(128).view(128, 1)
+    c = torch.arange(64).view(1, 64)
+    idx = (r * 128 + ((((c >> 3) ^ (r & 7))) << 4) + ((c & 7) << 1)) // 2          # element index inside a 16 KB block
+    out = raw[:, :, idx.reshape(-1)].view(ntiles, kb, 128, 64).permute(0, 2, 1, 3).reshape(ntiles * 128, kb * 64)
+    return out[:rows, :k].float()
+
+
+@pytest.mark.parametrize("rows,n_out,k1,k2", [(128 * 3 + 50, 256, 504, 0), (2000, 1024, 1024, 504), (128 * 151, 512, 512, 0),
+                                               (77, 1024, 1024, 0)])
+def test_wide_layer_gemm_vs_emulation(rows, n_out, k1, k2):
+    """hos_gemm_*: one wide nn.Linear on the tensor cores (tiled fp16 in / out, optional skip input and fp32 head)."""
+    gen = torch.Generator().manual_seed(rows + n_out)
+    x1 = torch.randn(rows, k1, generator=gen)
+    x2 = torch.randn(rows, k2, generator=gen) if k2 else None
+    W = (torch.rand(n_out, k1 + k2, generator=gen) * 2 - 1) * (6.0 / (k1 + k2)) ** 0.5
+    b = (torch.rand(n_out, generator=gen) * 2 - 1) * 0.1
+    hw = torch.randn(1, n_out, generator=gen) / n_out ** 0.5
+    hb = torch.randn(1, generator=gen) * 0.1
+    lin = ops.TiledLinear(n_out, k1, k2)
+    lin.set_weight(cu(W), cu(b))
+    lin.set_head(cu(hw), cu(hb))
+    y, head = lin.forward(ops.pack_rows_f16(cu(x1)), rows, x2_tiled=ops.pack_rows_f16(cu(x2)) if k2 else None,
+                          relu=True, head_post=1, head_shift=-1.0)
+    torch.cuda.synchronize()
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = torch.relu(xin.half().double() @ W.half().double().T + b.double()).float()
+    got = _untile_f16(y, rows, n_out)
+    assert rel_err(got, ref.half().float()) < 2e-3, rel_err(got, ref.half().float())          # an fp16 ulp of the output
+    href = torch.nn.functional.softplus(ref.double() @ hw.double().T + hb.double() - 1.0).float()
+    assert rel_err(head.cpu(), href) < 1e-3, rel_err(head.cpu(), href)
+
+
+def test_mip360_default_width_fp16_golden(golden):
+    """The reference's default configuration (NeRFMLP 1024 wide, S1 model.py:267-275) in fp16 mode: proposal MLPs on
+    the fused kernel, the wide NeRF MLP layer by layer on the GEMM kernel - against the reference's fp32 result."""
+    g = golden("s1_forward_default")
+    net = _bkg(precision="fp16")
+    with torch.no_grad():
+        rend, hist = net(_batch(g), 1.0, False, False, 0.1, 1e6)
+    torch.cuda.synchronize()
+    last = len(hist) - 1
+    assert max_abs(rend[-1]["rgb"].cpu(), g[f"R{last}_rgb"]) < 1e-2
+    assert rel_err(hist[0]["density"].cpu(), g["L0_density"]) < 3e-2
+    assert max_abs(hist[-1]["rgb"].cpu(), g[f"L{last}_rgb"]) < 2e-2
+
+
 def test_pair_kernel_matches_single_cta_kernel_fused_ipe():
     """The cluster-pair kernel (cta_group::2, two row tiles per SM in ping-pong) and the single-CTA kernel run
     the same fp16 program: C2 shape with the fused IPE prologue, ray count not a multiple of a 4-tile group."""
