@@ -405,6 +405,28 @@ def _hb(n, **kw):
     return {k: cu(v) for k, v in synth.make_human_batch(n, **kw).items()}
 
 
+def test_human_frame_cache_invalidation():
+    """The per-frame prologue (pose refinement, kinematic chain, motion-weight volume, folded condition bias) is cached
+    across the ray chunks of a frame; an in-place edit of a pose input or a new tensor must invalidate it."""
+    net = _human(precision="fp16")
+    hb = _hb(64)
+    with torch.no_grad():
+        a = net(**hb)["human_density"].clone()
+        b = net(**hb)["human_density"].clone()              # second chunk of the same frame: cached prologue
+        assert torch.equal(a, b)
+        hb["dst_Ts"].add_(0.05)                               # in-place edit: version counter changes
+        hb["dst_posevec"].mul_(1.5)
+        c = net(**hb)["human_density"].clone()
+        fresh = _human(precision="fp16")
+        d = fresh(**hb)["human_density"].clone()
+    assert not torch.allclose(a, c)
+    assert torch.equal(c, d)
+    hb2 = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in hb.items()}      # new tensors, same values
+    with torch.no_grad():
+        e = net(**hb2)["human_density"]
+    assert torch.equal(c, e)
+
+
 def test_human_s3_fp32_golden(golden):
     g = golden("human_s3_eval")
     net = _human()
