@@ -1,0 +1,71 @@
+"""Drop-in replacements for the reference's per-frame ray generators (S3 core/utils/camera_util.py:154-265):
+same names, argument order and return tuples, but the rays are produced by CUDA kernels and returned as torch
+CUDA tensors instead of numpy arrays (2 M rays per 1080p frame, numpy on the host in the reference)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_D = C.c_double
+
+
+def _host(a, n):
+    v = np.asarray(a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a, dtype=np.float64).reshape(-1)
+    assert v.size == n, (v.size, n)
+    return (_D * n)(*v.tolist())
+
+
+def _rays(H, W, K, R, T, bkg, dtype, device):
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError("dtype must be torch.float32 or torch.float64")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("hosnerf_b200.camera: rays are generated on a CUDA device (this package has no CPU path)")
+    kinv = np.linalg.inv(np.asarray(K.detach().cpu().numpy() if isinstance(K, torch.Tensor) else K, dtype=np.float64))
+    o = torch.empty(H, W, 3, device=dev, dtype=dtype)
+    d = torch.empty(H, W, 3, device=dev, dtype=dtype)
+    v = torch.empty(H, W, 3, device=dev, dtype=dtype) if bkg else None
+    r = torch.empty(H, W, 1, device=dev, dtype=dtype) if bkg else None
+    with torch.cuda.device(dev):
+        _lib.call("hos_rays_from_krt", int(H), int(W), _host(kinv, 9), _host(R, 9), _host(T, 3), int(bkg),
+                  int(dtype == torch.float64), o.data_ptr(), d.data_ptr(), None if v is None else v.data_ptr(),
+                  None if r is None else r.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return (o, d, v, r) if bkg else (o, d)
+
+
+def get_rays_from_KRT(H, W, K, R, T, dtype=torch.float32, device="cuda"):
+    """camera_util.py:154-181 -> (rays_o [H, W, 3], rays_d [H, W, 3])."""
+    return _rays(H, W, K, R, T, False, dtype, device)
+
+
+def get_rays_from_KRT_bkg(H, W, K, R, T, dtype=torch.float32, device="cuda"):
+    """camera_util.py:183-216 -> (rays_o, rays_d, viewdirs [H, W, 3], radii [H, W, 1])."""
+    return _rays(H, W, K, R, T, True, dtype, device)
+
+
+def rays_intersect_3d_bbox(bounds, ray_o, ray_d):
+    """camera_util.py:219-265 -> (near [N_valid], far [N_valid], mask_at_box [N]); like the reference, components of
+    ``ray_d`` below 1e-5 in magnitude are overwritten with 1e-5 in place."""
+    if isinstance(bounds, dict):
+        bounds = np.stack([np.asarray(bounds["min_xyz"]), np.asarray(bounds["max_xyz"])], axis=0)
+    b = np.asarray(bounds.detach().cpu().numpy() if isinstance(bounds, torch.Tensor) else bounds, dtype=np.float64)
+    assert b.shape == (2, 3)
+    for t, nm in ((ray_o, "ray_o"), (ray_d, "ray_d")):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or not t.is_contiguous() or t.dtype not in (torch.float32, torch.float64):
+            raise RuntimeError(f"hosnerf_b200.camera: `{nm}` must be a contiguous float32/float64 CUDA tensor")
+    assert ray_o.dtype == ray_d.dtype and ray_o.shape == ray_d.shape and ray_o.shape[-1] == 3
+    n = ray_o.numel() // 3
+    dev = ray_o.device
+    near = torch.empty(n, device=dev, dtype=torch.float32)
+    far = torch.empty(n, device=dev, dtype=torch.float32)
+    mask = torch.empty(n, device=dev, dtype=torch.uint8)
+    with torch.cuda.device(dev):
+        _lib.call_unless_empty(n, "hos_rays_intersect_bbox", _host(b[0], 3), _host(b[1], 3), ray_o.data_ptr(), ray_d.data_ptr(), n,
+                               int(ray_o.dtype == torch.float64), near.data_ptr(), far.data_ptr(), mask.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+    m = mask.bool()
+    return near[m], far[m], m
