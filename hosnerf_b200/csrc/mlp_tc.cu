@@ -1246,7 +1246,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
 // ----------------------------------------------------------------------------- packing
 // W fp32 [N, in_h + in_x] (nn.Linear layout, columns ordered [x|h] if x_first else [h|x])
 // -> fp16 chunks in kernel K order: kb_h chunks of h columns, then kb_x chunks of x columns.
-// ipe_perm != 0: the x columns are re-ordered from the reference's IPE layout
+// ipe_perm bit 0 (x columns) / bit 1 (h columns): that input holds generated IPE features, re-ordered from the reference layout
 // f = half*252 + l*21 + j  to the kernel's generation order
 // col = 2 * (pbase_g + l * gs_g + jj) + half,  j = jbase_g + jj  (groups of 8, 8, 5 directions; see ipe_generate_pass).
 __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h, int in_x, int x_first, int kb_h,
@@ -1259,18 +1259,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h,
   int kb = (int)(i / ((int64_t)kKB * N));
   float v = 0.f;
   const int ktot = in_h + in_x;
+  auto ipe_col = [](int c) {          // kernel generation order -> reference feature index
+    const int half = c & 1, pr = c >> 1;
+    const int gs = pr < 192 ? 8 : 5, pb = pr < 96 ? 0 : (pr < 192 ? 96 : 192), jb = pr < 96 ? 0 : (pr < 192 ? 8 : 16);
+    const int l = (pr - pb) / gs, jj = (pr - pb) % gs;
+    return half * (kIpeDeg * kIpeB) + l * kIpeB + jb + jj;
+  };
   if (kb < kb_h) {
     int c = kb * kKB + kk;
-    if (c < in_h) v = W[(int64_t)n * ktot + (x_first ? in_x + c : c)];
+    if (c < in_h) {
+      if (ipe_perm & 2) c = ipe_col(c);
+      v = W[(int64_t)n * ktot + (x_first ? in_x + c : c)];
+    }
   } else {
     int c = (kb - kb_h) * kKB + kk;
     if (c < in_x) {
-      if (ipe_perm) {
-        const int half = c & 1, pr = c >> 1;
-        const int gs = pr < 192 ? 8 : 5, pb = pr < 96 ? 0 : (pr < 192 ? 96 : 192), jb = pr < 96 ? 0 : (pr < 192 ? 8 : 16);
-        const int l = (pr - pb) / gs, jj = (pr - pb) % gs;
-        c = half * (kIpeDeg * kIpeB) + l * kIpeB + jb + jj;
-      }
+      if (ipe_perm & 1) c = ipe_col(c);
       v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
     }
   }
@@ -1565,6 +1569,31 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
   }
 }
 
+
+// Generated IPE features to HBM in the tiled fp16 layout (kernel column order, see ipe_generate_pass): the wide-layer
+// path reads them as a GEMM operand.  One thread per sample, the same packed recurrences as the fused prologue, one
+// 16-byte store per four (sin, cos) pairs; ~20x faster than the accurate fp32 parity kernel (hos_ipe_features).
+__global__ void __launch_bounds__(kTileM)
+ipe_features_fast_kernel(const __grid_constant__ IpeArgs ipe, int64_t rows, unsigned char* __restrict__ out) {
+  const int r = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int64_t row = tile * kTileM + r;
+  IpeRowGeom G;
+  ipe_row_setup(ipe, row, row < rows, G);
+  unsigned char* base = out + (size_t)tile * 8 * kXChunkBytes + (size_t)r * 128;
+  const uint32_t r7 = (uint32_t)(r & 7);
+  uint32_t pk[4];
+  auto emit = [&](int p, float sv, float cv) {             // p is a compile-time constant after unrolling
+    pk[p & 3] = cvt_f16x2(__float_as_uint(sv), __float_as_uint(cv));
+    if ((p & 3) == 3)
+      *reinterpret_cast<uint4*>(base + (size_t)(p >> 5) * kXChunkBytes + ((((uint32_t)(p & 31) >> 2) ^ r7) << 4)) =
+          make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  };
+  ipe_group<8, 0, 0>(ipe, G, emit);
+  ipe_group<8, 8, 96>(ipe, G, emit);
+  ipe_group<5, 16, 192>(ipe, G, emit);
+  *reinterpret_cast<uint4*>(base + (size_t)7 * kXChunkBytes + ((7u ^ r7) << 4)) = make_uint4(0u, 0u, 0u, 0u);   // columns 504..511
+}
 }  // namespace hos
 
 using namespace hos;
@@ -1836,6 +1865,25 @@ int hos_mlp_forward_ipe(hos_mlp_t* m, const float* tdist, const float* rays_o, c
   return mlp_launch(m, nullptr, &ipe, (int64_t)N * S, rowbias, rowbias_div, nullptr, out0, out1, stream);
 }
 
+int hos_ipe_features_fast(const float* tdist, const float* rays_o, const float* rays_d, const float* radii,
+                          const float* basis_host, int N, int S, void* feat_tiled, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(tdist && rays_o && rays_d && radii && basis_host && feat_tiled && N >= 0 && S >= 1, "hos_ipe_features_fast: bad arguments");
+  const int64_t rows = (int64_t)N * S;
+  if (rows == 0) return HOS_OK;
+  IpeArgs ipe;
+  ipe.tdist = tdist;
+  ipe.rays_o = rays_o;
+  ipe.rays_d = rays_d;
+  ipe.radii = radii;
+  ipe.S = S;
+  for (int i = 0; i < 3 * kIpeB; ++i) ipe.basis[i] = basis_host[i];
+  const int64_t ntiles = (rows + kTileM - 1) / kTileM;
+  ipe_features_fast_kernel<<<(unsigned)ntiles, kTileM, 0, (cudaStream_t)stream>>>(ipe, rows, (unsigned char*)feat_tiled);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}
+
 int hos_pack_rows_f16(const float* X, int64_t rows, int ld, int K, void* dst_tiled, void* stream) {
   HOS_ARCH_GUARD();
   HOS_REQUIRE(X && dst_tiled && rows >= 0 && K >= 1 && ld >= K, "hos_pack_rows_f16: bad arguments");
@@ -1851,21 +1899,27 @@ int hos_pack_rows_f16(const float* X, int64_t rows, int ld, int K, void* dst_til
 
 // ----------------------------------------------------------------------------- wide-layer GEMM handle
 struct hos_gemm {
-  int n = 0, k0 = 0, k1 = 0, kb0 = 0, kb1 = 0, x_first = 0, hn = 0;
+  int n = 0, k0 = 0, k1 = 0, kb0 = 0, kb1 = 0, x_first = 0, hn = 0, ipe_mask = 0;
   unsigned char* d_w = nullptr;     // packed fp16 [n / 256][kb0 + kb1][256 x 128 B]
   float* d_params = nullptr;        // [n] bias | [4][n] head weights | [4] head bias
   size_t smem_bytes = 0;
   int max_clusters = 0;
 };
 
-hos_gemm_t* hos_gemm_create(int n_out, int k0, int k1, int x_first) {
+hos_gemm_t* hos_gemm_create(int n_out, int k0, int k1, int x_first, int ipe_inputs) {
   if (hos::check_arch() != HOS_OK) return nullptr;
+  if (((ipe_inputs & 1) && k0 != 2 * kIpeDeg * kIpeB) || ((ipe_inputs & 2) && k1 != 2 * kIpeDeg * kIpeB)) {
+    hos::set_error("hos_gemm_create: an IPE input must have %d features", 2 * kIpeDeg * kIpeB);
+    return nullptr;
+  }
   if (n_out < kGemmNB || (n_out % kGemmNB) != 0 || n_out > 4096 || k0 < 1 || k1 < 0) {
     hos::set_error("hos_gemm_create: n_out must be a multiple of %d (got %d), k0 >= 1, k1 >= 0", kGemmNB, n_out);
     return nullptr;
   }
   hos_gemm* m = new hos_gemm();
   m->n = n_out; m->k0 = k0; m->k1 = k1; m->x_first = x_first;
+  // bit 0: A0 / bit 1: A1 hold generated IPE features (hos_ipe_features_fast) -> pack_weight_kernel's h / x flags
+  m->ipe_mask = ((ipe_inputs & 1) ? 2 : 0) | ((ipe_inputs & 2) ? 1 : 0);
   m->kb0 = (k0 + kKB - 1) / kKB;
   m->kb1 = (k1 + kKB - 1) / kKB;
   const size_t wbytes = (size_t)(n_out / kGemmNB) * (m->kb0 + m->kb1) * kGemmNB * 128;
@@ -1913,7 +1967,7 @@ int hos_gemm_set_weight(hos_gemm_t* m, const float* W, const float* b, void* str
     const int64_t tot = (int64_t)KB * kGemmNB * kKB;
     // rows [256 j, 256 j + 256) of W [n, k0 + k1]; the first input's columns become chunks 0 .. kb0 - 1
     pack_weight_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(W + (size_t)j * kGemmNB * (m->k0 + m->k1), kGemmNB, m->k0, m->k1,
-                                                                     m->x_first, m->kb0, m->kb1, 0,
+                                                                     m->x_first, m->kb0, m->kb1, m->ipe_mask,
                                                                      m->d_w + (size_t)j * KB * kGemmNB * 128);
     HOS_LAUNCH_CHECK();
   }

@@ -241,10 +241,13 @@ class MipNeRF360MLP(nn.Module):
                                       "use precision='fp32' for this network")
         f = self._folded(state_idx)
         F, nw = self.ipe_size, self.netwidth
+        fast = (FUSE_IPE and self.pos_basis_t.shape[1] == 21 and self.max_deg_point - self.min_deg_point == 12
+                and self.min_deg_point == 0)      # features from the fast generator (kernel column order)
         lins = []
         for i in range(self.netdepth):
             W, b, skip = f["layers"][i]
-            lin = ops.TiledLinear(nw, F if i == 0 else nw, F if skip else 0)     # _folded orders skip weights [h | x]
+            lin = ops.TiledLinear(nw, F if i == 0 else nw, F if skip else 0,       # _folded orders skip weights [h | x]
+                                  ipe_inputs=(1 if i == 0 else (2 if skip else 0)) if fast else 0)
             lin.set_weight(W, b)
             lins.append((lin, skip))
         lins[-1][0].set_head(*f["density"])
@@ -261,7 +264,10 @@ class MipNeRF360MLP(nn.Module):
             tail.set_layer(1, f["views"][2], None)
             tail.set_head(0, *f["rgb"])
             tail.view_bias = f["views"][1]
-        out = {"lins": lins, "tail": tail}
+        out = {"lins": lins, "tail": tail, "fast": fast}
+        if fast:
+            bh = self.pos_basis_t.detach().float().cpu().contiguous().reshape(-1).tolist()
+            out["basis_host"] = (ctypes.c_float * len(bh))(*bh)
         self._cache["wide_key"], self._cache["wide"] = key, out
         return out
 
@@ -276,7 +282,10 @@ class MipNeRF360MLP(nn.Module):
         if precision == "fp16" and self.netwidth > 256:
             wide = self._wide(st)
             rows = n * s
-            feat = ops.ipe_features(tdist, rays_o, rays_d, radii, basis, self.min_deg_point, self.max_deg_point, "tiled")
+            if wide["fast"]:
+                feat = ops.ipe_features_fast(tdist, rays_o, rays_d, radii, wide["basis_host"])
+            else:
+                feat = ops.ipe_features(tdist, rays_o, rays_d, radii, basis, self.min_deg_point, self.max_deg_point, "tiled")
             x = feat
             dens = None
             for i, (lin, skip) in enumerate(wide["lins"]):

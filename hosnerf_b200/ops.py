@@ -116,6 +116,17 @@ def ipe_features(tdist, rays_o, rays_d, radii, basis, min_deg=0, max_deg=12, out
     return (feat, means, lvar) if want_aux else feat
 
 
+def ipe_features_fast(tdist, rays_o, rays_d, radii, basis_host):
+    """504 IPE features per sample, tiled fp16, generation column order (for TiledLinear(ipe_inputs=...))."""
+    for t, nm in ((tdist, "tdist"), (rays_o, "rays_o"), (rays_d, "rays_d"), (radii, "radii")):
+        _chk(t, nm)
+    n, s = tdist.shape[0], tdist.shape[1] - 1
+    feat = torch.empty(tiled_bytes(n * s, 504), device=tdist.device, dtype=torch.uint8)
+    _lib.call_unless_empty(n * s, "hos_ipe_features_fast", _p(tdist), _p(rays_o), _p(rays_d), _p(radii), basis_host, n, s,
+                           _p(feat), _stream())
+    return feat
+
+
 def pos_enc(x, min_deg, max_deg, append_identity=True):
     _chk(x, "x")
     n = x.shape[0]
@@ -272,10 +283,10 @@ class TiledLinear:
     """One wide nn.Linear (n_out a multiple of 256) on the tensor cores: tiled fp16 in, tiled fp16 out
     (``hos_gemm_*``).  ``x2`` is the skip-connection input whose columns follow (or, ``x_first``, precede) x1's in W."""
 
-    def __init__(self, n_out, k1, k2=0, x_first=False):
+    def __init__(self, n_out, k1, k2=0, x_first=False, ipe_inputs=0):
         lib = _lib.load()
         self.n_out, self.k1, self.k2 = n_out, k1, k2
-        self._h = lib.hos_gemm_create(n_out, k1, k2, int(x_first))
+        self._h = lib.hos_gemm_create(n_out, k1, k2, int(x_first), int(ipe_inputs))
         if not self._h:
             raise RuntimeError("hos_gemm_create failed: " + lib.hos_last_error().decode())
         self.head_dim = 0
