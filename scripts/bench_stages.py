@@ -89,3 +89,28 @@ for prec in ("fp16", "fp32"):
     with torch.no_grad():
         ms = timeit(lambda: hn(**hb), reps=5)
     print(f"C3 human branch (Network.forward, {n_h} rays x 128 samples, {prec}): {ms:.3f} ms/step = {n_h * 128 / ms / 1e3:.1f} M ray-samples/s")
+
+# ---- C4-style stage-3 chunk, forward only: background (128 proposal + 64 NeRF samples, 256 wide) + human branch (128 samples)
+# on the same 8192 rays + depth-merge composite (render_hosnerf_chunk)
+from hosnerf_b200 import render_hosnerf_chunk
+n4 = 8192
+hb4 = synth.make_human_batch(n4)
+Mw = synth.random_rigid()
+ro, rd = hb4["rays"][0], hb4["rays"][1]
+ro_w = (Mw[:3, :3] @ ro.T).T + Mw[:3, 3]
+rd_w = (Mw[:3, :3] @ rd.T).T
+bb4 = {"rays_o": ro_w, "rays_d": rd_w, "viewdirs": rd_w / rd_w.norm(dim=-1, keepdim=True), "radii": torch.full((n4, 1), 1e-3),
+       "times": torch.tensor(0.0)}
+bb4 = {k: v.to(dev) for k, v in bb4.items()}
+hb4 = {k: (v.to(dev) if isinstance(v, torch.Tensor) else v) for k, v in hb4.items()}
+bkg4 = MipNeRF360("/nonexistent", num_levels=2, num_prop_samples=128, num_nerf_samples=64, nerf_netwidth=256, opaque_background=True,
+                  stage3=True, precision="fp16")
+synth.fill_params_(bkg4, 0)
+bkg4 = bkg4.to(dev)
+hn4 = Network(default_cfg(), stage2=False, precision="fp16")
+synth.fill_params_(hn4, 0)
+synth.boost_human_density_(hn4)
+hn4 = hn4.to(dev)
+ms = timeit(lambda: render_hosnerf_chunk(bkg4, hn4, bb4, hb4, Mw), reps=5)
+print(f"C4-style stage-3 chunk, forward only ({n4} rays x (128 prop + 64 NeRF + 128 human) samples, fp16): {ms:.3f} ms/chunk = "
+      f"{n4 / ms / 1e3:.2f} M rays/s")
