@@ -17,7 +17,7 @@ from hosnerf_b200 import MipNeRF360, Network, camera, default_cfg, ops, synth
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 1080
 W = int(sys.argv[2]) if len(sys.argv) > 2 else 1920
-CHUNK = int(sys.argv[3]) if len(sys.argv) > 3 else 32768
+CHUNK = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
 dev = "cuda:0"
 
 bkg = MipNeRF360("/nonexistent", num_prop_samples=64, num_nerf_samples=64, opaque_background=True, stage3=True, precision="fp16")
@@ -80,8 +80,10 @@ def render_frame():
 
 
 with torch.no_grad():
-    small = (H, W)
-    render_frame() if H * W <= 300000 else None           # warm-up on small frames only; big frames warm up in the first chunks
+    Hs, Ws = H, W
+    H, W = max(2, CHUNK // W), W                          # warm-up: one chunk-sized strip (weight packing, lazy inits)
+    render_frame()
+    H, W = Hs, Ws
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     rgb, n_hit = render_frame()
