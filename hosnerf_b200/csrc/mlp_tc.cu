@@ -863,7 +863,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           const LayerDev L = prog.layers[l];
           const uint32_t half_bytes = (uint32_t)L.n * 64u;
           const int nkb = L.kb_h + L.kb_x;
-          for (int kb = 0; kb <= nkb; ++kb, ++wi) {            // chunk nkb: the bias chunk
+          for (int kk = 0; kk <= nkb; ++kk, ++wi) {            // consumption order: the bias chunk (stored last) first
+            const int kb = kk == 0 ? nkb : kk - 1;
             const bool from_x = kb >= L.kb_h && kb < nkb;
             const uint32_t xs = xi % kPairStagesX, xuse = xi / kPairStagesX;
             if (from_x) ++xi;
@@ -913,6 +914,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     if (rank == 0) {
       uint32_t u = 0, hpar = 0;                      // unit counter; parity of the hready phase the next H-reading unit waits for
       uint32_t ws = 0, wpar = 0, xs = 0, xpar = 0;   // weight / feature ring cursors + phase parities
+      bool prev_had_h = true;
       const uint64_t desc_hi = umma_desc(0);
       const uint32_t wfull0 = smem_u32(&bar_wfull[0]), wempty0 = smem_u32(&bar_wempty[0]);
       const uint32_t xfull0 = smem_u32(&bar_xfull[0]), xempty0 = smem_u32(&bar_xempty[0]);
@@ -929,22 +931,39 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           const bool tl = args.timeline && blockIdx.x == 0 && u < 64 && lane == 0;
           long long wait_sum = 0;
           if (tl) args.timeline[u * 12 + 0] = clock64();
-          // Accumulator buffer (u & 1) was last read by the epilogue of unit u - 2, which finished before it
-          // signalled the last H chunk that unit u - 1 waited for; H chunk kb is overwritten by the epilogue of
-          // unit u only after all MMAs of unit u retired (tfull).
+          // H chunk kb is overwritten by the epilogue of unit u only after all MMAs of unit u retired (tfull).
+          {
+            // Bias first: ones (columns 0, 1 of the constant operand) x (hi, lo) -> one K = 16 MMA that INITIALISES the
+            // accumulator.  It needs only its weight stage, so it is issued (and runs) while the previous layer's
+            // epilogue is still producing this layer's first operand chunk.
+            // Accumulator buffer (u & 1) was last read by the epilogue of unit u - 2.  If unit u - 1 read activation
+            // chunks it waited for that epilogue's last chunk signal, so the buffer is free now; if unit u - 1 read only
+            // features (first layer of a tile) nothing has ordered us after epilogue(u - 2) yet: then wait for the first
+            // operand chunk of this unit as well (signalled by epilogue(u - 1), which runs after epilogue(u - 2)).
+            if (u < 2 || prev_had_h) mbar_wait2_spin(wfull0 + 8u * ws, wpar, wfull0 + 8u * ws, wpar);
+            else mbar_wait2_spin(wfull0 + 8u * ws, wpar, kb_h > 0 ? hready_a : xfull0 + 8u * xs, kb_h > 0 ? hpar : xpar);
+            prev_had_h = kb_h > 0;
+            tc_fence_after();
+            if (elect_one()) {
+              tc_mma_f16_pair(acc, desc_hi | (uint64_t)ones16, desc_hi | (uint64_t)(w16 + ws * wstage16), idesc, 0u);
+              tc_commit_pair_addr(wempty0 + 8u * ws);
+            }
+            if (++ws == S) { ws = 0; wpar ^= 1; }
+            __syncwarp();
+          }
           int kb = 0, gi3 = 0;
           while (kb < nkb) {
             const bool is_h = kb < kb_h;
             const int cnt = (is_h && kb > 0 && kb + 1 < kb_h) ? 2 : 1;
-            const bool with_bias = kb + cnt == nkb;
-            const int nst = cnt + (with_bias ? 1 : 0);           // ring stages consumed by this group (<= 3)
-            // ---- one parallel poll (four try_waits in flight together cost ~220 cycles, four separate phase checks
+            const bool last_group = kb + cnt == nkb;
+            const int nst = cnt;                                   // ring stages consumed by this group (<= 2)
+            // ---- one parallel poll (several try_waits in flight together cost ~220 cycles, separate phase checks
             // ~150 each): the weight stages + the newest operand chunk (earlier ones are implied)
-            uint32_t wb[3], wp[3];
+            uint32_t wb[2], wp[2];
             {
               uint32_t s_ = ws, p_ = wpar;
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
+              for (int i = 0; i < 2; ++i) {
                 wb[i] = wfull0 + 8u * s_; wp[i] = p_;
                 if (i + 1 < nst) { if (++s_ == S) { s_ = 0; p_ ^= 1; } }
               }
@@ -952,7 +971,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             const uint32_t ob = is_h ? hready_a + 8u * (uint32_t)(kb + cnt - 1) : xfull0 + 8u * xs;
             const uint32_t op = is_h ? hpar : xpar;
             const long long c0 = tl ? clock64() : 0;
-            mbar_wait4_spin(wb[0], wp[0], wb[1], wp[1], wb[2], wp[2], ob, op);
+            mbar_wait3_spin(wb[0], wp[0], wb[1], wp[1], ob, op);
             const bool tl3 = tl && (u == 11 || u == 12) && gi3 < 5;
             if (tl) {
               const long long c1 = clock64();
@@ -970,20 +989,13 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
               if (leader_lane) {
 #pragma unroll
                 for (int k = 0; k < kKB / 16; ++k)
-                  tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb + i) != 0 || k != 0 ? 1u : 0u);
+                  tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                 tc_commit_pair_addr(wempty0 + 8u * ws);
                 if (!is_h) tc_commit_pair_addr(xempty0 + 8u * xs);
+                if (last_group && i == cnt - 1) tc_commit_pair_addr(tfull0 + 8u * (u & 1));     // accumulator complete
               }
               if (++ws == S) { ws = 0; wpar ^= 1; }
               if (!is_h) { if (++xs == kPairStagesX) { xs = 0; xpar ^= 1; } }
-            }
-            if (with_bias) {   // ones (columns 0, 1 of the constant operand) x (hi, lo) -> one K = 16 MMA
-              if (leader_lane) {
-                tc_mma_f16_pair(acc, desc_hi | (uint64_t)ones16, desc_hi | (uint64_t)(w16 + ws * wstage16), idesc, 1u);
-                tc_commit_pair_addr(wempty0 + 8u * ws);
-                tc_commit_pair_addr(tfull0 + 8u * (u & 1));
-              }
-              if (++ws == S) { ws = 0; wpar ^= 1; }
             }
             __syncwarp();
             if (tl3) args.timeline[840 + (u - 11) * 16 + gi3 * 3 + 2] = clock64();
