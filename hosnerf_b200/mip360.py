@@ -143,10 +143,10 @@ class MipNeRF360MLP(nn.Module):
         if self.netdepth_condition != 1 or self.num_density_channels != 1:
             raise NotImplementedError("hosnerf_b200: netdepth_condition != 1 / density channels != 1 are not built")
 
-    def _folded(self, state_idx: int):
+    def _folded(self, state_idx: int, _ver=None):
         """fp32 weights with the (constant per call) state embedding folded into the bias of
         every layer that sees the encoded input: W[:, ipe:ipe+64] @ e  (S1 model.py:208-209)."""
-        key = ("f32", state_idx, self._versions())
+        key = ("f32", state_idx, _ver if _ver is not None else self._versions())
         if self._cache.get("f32_key") == key:
             return self._cache["f32"]
         self._check_supported()
@@ -175,16 +175,16 @@ class MipNeRF360MLP(nn.Module):
         self._cache["f32_key"], self._cache["f32"] = key, out
         return out
 
-    def _fused(self, state_idx: int):
+    def _fused(self, state_idx: int, _ver=None):
         """tcgen05 program + uploaded fp16 weights (rebuilt when any parameter changes)."""
-        key = ("f16", state_idx, self._versions())
+        key = ("f16", state_idx, _ver if _ver is not None else self._versions())
         if self._cache.get("f16_key") == key:
             return self._cache["f16"]
         if self.netwidth > 256 or self.netwidth % 64 != 0:
             raise NotImplementedError(
                 f"hosnerf_b200: the fused tcgen05 MLP kernel supports widths <= 256 (got {self.netwidth}); "
                 "wide networks run layer by layer (_wide)")
-        f = self._folded(state_idx)
+        f = self._folded(state_idx, _ver)
         F, nw = self.ipe_size, self.netwidth
         layers, heads = [], []
         for i in range(self.netdepth):
@@ -228,18 +228,18 @@ class MipNeRF360MLP(nn.Module):
         self._cache["f16_key"], self._cache["f16"] = key, mlp
         return mlp
 
-    def _wide(self, state_idx: int):
+    def _wide(self, state_idx: int, _ver=None):
         """Wide networks (netwidth a multiple of 256 above 256 - the reference default NeRFMLP is 1024 wide,
         S1 model.py:267-275): every pts_linear layer is one tensor-core GEMM over tiled fp16 activations
         (``ops.TiledLinear``), the density head rides in the last one's epilogue, and the narrow bottleneck + view
         layers run on the fused kernel."""
-        key = ("wide", state_idx, self._versions())
+        key = ("wide", state_idx, _ver if _ver is not None else self._versions())
         if self._cache.get("wide_key") == key:
             return self._cache["wide"]
         if self.netwidth % 256 != 0:
             raise NotImplementedError(f"hosnerf_b200: fp16 mode needs netwidth <= 256 or a multiple of 256 (got {self.netwidth}); "
                                       "use precision='fp32' for this network")
-        f = self._folded(state_idx)
+        f = self._folded(state_idx, _ver)
         F, nw = self.ipe_size, self.netwidth
         fast = (FUSE_IPE and self.pos_basis_t.shape[1] == 21 and self.max_deg_point - self.min_deg_point == 12
                 and self.min_deg_point == 0)      # features from the fast generator (kernel column order)
@@ -277,10 +277,11 @@ class MipNeRF360MLP(nn.Module):
         cast_rays + contract + IPE + MLP (S1 model.py:410-424 and 126-264)."""
         n, s = tdist.shape[0], tdist.shape[1] - 1
         st = self._state_index(time)
-        f = self._folded(st)
+        ver = self._versions()                  # one pass over the parameters per call (the caches below all key on it)
+        f = self._folded(st, ver)
         basis = self.pos_basis_t
         if precision == "fp16" and self.netwidth > 256:
-            wide = self._wide(st)
+            wide = self._wide(st, ver)
             rows = n * s
             if wide["fast"]:
                 feat = ops.ipe_features_fast(tdist, rays_o, rays_d, radii, wide["basis_host"])
@@ -304,7 +305,7 @@ class MipNeRF360MLP(nn.Module):
             rgb = tail.forward(x, rows, rowbias=rowbias, rowbias_div=s)[0]
             return density, rgb.view(n, s, 3)
         if precision == "fp16":
-            mlp = self._fused(st)
+            mlp = self._fused(st, ver)
             rowbias = None
             if not self.disable_rgb:
                 de = ops.pos_enc(viewdirs, 0, self.deg_view, True)
@@ -414,8 +415,13 @@ class MipNeRF360(nn.Module):
         else:
             lo = max(min(1 - train_frac / self.near_anneal_rate, 1), 0)
         hi = 1.0
-        sdist = torch.cat([torch.full((n, 1), lo, device=dev), torch.full((n, 1), hi, device=dev)], dim=-1)
-        weights = torch.ones(n, 1, device=dev)
+        # level-0 inputs (one interval [lo, hi] of weight 1 per ray) are constants of (n, lo, hi): built once, read-only
+        k0 = (n, float(lo), float(hi), str(dev))
+        if self._u_cache.get("lvl0_key") != k0:
+            self._u_cache["lvl0_key"] = k0
+            self._u_cache["lvl0"] = (torch.cat([torch.full((n, 1), lo, device=dev), torch.full((n, 1), hi, device=dev)], dim=-1),
+                                     torch.ones(n, 1, device=dev))
+        sdist, weights = self._u_cache["lvl0"]
         prod = 1
         history, renderings = [], []
         anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) \
