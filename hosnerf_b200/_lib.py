@@ -71,6 +71,9 @@ SIGNATURES = {
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "hos_composite_s3": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_hp, c_f, c_f, c_i, c_i, c_i, c_fl,
                                c_f, c_f, c_f, c_f]),
+    "hos_lossfun_distortion": (c_i, [c_f, c_f, c_i, c_i, c_f, c_f]),
+    "hos_lossfun_outer": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f]),
+    "hos_reduce_scaled": (c_i, [c_f, c_f, c_l, C.c_double, c_f, c_f]),
 }
 
 _lib = None

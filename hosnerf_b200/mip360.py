@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes
 import json
+import math
 import os
 from typing import Optional, Tuple
 
@@ -509,8 +510,39 @@ class LitMipNeRF360(_LitBase):
     def test_step(self, batch, batch_idx):
         return self.render_rays(batch, batch_idx)
 
+    def interlevel_loss(self, ray_history):
+        """S1 model.py:609-618: sum over proposal levels of mean(lossfun_outer(final level | level))."""
+        c, w = ray_history[-1]["sdist"].contiguous(), ray_history[-1]["weights"].contiguous()
+        total = None
+        for lvl in ray_history[:-1]:
+            _, rows = ops.lossfun_outer(c, w, lvl["sdist"].contiguous(), lvl["weights"].contiguous(), want_rows=True)
+            term = ops.reduce_scaled(rows, 1.0 / max(w.numel(), 1))
+            total = term if total is None else total + term
+        return total if total is not None else torch.zeros((), device=w.device)
+
+    def distortion_loss(self, ray_history):
+        """S1 model.py:620-625: mean over rays of lossfun_distortion(final level)."""
+        c, w = ray_history[-1]["sdist"].contiguous(), ray_history[-1]["weights"].contiguous()
+        return ops.reduce_scaled(ops.lossfun_distortion(c, w), 1.0 / max(w.shape[0], 1))
+
+    def loss_terms(self, batch, randomized: bool = True, rands=None):
+        """Forward value of the stage-1 training objective (S1 model.py:488-512) on one ray batch:
+        Charbonnier data term + interlevel + distortion, and the PSNR the reference logs.  No autograd graph
+        is built (backward kernels are not part of this round), so this evaluates the loss, it does not train."""
+        with torch.no_grad():
+            rendered, hist = self.model(batch, self._frac(), randomized, True, self.near, self.far, rands=rands)
+            rgb = rendered[-1]["rgb"].contiguous()
+            mse = ops.reduce_scaled(rgb, 1.0 / max(rgb.numel(), 1), y=batch["target"].to(rgb.dtype).contiguous())
+            data = torch.sqrt(mse + self.charb_padding ** 2) * self.data_loss_mult
+            inter = self.interlevel_loss(hist)
+            dist = self.distortion_loss(hist)
+            loss = data + inter * self.interlevel_loss_mult + dist * self.distortion_loss_mult
+            psnr = -10.0 * torch.log(mse) / math.log(10.0)
+        return {"loss": loss, "rgbloss": mse, "interlevel": inter, "distortion": dist, "psnr": psnr}
+
     def training_step(self, batch, batch_idx):
-        raise NotImplementedError("hosnerf_b200: backward kernels are not part of this round (forward/eval only)")
+        raise NotImplementedError("hosnerf_b200: backward kernels are not part of this round (forward/eval only); "
+                                  "loss_terms() evaluates the objective's forward value")
 
     def configure_optimizers(self):
         return torch.optim.Adam(params=self.parameters(), lr=self.lr_init, betas=(0.9, 0.999))

@@ -383,3 +383,39 @@ def composite_s3(bkg_rgb, bkg_density, bkg_tdist, human_rgb, human_density, pts_
               _p(pts_mask), _p(newsmpl_pts), _host3(M, 16), _p(rays_o), _p(rays_d), n, sb, sh, thre_fg,
               _p(rgb), _p(is_fg), _p(hw), _stream())
     return rgb, is_fg.bool(), hw
+
+
+# ----------------------------------------------------------------------------- stage-1 loss terms (forward values)
+def lossfun_distortion(t, w):
+    """helper.lossfun_distortion (S1 helper.py:122-128): t [N,S+1], w [N,S] -> [N]."""
+    _chk(t, "t"), _chk(w, "w")
+    n, s = w.shape
+    if tuple(t.shape) != (n, s + 1):
+        raise RuntimeError(f"hosnerf_b200: lossfun_distortion expects t [N,S+1] and w [N,S], got {tuple(t.shape)} / {tuple(w.shape)}")
+    out = torch.empty(n, device=w.device, dtype=_F32)
+    _lib.call_unless_empty(n, "hos_lossfun_distortion", _p(t), _p(w), n, s, _p(out), _stream())
+    return out
+
+
+def lossfun_outer(t, w, t_env, w_env, want_rows=False):
+    """helper.lossfun_outer (S1 helper.py:92-120): fine histogram (t, w) against the proposal envelope
+    (t_env, w_env) -> loss [N,S] (and its row sums [N] when ``want_rows``)."""
+    _chk(t, "t"), _chk(w, "w"), _chk(t_env, "t_env"), _chk(w_env, "w_env")
+    n, s = w.shape
+    se = w_env.shape[1]
+    if tuple(t.shape) != (n, s + 1) or tuple(t_env.shape) != (n, se + 1) or w_env.shape[0] != n:
+        raise RuntimeError("hosnerf_b200: lossfun_outer expects t [N,S+1], w [N,S], t_env [N,Se+1], w_env [N,Se]")
+    loss = torch.empty(n, s, device=w.device, dtype=_F32)
+    rows = torch.empty(n, device=w.device, dtype=_F32) if want_rows else None
+    _lib.call_unless_empty(n, "hos_lossfun_outer", _p(t), _p(w), _p(t_env), _p(w_env), n, s, se, _p(loss), _p(rows), _stream())
+    return (loss, rows) if want_rows else loss
+
+
+def reduce_scaled(x, scale, y=None):
+    """scale * sum(x) (or scale * sum((x - y)^2)) as a 0-d CUDA tensor: one CTA, fixed order, double accumulation."""
+    _chk(x, "x"), _chk(y, "y")
+    if y is not None and y.numel() != x.numel():
+        raise RuntimeError("hosnerf_b200: reduce_scaled: x and y differ in size")
+    out = torch.zeros((), device=x.device, dtype=_F32)
+    _lib.call_unless_empty(x.numel(), "hos_reduce_scaled", _p(x), _p(y), x.numel(), float(scale), _p(out), _stream())
+    return out

@@ -1,0 +1,129 @@
+"""GPU parity of the stage-1 loss kernels (hos_lossfun_outer / hos_lossfun_distortion / hos_reduce_scaled and the
+LitMipNeRF360 loss methods on top) against the reference's own outputs (tests/golden/s1_losses.npz), the oracle, and
+size-independent properties at the C2 batch size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from hosnerf_b200 import LitMipNeRF360, ops, synth  # noqa: E402
+from oracle import losses_ref as L  # noqa: E402
+from oracle import mip360_ref as R  # noqa: E402
+
+HERE = os.path.dirname(__file__)
+G = np.load(os.path.join(HERE, "golden", "s1_losses.npz"))
+FIXTURES = ("s1_forward_default", "s1_forward_default_rand", "s1_forward_c2")
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _history(name):
+    F = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    levels = sorted({int(k[1]) for k in F.files if k.startswith("L") and k[2] == "_"})
+    return [{"sdist": cu(F[f"L{i}_sdist"]), "weights": cu(F[f"L{i}_weights"])} for i in levels], cu(F[f"R{levels[-1]}_rgb"])
+
+
+@pytest.mark.parametrize("pre,env", [("syn", ""), ("syn", "1"), ("big", "")])
+def test_lossfun_outer_golden(pre, env):
+    t, w, te, we = cu(G[f"{pre}_t"]), cu(G[f"{pre}_w"]), cu(G[f"{pre}_te{env}"]), cu(G[f"{pre}_we{env}"])
+    loss, rows = ops.lossfun_outer(t, w, te, we, want_rows=True)
+    ref = G[f"{pre}_outer{env}"]
+    # differences of float prefix sums: one ulp of the prefix sum (6e-8) is the floor for a term
+    assert np.abs(loss.cpu().numpy() - ref).max() < 3e-7
+    assert np.allclose(rows.cpu().numpy(), ref.sum(-1), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("pre", ["syn", "big"])
+def test_lossfun_distortion_golden(pre):
+    got = ops.lossfun_distortion(cu(G[f"{pre}_t"]), cu(G[f"{pre}_w"]))
+    assert np.allclose(got.cpu().numpy(), G[f"{pre}_distortion"], rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_lit_losses_on_reference_histories(name):
+    hist, rgb = _history(name)
+    lit = LitMipNeRF360("/nonexistent", num_levels=len(hist))
+    inter, dist = lit.interlevel_loss(hist), lit.distortion_loss(hist)
+    assert np.allclose(float(inter), G[f"{name}__interlevel"], rtol=2e-5)
+    assert np.allclose(float(dist), G[f"{name}__distortion"], rtol=2e-5)
+    mse = ops.reduce_scaled(rgb, 1.0 / rgb.numel(), y=cu(G[f"{name}__target"]))
+    assert np.allclose(float(mse), G[f"{name}__mse"], rtol=2e-6)
+
+
+def test_loss_terms_end_to_end_vs_oracle():
+    """Forward value of the training objective through the CUDA path (fp32) against the oracle pipeline with the
+    same jitter draws: forward pass + losses."""
+    kw = dict(num_levels=3, num_prop_samples=64, num_nerf_samples=32, opaque_background=True)
+    lit = LitMipNeRF360("/nonexistent", **kw)
+    synth.fill_params_(lit.model, 0)
+    lit.model.precision = "fp32"
+    lit._train_frac = 0.3
+    b = synth.make_bkg_batch(48, seed=4)
+    b["target"] = torch.rand(48, 3, generator=torch.Generator().manual_seed(9))
+    rands = [torch.rand(48, 1, generator=torch.Generator().manual_seed(20 + i)) for i in range(3)]
+    sd = {k: v.detach() for k, v in lit.model.state_dict().items()}
+    with torch.no_grad():
+        rr, rh = R.mip360_forward(sd, b, 0.3, True, 0.1, 1e6, rands=rands)
+    ref = L.stage1_objective([{k: v.numpy() for k, v in h.items() if k in ("sdist", "weights")} for h in rh],
+                             rr[-1]["rgb"].numpy(), b["target"].numpy())
+    lit = lit.cuda()
+    got = lit.loss_terms({k: v.cuda() for k, v in b.items()}, randomized=True, rands=[r.cuda() for r in rands])
+    for k in ("rgbloss", "interlevel", "distortion", "psnr", "loss"):
+        assert np.allclose(float(got[k]), ref[k], rtol=1e-4), (k, float(got[k]), ref[k])
+    with pytest.raises(NotImplementedError):
+        lit.training_step(b, 0)
+
+
+def test_loss_kernels_full_size_properties():
+    """C2 batch (4096 rays, 128 fine bins, 383-bin dilated envelope): size-independent properties."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, s, se = 4096, 128, 383
+    t = torch.sort(torch.rand(n, s + 1, device="cuda", generator=g), dim=-1).values
+    w = torch.rand(n, s, device="cuda", generator=g)
+    w = w / w.sum(-1, keepdim=True)
+    te = torch.sort(torch.rand(n, se + 1, device="cuda", generator=g), dim=-1).values
+    we = torch.rand(n, se, device="cuda", generator=g)
+    we = we / we.sum(-1, keepdim=True)
+    # (1) a histogram bounds itself: the outer measure of every bin is >= its own weight -> zero loss, up to the
+    # rounding of the float prefix sums (|d| <= 1.2e-7 on a tiny bin: d^2 / w ~ 1e-9)
+    assert float(ops.lossfun_outer(t, w, t, w).abs().max()) < 1e-8
+    # (2) an empty envelope leaves w^2 / (w + eps)
+    z = ops.lossfun_outer(t, w, te, torch.zeros_like(we))
+    assert torch.allclose(z, w * w / (w + 1.1920929e-07), rtol=1e-6, atol=0)
+    # (3) monotone: a heavier envelope never increases the loss
+    a, b2 = ops.lossfun_outer(t, w, te, we), ops.lossfun_outer(t, w, te, 2 * we)
+    assert bool((b2 <= a).all())
+    # (4) row sums and the mean agree with the element output
+    loss, rows = ops.lossfun_outer(t, w, te, we, want_rows=True)
+    assert torch.allclose(rows, loss.sum(-1), rtol=1e-5, atol=1e-8)
+    m = ops.reduce_scaled(rows, 1.0 / loss.numel())
+    assert np.allclose(float(m), float(loss.double().mean()), rtol=1e-6)
+    # (5) distortion is a quadratic form in w and translation invariant in t
+    d1 = ops.lossfun_distortion(t, w)
+    assert torch.allclose(ops.lossfun_distortion(t, 2 * w), 4 * d1, rtol=1e-6)
+    assert torch.allclose(ops.lossfun_distortion((t + 0.5).contiguous(), w), d1, rtol=2e-4, atol=1e-7)
+    # (6) a single occupied bin: only the intra-bin term w^2 dt / 3 is left
+    one = torch.zeros_like(w)
+    one[:, 17] = 0.7
+    assert torch.allclose(ops.lossfun_distortion(t, one), 0.49 * (t[:, 18] - t[:, 17]) / 3, rtol=1e-5, atol=1e-10)
+    # (7) against the oracle on a slice of the same inputs
+    k = 64
+    ref = L.lossfun_outer(t[:k].cpu().numpy(), w[:k].cpu().numpy(), te[:k].cpu().numpy(), we[:k].cpu().numpy())
+    assert np.abs(a[:k].cpu().numpy() - ref).max() < 3e-7
+    assert np.allclose(d1[:k].cpu().numpy(), L.lossfun_distortion(t[:k].cpu().numpy(), w[:k].cpu().numpy()), rtol=1e-5)
+
+
+def test_loss_kernels_empty_and_errors():
+    e = torch.empty(0, 33, device="cuda"), torch.empty(0, 32, device="cuda")
+    assert ops.lossfun_distortion(*e).shape == (0,)
+    assert ops.lossfun_outer(e[0], e[1], e[0], e[1]).shape == (0, 32)
+    assert float(ops.reduce_scaled(torch.empty(0, device="cuda"), 1.0)) == 0.0
+    with pytest.raises(RuntimeError):
+        ops.lossfun_distortion(torch.zeros(2, 33), torch.zeros(2, 32))            # CPU tensors: no CPU path
+    with pytest.raises(RuntimeError):
+        ops.lossfun_distortion(torch.zeros(2, 2000, device="cuda"), torch.zeros(2, 1999, device="cuda"))   # S > 1024
