@@ -504,6 +504,33 @@ class LitMipNeRF360(_LitBase):
             rendered, _ = self.model(batch, self._frac(), False, False, self.near, self.far)
         return {"target": batch.get("target"), "rgb": rendered[-1]["rgb"]}
 
+    def render_rays_stream(self, host_batches, depth: int = 2):
+        """``render_rays`` over an iterable of HOST ray batches (pinned tensors), as the eval loops do chunk by chunk
+        (S1 model.py:516-560), without a host/device round trip per chunk: the copy-in and the kernels of chunk i+1 are
+        enqueued before the rgb of chunk i is awaited.  Yields one pinned host tensor [n,3] per batch, in order; a
+        yielded tensor is a staging buffer that is overwritten once the next item is requested, so copy what you keep."""
+        dev = next(self.model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("hosnerf_b200: render_rays_stream needs the module on a CUDA device (no CPU path)")
+        slots, pending = [None] * depth, []
+        for i, hb in enumerate(host_batches):
+            batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in hb.items()}
+            rgb = self.render_rays(batch, i)["rgb"]
+            j = i % depth
+            if len(pending) == depth:             # slot j still belongs to chunk i - depth: hand it out first
+                ev, out = pending.pop(0)
+                ev.synchronize()
+                yield out
+            if slots[j] is None or slots[j].shape != rgb.shape:
+                slots[j] = torch.empty(rgb.shape, dtype=rgb.dtype, pin_memory=True)
+            slots[j].copy_(rgb, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((ev, slots[j]))
+        for ev, out in pending:
+            ev.synchronize()
+            yield out
+
     def validation_step(self, batch, batch_idx):
         return self.render_rays(batch, batch_idx)
 

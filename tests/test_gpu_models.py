@@ -168,6 +168,26 @@ def test_render_rays_surface(golden):
     assert any(k.startswith("model.mlps.2.pts_linear.7") for k in lit.state_dict())
 
 
+def test_render_rays_stream_matches_per_batch_calls():
+    """The chunk-streaming call returns, in order, exactly what render_rays returns batch by batch (different batch
+    sizes, more chunks than staging buffers, fp16 kernels)."""
+    lit = LitMipNeRF360("/nonexistent", opaque_background=True, precision="fp16", num_levels=2, num_prop_samples=64,
+                        num_nerf_samples=32, nerf_netwidth=256)
+    synth.fill_params_(lit.model, 0)
+    lit = lit.to(DEV)
+    sizes = [300, 257, 300, 64, 1, 512, 300]
+    host = [{k: v.contiguous().pin_memory() for k, v in synth.make_bkg_batch(n, seed=10 + i).items()}
+            for i, n in enumerate(sizes)]
+    want = [lit.render_rays({k: v.to(DEV) for k, v in hb.items()}, 0)["rgb"].cpu() for hb in host]
+    got = [o.clone() for o in lit.render_rays_stream(iter(host))]
+    assert [tuple(o.shape) for o in got] == [(n, 3) for n in sizes]
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert list(lit.render_rays_stream(iter([]))) == []
+    with pytest.raises(RuntimeError):
+        list(LitMipNeRF360("/nonexistent").render_rays_stream(iter(host)))      # module on the CPU: no CPU path
+
+
 def test_mip360_larger_batch_vs_oracle_fp32():
     """Seeded 200-ray batch (not in the fixtures), ragged vs every tile size in the kernels."""
     net = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256, precision="fp32")
