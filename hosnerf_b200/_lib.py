@@ -28,6 +28,21 @@ class MlpHead(C.Structure):
     _fields_ = [("out_dim", c_i), ("post", c_i), ("shift", c_fl), ("out_slot", c_i)]
 
 
+BKG_MAX_LEVELS = 4
+
+
+class BkgLevel(C.Structure):      # hos_bkg_level
+    _fields_ = [("mlp", C.c_void_p), ("n_samples", c_i), ("dilate", c_i), ("dilation", c_fl), ("u_base", c_f), ("jitter", c_f), ("jitter_cols", c_i),
+                ("max_jitter", c_fl), ("view_W", c_f), ("view_b", c_f), ("view_dim", c_i)]
+
+
+class BkgConfig(C.Structure):     # hos_bkg_config
+    _fields_ = [("n_levels", c_i), ("levels", BkgLevel * BKG_MAX_LEVELS), ("s_near", c_fl), ("s_far", c_fl),
+                ("dom_lo", c_fl), ("dom_hi", c_fl), ("anneal", c_fl), ("resample_padding", c_fl),
+                ("opaque_background", c_i), ("bg", c_fl), ("deg_view", c_i), ("basis_host", c_hp),
+                ("mlp_events", C.POINTER(C.c_void_p))]
+
+
 # name -> (restype, argtypes); mirrors include/hosnerf_b200.h one to one
 SIGNATURES = {
     "hos_last_error": (C.c_char_p, []),
@@ -71,6 +86,8 @@ SIGNATURES = {
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "hos_composite_s3": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_hp, c_f, c_f, c_i, c_i, c_i, c_fl,
                                c_f, c_f, c_f, c_f]),
+    "hos_render_bkg_workspace": (c_i, [C.POINTER(BkgConfig), c_i, C.POINTER(C.c_size_t)]),
+    "hos_render_bkg": (c_i, [C.POINTER(BkgConfig), c_f, c_f, c_f, c_f, c_i, c_f, C.c_size_t, c_f, c_f, c_f, c_f]),
     "hos_lossfun_distortion": (c_i, [c_f, c_f, c_i, c_i, c_f, c_f]),
     "hos_lossfun_outer": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f]),
     "hos_reduce_scaled": (c_i, [c_f, c_f, c_l, C.c_double, c_f, c_f]),
@@ -79,7 +96,8 @@ SIGNATURES = {
 _lib = None
 LAUNCHES = 0          # kernels of this library launched so far (bench.py reports it per timed region)
 _KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_layer": 2, "hos_mlp_set_bias": 1, "hos_mlp_set_head": 0,
-                     "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0, "hos_gemm_set_head": 0}
+                     "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0, "hos_gemm_set_head": 0,
+                     "hos_render_bkg_workspace": 0, "hos_render_bkg": 0}      # hos_render_bkg: counted by its caller
 
 
 def load():

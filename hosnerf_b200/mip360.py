@@ -464,6 +464,96 @@ class MipNeRF360(nn.Module):
         return renderings, history
 
 
+    # ------------------------------------------------------------------ one C call per batch
+    def fused_render_supported(self, precision=None) -> bool:
+        """True when ``render_fused`` can replace ``forward`` for an rgb-only render: tcgen05 mode, every level's MLP
+        runs with the fused IPE prologue (widths <= 256), stage-1 composite."""
+        precision = precision or self.precision or _DEFAULT_PRECISION
+        if precision != "fp16" or self.stage3 or ops.PROFILE is not None or not FUSE_IPE:
+            return False
+        if self.bg_intensity_range[0] != self.bg_intensity_range[1]:
+            return False
+        for i, m in enumerate(self.mlps):
+            if m.netwidth > 256 or m.pos_basis_t.shape[1] != 21 or m.max_deg_point - m.min_deg_point != 12 or m.min_deg_point != 0:
+                return False
+            if (i == self.num_levels - 1) == bool(m.disable_rgb):
+                return False
+        return True
+
+    def render_fused(self, batch, train_frac, randomized, near, far, rands=None, want_hist=False, mlp_events=None):
+        """The rgb of ``forward(...)[0][-1]`` through ONE library call (``hos_render_bkg``: the level loop of S1
+        model.py:331-461 sequenced in C on the current stream).  Same kernels, same order, same results as
+        ``forward``; what is saved is the per-level Python and allocator work.  Returns rgb [N,3] (and the final
+        level's (sdist, weights) when ``want_hist``).  ``mlp_events``: optional list of 2 * num_levels recorded-once
+        ``torch.cuda.Event(enable_timing=True)``; the library records them around each level's MLP launch."""
+        from . import _lib
+        rays_o = batch["rays_o"]
+        if not rays_o.is_cuda:
+            raise RuntimeError("hosnerf_b200.MipNeRF360: inputs must be CUDA tensors (no CPU fallback)")
+        if not self.fused_render_supported():
+            raise RuntimeError("hosnerf_b200.MipNeRF360.render_fused: configuration not covered (see fused_render_supported)")
+        n, dev = rays_o.shape[0], rays_o.device
+        rays_o = rays_o.contiguous().float()
+        rays_d = batch["rays_d"].contiguous().float()
+        viewdirs = batch["viewdirs"].contiguous().float()
+        radii = batch["radii"].reshape(-1).contiguous().float()
+        time = batch["times"][0:1]
+        lo = 0.0 if self.near_anneal_rate is None else max(min(1 - train_frac / self.near_anneal_rate, 1), 0)
+        anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) if self.anneal_slope > 0 else 1.0
+        keep = []                                  # tensors the config points into
+        cfg = _lib.BkgConfig()
+        cfg.n_levels = self.num_levels
+        prod = 1
+        for lvl, m in enumerate(self.mlps):
+            st = m._state_index(time)
+            ver = m._versions()
+            mlp = m._fused(st, ver)
+            L = cfg.levels[lvl]
+            L.mlp = mlp._h
+            s = self.num_prop_samples if lvl < self.num_levels - 1 else self.num_nerf_samples
+            u_base, mj = self._u_base(s, randomized, dev)
+            L.n_samples, L.u_base, L.max_jitter = s, u_base.data_ptr(), mj
+            L.dilation = self.dilation_bias + self.dilation_multiplier * (1.0 - lo) / prod
+            L.dilate = int(lvl > 0 and (self.dilation_bias > 0 or self.dilation_multiplier > 0))
+            prod *= s
+            if randomized:
+                d = 1 if self.single_jitter else s
+                r = (torch.rand(n, d) if rands is None else rands[lvl]).to(dev, torch.float32).contiguous()
+                keep.append(r)
+                L.jitter, L.jitter_cols = r.data_ptr(), d
+            if not m.disable_rgb:
+                f = m._folded(st, ver)
+                L.view_W, L.view_b, L.view_dim = f["views"][3].data_ptr(), mlp.view_bias.data_ptr(), m.netwidth_condition
+                cfg.deg_view = m.deg_view
+            cfg.basis_host = mlp.basis_host
+        cfg.s_near, cfg.s_far = float(np.float32(1 / near)), float(np.float32(1 / far))
+        cfg.dom_lo, cfg.dom_hi = float(lo), 1.0
+        cfg.anneal, cfg.resample_padding = float(anneal), float(self.resample_padding)
+        if mlp_events is not None:
+            assert len(mlp_events) == 2 * self.num_levels
+            evs = (ctypes.c_void_p * len(mlp_events))(*[e.cuda_event for e in mlp_events])
+            keep.append(evs)
+            cfg.mlp_events = ctypes.cast(evs, ctypes.POINTER(ctypes.c_void_p))
+        cfg.opaque_background, cfg.bg = int(self.opaque_background), float(self.bg_intensity_range[0])
+        rgb = torch.empty(n, 3, device=dev)
+        s_last = self.num_nerf_samples
+        sd = torch.empty(n, s_last + 1, device=dev) if want_hist else None
+        wt = torch.empty(n, s_last, device=dev) if want_hist else None
+        if n:
+            wkey = ("ws", n, str(dev), self.num_levels, self.num_prop_samples, self.num_nerf_samples)
+            if self._u_cache.get("ws_key") != wkey:
+                nbytes = ctypes.c_size_t(0)
+                _lib.call("hos_render_bkg_workspace", ctypes.byref(cfg), n, ctypes.byref(nbytes))
+                self._u_cache["ws_key"], self._u_cache["ws"] = wkey, torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            ws = self._u_cache["ws"]
+            _lib.call("hos_render_bkg", ctypes.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
+                      radii.data_ptr(), n, ws.data_ptr(), ws.numel(), rgb.data_ptr(),
+                      sd.data_ptr() if want_hist else None, wt.data_ptr() if want_hist else None,
+                      torch.cuda.current_stream().cuda_stream)
+            _lib.LAUNCHES += 1 + 3 * self.num_levels + 2      # level-0 histogram; resample + MLP + composite per level; view term
+        return (rgb, sd, wt) if want_hist else rgb
+
+
 try:
     import pytorch_lightning as _pl  # type: ignore
     _LitBase = _pl.LightningModule
@@ -501,8 +591,12 @@ class LitMipNeRF360(_LitBase):
 
     def render_rays(self, batch, batch_idx):
         with torch.no_grad():
-            rendered, _ = self.model(batch, self._frac(), False, False, self.near, self.far)
-        return {"target": batch.get("target"), "rgb": rendered[-1]["rgb"]}
+            if self.model.fused_render_supported():        # one library call for the whole level loop
+                rgb = self.model.render_fused(batch, self._frac(), False, self.near, self.far)
+            else:
+                rendered, _ = self.model(batch, self._frac(), False, False, self.near, self.far)
+                rgb = rendered[-1]["rgb"]
+        return {"target": batch.get("target"), "rgb": rgb}
 
     def render_rays_stream(self, host_batches, depth: int = 2):
         """``render_rays`` over an iterable of HOST ray batches (pinned tensors), as the eval loops do chunk by chunk

@@ -188,6 +188,32 @@ def test_render_rays_stream_matches_per_batch_calls():
         list(LitMipNeRF360("/nonexistent").render_rays_stream(iter(host)))      # module on the CPU: no CPU path
 
 
+@pytest.mark.parametrize("levels,randomized", [(2, False), (3, False), (3, True)])
+def test_render_fused_one_call_matches_level_loop(levels, randomized):
+    """hos_render_bkg (the whole level loop behind one C call) returns bit-for-bit what MipNeRF360.forward computes
+    level by level through the separate entry points; ragged ray count, multi-state model, optional jitter."""
+    net = _bkg(transitions=[0.25, 0.6], num_levels=levels, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256,
+               precision="fp16")
+    assert net.fused_render_supported()
+    n = 333
+    b = {k: cu(v) for k, v in synth.make_bkg_batch(n, seed=6, time=0.4).items()}
+    rands = [torch.rand(n, 1, generator=torch.Generator().manual_seed(40 + i)) for i in range(levels)] if randomized else None
+    with torch.no_grad():
+        rend, hist = net(b, 0.37, randomized, False, 0.1, 1e6, rands=rands)
+        rgb, sd, wt = net.render_fused(b, 0.37, randomized, 0.1, 1e6, rands=rands, want_hist=True)
+        rgb_only = net.render_fused(b, 0.37, randomized, 0.1, 1e6, rands=rands)
+    torch.cuda.synchronize()
+    assert torch.equal(rgb, rend[-1]["rgb"]) and torch.equal(rgb_only, rgb)
+    assert torch.equal(sd, hist[-1]["sdist"]) and torch.equal(wt, hist[-1]["weights"])
+    empty = {k: (v[:0] if v.dim() else v) for k, v in b.items()}
+    empty["times"] = b["times"]
+    assert net.render_fused(empty, 0.37, False, 0.1, 1e6).shape == (0, 3)
+    wide = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, precision="fp16")      # 1024-wide NeRF MLP
+    assert not wide.fused_render_supported()
+    with pytest.raises(RuntimeError):
+        wide.render_fused(b, 1.0, False, 0.1, 1e6)
+
+
 def test_mip360_larger_batch_vs_oracle_fp32():
     """Seeded 200-ray batch (not in the fixtures), ragged vs every tile size in the kernels."""
     net = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256, precision="fp32")
