@@ -480,7 +480,15 @@ class MipNeRF360(nn.Module):
                 return False
         return True
 
-    def render_fused(self, batch, train_frac, randomized, near, far, rands=None, want_hist=False, mlp_events=None):
+    @staticmethod
+    def fused_workspace(cfg, n, dev):
+        from . import _lib
+        nbytes = ctypes.c_size_t(0)
+        _lib.call("hos_render_bkg_workspace", ctypes.byref(cfg), n, ctypes.byref(nbytes))
+        return torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+
+    def render_fused(self, batch, train_frac, randomized, near, far, rands=None, want_hist=False, mlp_events=None,
+                     workspace=None):
         """The rgb of ``forward(...)[0][-1]`` through ONE library call (``hos_render_bkg``: the level loop of S1
         model.py:331-461 sequenced in C on the current stream).  Same kernels, same order, same results as
         ``forward``; what is saved is the per-level Python and allocator work.  Returns rgb [N,3] (and the final
@@ -540,12 +548,12 @@ class MipNeRF360(nn.Module):
         sd = torch.empty(n, s_last + 1, device=dev) if want_hist else None
         wt = torch.empty(n, s_last, device=dev) if want_hist else None
         if n:
-            wkey = ("ws", n, str(dev), self.num_levels, self.num_prop_samples, self.num_nerf_samples)
-            if self._u_cache.get("ws_key") != wkey:
-                nbytes = ctypes.c_size_t(0)
-                _lib.call("hos_render_bkg_workspace", ctypes.byref(cfg), n, ctypes.byref(nbytes))
-                self._u_cache["ws_key"], self._u_cache["ws"] = wkey, torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-            ws = self._u_cache["ws"]
+            ws = workspace                  # a caller that captures this call in a CUDA graph owns its workspace
+            if ws is None:
+                wkey = ("ws", n, str(dev), self.num_levels, self.num_prop_samples, self.num_nerf_samples)
+                if self._u_cache.get("ws_key") != wkey:
+                    self._u_cache["ws_key"], self._u_cache["ws"] = wkey, self.fused_workspace(cfg, n, dev)
+                ws = self._u_cache["ws"]
             _lib.call("hos_render_bkg", ctypes.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
                       radii.data_ptr(), n, ws.data_ptr(), ws.numel(), rgb.data_ptr(),
                       sd.data_ptr() if want_hist else None, wt.data_ptr() if want_hist else None,
@@ -598,18 +606,63 @@ class LitMipNeRF360(_LitBase):
                 rgb = rendered[-1]["rgb"]
         return {"target": batch.get("target"), "rgb": rgb}
 
-    def render_rays_stream(self, host_batches, depth: int = 2):
+    _RAY_KEYS = ("rays_o", "rays_d", "viewdirs", "radii")
+
+    def _graphed_render(self, hb, dev):
+        """Copy one HOST batch into the static inputs of a captured CUDA graph of ``render_fused`` and replay it (the
+        step is nine dependent launches: one graph launch instead).  Returns the graph's static rgb [n,3]."""
+        from . import _lib
+        m = self.model
+        n = hb["rays_o"].shape[0]
+        frac = self._frac()
+        times = hb["times"]                                   # stays on the host: only selects the state embedding
+        states = tuple(x._state_index(times[0:1]) for x in m.mlps)
+        key = (n, str(dev), frac, self.near, self.far, states, tuple(x._versions() for x in m.mlps))
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) >= 4:                               # a render has one or two batch sizes; weights change rarely
+                cache.pop(next(iter(cache)))
+            static = {k: torch.empty(tuple(hb[k].shape), dtype=torch.float32, device=dev) for k in self._RAY_KEYS}
+            static["times"] = times
+            for k in self._RAY_KEYS:
+                static[k].copy_(hb[k], non_blocking=True)
+            launches0 = _lib.LAUNCHES
+            m.render_fused(static, frac, False, self.near, self.far)     # packs weights / sizes the workspace before capture
+            per_replay = _lib.LAUNCHES - launches0
+            ws = torch.empty_like(m._u_cache["ws"])          # the graph's own workspace: never resized under it
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                rgb = m.render_fused(static, frac, False, self.near, self.far, workspace=ws)
+            _lib.LAUNCHES -= per_replay                      # the capture pass launched nothing
+            ent = cache[key] = (g, static, rgb, per_replay, ws)
+        g, static, rgb, per_replay, _ = ent
+        for k in self._RAY_KEYS:
+            static[k].copy_(hb[k], non_blocking=True)
+        g.replay()
+        _lib.LAUNCHES += per_replay
+        return rgb
+
+    def render_rays_stream(self, host_batches, depth: int = 2, graph: bool = True):
         """``render_rays`` over an iterable of HOST ray batches (pinned tensors), as the eval loops do chunk by chunk
         (S1 model.py:516-560), without a host/device round trip per chunk: the copy-in and the kernels of chunk i+1 are
-        enqueued before the rgb of chunk i is awaited.  Yields one pinned host tensor [n,3] per batch, in order; a
-        yielded tensor is a staging buffer that is overwritten once the next item is requested, so copy what you keep."""
+        enqueued before the rgb of chunk i is awaited.  With ``graph`` (and a model whose levels all run on the fused
+        tcgen05 path) every chunk is one CUDA-graph replay of ``hos_render_bkg`` on static input buffers.  Yields one
+        pinned host tensor [n,3] per batch, in order; a yielded tensor is a staging buffer that is overwritten once the
+        next item is requested, so copy what you keep."""
         dev = next(self.model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("hosnerf_b200: render_rays_stream needs the module on a CUDA device (no CPU path)")
         slots, pending = [None] * depth, []
         for i, hb in enumerate(host_batches):
-            batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in hb.items()}
-            rgb = self.render_rays(batch, i)["rgb"]
+            with torch.no_grad():
+                if graph and hb["rays_o"].shape[0] > 0 and self.model.fused_render_supported():
+                    rgb = self._graphed_render(hb, dev)
+                else:
+                    batch = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) and k != "times" else v)
+                             for k, v in hb.items()}
+                    rgb = self.render_rays(batch, i)["rgb"]
             j = i % depth
             if len(pending) == depth:             # slot j still belongs to chunk i - depth: hand it out first
                 ev, out = pending.pop(0)

@@ -179,10 +179,17 @@ def test_render_rays_stream_matches_per_batch_calls():
     host = [{k: v.contiguous().pin_memory() for k, v in synth.make_bkg_batch(n, seed=10 + i).items()}
             for i, n in enumerate(sizes)]
     want = [lit.render_rays({k: v.to(DEV) for k, v in hb.items()}, 0)["rgb"].cpu() for hb in host]
-    got = [o.clone() for o in lit.render_rays_stream(iter(host))]
-    assert [tuple(o.shape) for o in got] == [(n, 3) for n in sizes]
-    for a, b in zip(got, want):
-        assert torch.equal(a, b)
+    for graph in (True, False, True):              # CUDA-graph replay per chunk / plain launches / cached graphs again
+        got = [o.clone() for o in lit.render_rays_stream(iter(host), graph=graph)]
+        assert [tuple(o.shape) for o in got] == [(n, 3) for n in sizes]
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    # a weight update invalidates the captured graphs (they are keyed on the parameter versions)
+    with torch.no_grad():
+        lit.model.mlps[-1].rgb_layer.bias.add_(0.05)
+    want2 = lit.render_rays({k: v.to(DEV) for k, v in host[0].items()}, 0)["rgb"].cpu()
+    got2 = next(iter(lit.render_rays_stream(iter(host[:1])))).clone()
+    assert torch.equal(got2, want2) and not torch.equal(got2, want[0])
     assert list(lit.render_rays_stream(iter([]))) == []
     with pytest.raises(RuntimeError):
         list(LitMipNeRF360("/nonexistent").render_rays_stream(iter(host)))      # module on the CPU: no CPU path
