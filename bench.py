@@ -298,7 +298,8 @@ def main():
             "e2e": {"value": samples / (e2e_ms_max * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / K,
                     "api": "LitMipNeRF360.render_rays_stream(host batches): pinned host tensors in, rgb in pinned host memory out, "
-                           "every step; chunk i+1 is enqueued before chunk i's rgb is awaited",
+                           "every step; chunk i+1 is enqueued before chunk i's rgb is awaited; each chunk is one CUDA-graph "
+                           "replay of hos_render_bkg on static input buffers",
                     "blocking_ms_per_step": e2e_sync_ms_max / K,
                     "blocking_api": "LitMipNeRF360.render_rays(batch) with pinned host tensors in, rgb.cpu() out, one call at a time"},
             "gpu_launches": launches,

@@ -633,7 +633,7 @@ class LitMipNeRF360(_LitBase):
             ws = torch.empty_like(m._u_cache["ws"])          # the graph's own workspace: never resized under it
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
                 rgb = m.render_fused(static, frac, False, self.near, self.far, workspace=ws)
             _lib.LAUNCHES -= per_replay                      # the capture pass launched nothing
             ent = cache[key] = (g, static, rgb, per_replay, ws)
