@@ -315,9 +315,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n = 2048
-            sec = cpu_reference_steps(n, 2, 1, threads)
+            sec = cpu_reference_steps(n, 6, 1, threads)          # about 10 s of host work on the box's cores
             line["cpu_baseline"] = {"value": n * SAMPLES_PER_RAY / sec, "unit": "ray-samples/s", "cores": threads,
-                                    "kind": "port", "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 2 timed passes, torch CPU fp32 oracle"}
+                                    "kind": "port", "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 6 timed passes, torch CPU fp32 oracle"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
