@@ -221,6 +221,49 @@ def test_render_fused_one_call_matches_level_loop(levels, randomized):
         wide.render_fused(b, 1.0, False, 0.1, 1e6)
 
 
+def test_render_bkg_c_abi_argument_errors():
+    """hos_render_bkg reports bad arguments through its status code / hos_last_error instead of launching."""
+    import ctypes
+    from hosnerf_b200 import _lib
+    lib = _lib.load()
+    net = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256, precision="fp16")
+    b = {k: cu(v) for k, v in synth.make_bkg_batch(64, seed=2).items()}
+    with torch.no_grad():
+        net.render_fused(b, 1.0, False, 0.1, 1e6)                       # builds the MLP handles
+    cfg = _lib.BkgConfig()
+    nbytes = ctypes.c_size_t(0)
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 64, ctypes.byref(nbytes)) != 0     # n_levels = 0
+    assert b"n_levels" in lib.hos_last_error()
+    cfg.n_levels = 1
+    cfg.levels[0].n_samples = 32
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 64, ctypes.byref(nbytes)) != 0     # null mlp / u_base
+    m = net.mlps[-1]
+    mlp = m._fused(0)
+    u = torch.linspace(0.1, 0.9, 32, device=DEV)
+    basis = mlp.basis_host
+    cfg.levels[0].mlp, cfg.levels[0].u_base, cfg.basis_host = mlp._h, u.data_ptr(), basis
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 64, ctypes.byref(nbytes)) != 0     # final level without view term
+    assert b"view" in lib.hos_last_error()
+    f = m._folded(0)
+    cfg.levels[0].view_W, cfg.levels[0].view_b, cfg.levels[0].view_dim = f["views"][3].data_ptr(), mlp.view_bias.data_ptr(), 128
+    cfg.deg_view, cfg.s_near, cfg.s_far, cfg.dom_hi, cfg.anneal, cfg.resample_padding = 4, 10.0, 1e-6, 1.0, 1.0, 1e-5
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 64, ctypes.byref(nbytes)) == 0 and nbytes.value > 0
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=DEV)
+    rgb = torch.empty(64, 3, device=DEV)
+    args = [b["rays_o"].data_ptr(), b["rays_d"].data_ptr(), b["viewdirs"].data_ptr(), b["radii"].data_ptr(), 64]
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.hos_render_bkg(ctypes.byref(cfg), *args, ws.data_ptr(), nbytes.value - 1, rgb.data_ptr(), None, None, stream) != 0
+    assert b"workspace too small" in lib.hos_last_error()
+    assert lib.hos_render_bkg(ctypes.byref(cfg), *args, ws.data_ptr() + 4, nbytes.value, rgb.data_ptr(), None, None, stream) != 0
+    assert b"aligned" in lib.hos_last_error()
+    assert lib.hos_render_bkg(ctypes.byref(cfg), *args, ws.data_ptr(), nbytes.value, None, None, None, stream) != 0      # null output
+    assert lib.hos_render_bkg(ctypes.byref(cfg), *args, ws.data_ptr(), nbytes.value, rgb.data_ptr(), None, None, stream) == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(rgb).all()                                    # single-level render (NeRF MLP on the level-0 histogram)
+    args[-1] = 0
+    assert lib.hos_render_bkg(ctypes.byref(cfg), *args, None, 0, None, None, None, stream) == 0                            # empty batch: no-op
+
+
 def test_mip360_larger_batch_vs_oracle_fp32():
     """Seeded 200-ray batch (not in the fixtures), ragged vs every tile size in the kernels."""
     net = _bkg(num_levels=2, num_prop_samples=64, num_nerf_samples=32, nerf_netwidth=256, precision="fp32")
