@@ -328,7 +328,9 @@ struct MlpArgs {
 // the K-blocks come out in order while the recurrences run along l:
 //   sin/cos(2^l m): angle doubling, re-seeded from MUFU sin/cos after Cody-Waite reduction every 4
 //                   octaves (error <= ~1e-5, below the fp16 resolution of the operand);
-//   exp(-.5 4^l v): ex2.approx every 3rd octave, e_{l+1} = e_l^4 in between.
+//   exp(-.5 4^l v): ex2.approx every 4th octave, e_{l+1} = e_l^4 in between.
+//   (the sine of odd octaves comes out negated - three instructions per doubling instead of four - and the weight
+//   columns carry the sign.)
 // Per row and pass: ~210 MUFU + ~2.5 k FP instructions instead of 756 libm calls, and the features
 // never exist outside shared memory.
 // Geometry of one sample, shared by the three j-group passes of a feature pass.
@@ -413,13 +415,15 @@ __device__ __forceinline__ void ipe_group(const IpeArgs& A, const IpeRowGeom& G,
         s[q] = make_float2(__sinf(rx), __sinf(ry));
         c[q] = make_float2(__cosf(rx), __cosf(ry));
       } else {
-        const float2 nt = __fmul2_rn(s[q], kNeg2);         // -2 sin
-        const float2 sc = __fmul2_rn(s[q], c[q]);
-        c[q] = __ffma2_rn(nt, s[q], kOne);                 // 1 - 2 sin^2
-        s[q] = __fadd2_rn(sc, sc);                         // 2 sin cos
+        // three packed instructions per doubling: s holds (-1)^(l & 3) sin - the sign that -2 s c leaves behind is
+        // folded into the weights of the odd-octave sine columns at upload time (pack_weight_kernel)
+        const float2 nt = __fmul2_rn(s[q], kNeg2);         // -2 s
+        const float2 ns = __fmul2_rn(nt, c[q]);            // -2 s c = -(sin of the doubled angle, up to s's sign)
+        c[q] = __ffma2_rn(nt, s[q], kOne);                 // 1 - 2 s^2 (sign-invariant)
+        s[q] = ns;
       }
-      // ---- exp(-0.5 * 4^l * var_j): ex2 every 3rd octave, fourth powers in between
-      if ((l % 3) == 0) {
+      // ---- exp(-0.5 * 4^l * var_j): ex2 every 4th octave, fourth powers in between (<= 64 x the ex2.approx error)
+      if ((l & 3) == 0) {
         const float sc4 = -kHalfLog2e * (float)(1 << (2 * l));
         e[q] = make_float2(exp2f(sc4 * lv[q].x), exp2f(sc4 * lv[q].y));
       } else {
@@ -439,7 +443,9 @@ __device__ __forceinline__ void ipe_group(const IpeArgs& A, const IpeRowGeom& G,
 // so that a thread only carries one group's recurrence state at a time and the K-chunks come out in order.
 //   sin/cos(2^l m): angle doubling, re-seeded from MUFU sin/cos after Cody-Waite reduction every 4
 //                   octaves (error <= ~1e-5, below the fp16 resolution of the operand);
-//   exp(-.5 4^l v): ex2.approx every 3rd octave, e_{l+1} = e_l^4 in between.
+//   exp(-.5 4^l v): ex2.approx every 4th octave, e_{l+1} = e_l^4 in between.
+//   (the sine of odd octaves comes out negated - three instructions per doubling instead of four - and the weight
+//   columns carry the sign.)
 // kStg: ring depth.  kWarpArrive == false: every thread arrives on bar_xfull (count 128).
 // kWarpArrive == true (cluster-pair kernel): one arrival per warp, on the local bar_xfull (xfull_remote == 0)
 // or on the leader CTA's barrier at cluster address xfull_remote + 8 * stage.
@@ -1277,17 +1283,26 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int N, int in_h,
     const int l = (pr - pb) / gs, jj = (pr - pb) % gs;
     return half * (kIpeDeg * kIpeB) + l * kIpeB + jb + jj;
   };
+  // the generator emits (-1)^(l & 3) sin(2^l m) (ipe_group): odd octaves of the sine half take the sign here
+  auto ipe_sign = [](int c) {
+    const int pr = c >> 1;
+    const int gs = pr < 192 ? 8 : 5, pb = pr < 96 ? 0 : (pr < 192 ? 96 : 192);
+    const int l = (pr - pb) / gs;
+    return ((c & 1) == 0 && (l & 1)) ? -1.f : 1.f;
+  };
   if (kb < kb_h) {
     int c = kb * kKB + kk;
     if (c < in_h) {
-      if (ipe_perm & 2) c = ipe_col(c);
-      v = W[(int64_t)n * ktot + (x_first ? in_x + c : c)];
+      float sg = 1.f;
+      if (ipe_perm & 2) { sg = ipe_sign(c); c = ipe_col(c); }
+      v = sg * W[(int64_t)n * ktot + (x_first ? in_x + c : c)];
     }
   } else {
     int c = (kb - kb_h) * kKB + kk;
     if (c < in_x) {
-      if (ipe_perm & 1) c = ipe_col(c);
-      v = W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
+      float sg = 1.f;
+      if (ipe_perm & 1) { sg = ipe_sign(c); c = ipe_col(c); }
+      v = sg * W[(int64_t)n * ktot + (x_first ? c : in_h + c)];
     }
   }
   *reinterpret_cast<__half*>(dst + (size_t)kb * N * 128 + tile_byte_offset(n, kk)) = __float2half_rn(v);

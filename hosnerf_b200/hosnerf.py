@@ -31,3 +31,13 @@ def render_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dic
             thre_fg=thre_fg)
     return {"rgb": rgb, "idx_fg": idx_fg, "human_weights": human_w, "ray_history": ray_history,
             "net_output": net_output}
+
+
+def cycle_loss(net_output: dict):
+    """The cycle-consistency term of the stage-2/3 objective (S3 src/model/mipnerf360/model.py:1705-1707):
+    mean over the m foreground points of |observe - deform|^2 / 2, as a 0-d CUDA tensor (forward value; one
+    deterministic reduction kernel)."""
+    a, b = net_output["observe_pts"].contiguous().float(), net_output["deform_pts_final"].contiguous().float()
+    if a.shape != b.shape:
+        raise RuntimeError("hosnerf_b200.cycle_loss: observe_pts and deform_pts_final differ in shape")
+    return ops.reduce_scaled(a, 0.5 / max(a.shape[0], 1), y=b)

@@ -661,6 +661,14 @@ def test_human_cycle_outputs_vs_oracle():
     assert out["observe_pts"].shape == ref["observe_pts"].shape
     assert torch.equal(out["observe_pts"].cpu(), ref["observe_pts"])
     assert max_abs(out["deform_pts_final"].cpu(), ref["deform_pts_final"]) < 1e-3
+    # the cycle term of the objective (S3 model.py:1705-1707) on these outputs: reference formula on the oracle's
+    # points, and on the CUDA path's own points (isolates the reduction kernel)
+    from hosnerf_b200 import cycle_loss
+    got = float(cycle_loss(out))
+    own = float(torch.mean(torch.sum((out["observe_pts"] - out["deform_pts_final"]).double() ** 2, 1) / 2.0))
+    want = float(torch.mean(torch.sum((ref["observe_pts"] - ref["deform_pts_final"]) ** 2, 1) / 2.0))
+    assert abs(got - own) <= 1e-6 * abs(own)
+    assert abs(got - want) <= 2e-3 * abs(want) + 1e-9
 
 
 def test_edge_cases():
