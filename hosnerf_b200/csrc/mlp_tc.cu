@@ -377,7 +377,7 @@ __device__ __forceinline__ void ipe_row_setup(const IpeArgs& A, int64_t row, boo
 }
 
 // One group of GS basis directions (JBASE .. JBASE + GS - 1), all 12 octaves, two directions per packed fp32x2
-// instruction (sm_100 FMUL2 / FFMA2 / FADD2): per direction pair and octave 8 packed instructions instead of 16
+// instruction (sm_100 FMUL2 / FFMA2): per direction pair and octave 6 packed instructions instead of 16
 // scalar ones.  emit(p, e sin, e cos) receives the pair index p = PBASE + l * GS + jj (columns 2p, 2p + 1).
 template <int GS, int JBASE, int PBASE, class Emit>
 __device__ __forceinline__ void ipe_group(const IpeArgs& A, const IpeRowGeom& G, Emit&& emit) {
@@ -386,53 +386,64 @@ __device__ __forceinline__ void ipe_group(const IpeArgs& A, const IpeRowGeom& G,
   constexpr float k2PiLo = -1.7484555e-07f;               // 2 pi - fl32(2 pi)
   constexpr float kHalfLog2e = 0.72134752044448170f;      // 0.5 * log2(e)
   constexpr int NP = (GS + 1) / 2;                        // packed pairs (an odd group pads with a copy of its last direction)
-  float2 s[NP], c[NP], e[NP], lv[NP], lm[NP];
+  float2 S[NP], C[NP], e[NP], lv[NP], lm[NP];             // S = e * (+-sin), C = e * cos: the emitted values themselves
   // lifted mean  m_j = z.b_j  and variance  b_j^T J cov J^T b_j  with cov = t_var d d^T + r_var (I - d d^T/|d|^2):
   //   v = J b_j = a b_j + bq (x.b_j) x ;  var = t_var (d.v)^2 + r_var (|v|^2 - (d.v)^2 / |d|^2)
+  // two directions per packed instruction, the row's scalars broadcast to both halves
+  {
+    const float2 x0 = make_float2(G.x[0], G.x[0]), x1 = make_float2(G.x[1], G.x[1]), x2 = make_float2(G.x[2], G.x[2]);
+    const float2 d0 = make_float2(G.d[0], G.d[0]), d1 = make_float2(G.d[1], G.d[1]), d2 = make_float2(G.d[2], G.d[2]);
+    const float2 pa = make_float2(G.a, G.a), pbq = make_float2(G.bq, G.bq), pxd = make_float2(G.xd, G.xd);
+    const float2 pm = make_float2(G.m, G.m), p2a = make_float2(2.f * G.a, 2.f * G.a), paa = make_float2(G.a * G.a, G.a * G.a);
+    const float2 ptv = make_float2(G.t_var, G.t_var), prv = make_float2(G.r_var, G.r_var);
+    const float2 pnid = make_float2(-G.inv_dsq, -G.inv_dsq);
 #pragma unroll
-  for (int jj = 0; jj < 2 * NP; ++jj) {
-    const int j = JBASE + (jj < GS ? jj : GS - 1);
-    const float b0 = A.basis[j], b1 = A.basis[kIpeB + j], b2 = A.basis[2 * kIpeB + j];
-    const float xb = G.x[0] * b0 + G.x[1] * b1 + G.x[2] * b2;
-    const float db = G.d[0] * b0 + G.d[1] * b1 + G.d[2] * b2;
-    const float k = G.bq * xb;
-    const float dv = fmaf(k, G.xd, G.a * db);
-    const float vv = G.a * G.a + k * (2.f * G.a * xb + k * G.m);        // |b_j| = 1
-    const float var = fmaxf(fmaf(G.t_var, dv * dv, G.r_var * (vv - dv * dv * G.inv_dsq)), 0.f);
-    const float mean = G.a * xb;
-    if (jj & 1) { lv[jj >> 1].y = var; lm[jj >> 1].y = mean; } else { lv[jj >> 1].x = var; lm[jj >> 1].x = mean; }
+    for (int q = 0; q < NP; ++q) {
+      const int j0 = JBASE + 2 * q, j1 = JBASE + (2 * q + 1 < GS ? 2 * q + 1 : GS - 1);
+      const float2 b0 = make_float2(A.basis[j0], A.basis[j1]);
+      const float2 b1 = make_float2(A.basis[kIpeB + j0], A.basis[kIpeB + j1]);
+      const float2 b2 = make_float2(A.basis[2 * kIpeB + j0], A.basis[2 * kIpeB + j1]);
+      const float2 xb = __ffma2_rn(x2, b2, __ffma2_rn(x1, b1, __fmul2_rn(x0, b0)));
+      const float2 db = __ffma2_rn(d2, b2, __ffma2_rn(d1, b1, __fmul2_rn(d0, b0)));
+      const float2 k = __fmul2_rn(pbq, xb);
+      const float2 dv = __ffma2_rn(k, pxd, __fmul2_rn(pa, db));
+      const float2 vv = __ffma2_rn(k, __ffma2_rn(k, pm, __fmul2_rn(p2a, xb)), paa);       // |b_j| = 1
+      const float2 dv2 = __fmul2_rn(dv, dv);
+      const float2 var = __ffma2_rn(ptv, dv2, __fmul2_rn(prv, __ffma2_rn(dv2, pnid, vv)));
+      lv[q] = make_float2(fmaxf(var.x, 0.f), fmaxf(var.y, 0.f));
+      lm[q] = __fmul2_rn(pa, xb);
+    }
   }
-  const float2 kNeg2 = make_float2(-2.f, -2.f), kOne = make_float2(1.f, 1.f);
+  const float2 kNeg2 = make_float2(-2.f, -2.f);
 #pragma unroll
   for (int l = 0; l < kIpeDeg; ++l) {
 #pragma unroll
     for (int q = 0; q < NP; ++q) {
-      // ---- sin/cos of 2^l m_j: angle doubling, re-seeded from MUFU after Cody-Waite reduction every 4 octaves
       if ((l & 3) == 0) {
+        // ---- re-seed every 4 octaves: sin/cos of 2^l m_j from MUFU after Cody-Waite reduction, exp(-0.5 4^l var_j)
+        // from ex2.approx
         const float ax = lm[q].x * (float)(1 << l), ay = lm[q].y * (float)(1 << l);
         const float kx = rintf(ax * kInv2Pi), ky = rintf(ay * kInv2Pi);
         const float rx = fmaf(-kx, k2PiLo, fmaf(-kx, k2PiHi, ax)), ry = fmaf(-ky, k2PiLo, fmaf(-ky, k2PiHi, ay));
-        s[q] = make_float2(__sinf(rx), __sinf(ry));
-        c[q] = make_float2(__cosf(rx), __cosf(ry));
-      } else {
-        // three packed instructions per doubling: s holds (-1)^(l & 3) sin - the sign that -2 s c leaves behind is
-        // folded into the weights of the odd-octave sine columns at upload time (pack_weight_kernel)
-        const float2 nt = __fmul2_rn(s[q], kNeg2);         // -2 s
-        const float2 ns = __fmul2_rn(nt, c[q]);            // -2 s c = -(sin of the doubled angle, up to s's sign)
-        c[q] = __ffma2_rn(nt, s[q], kOne);                 // 1 - 2 s^2 (sign-invariant)
-        s[q] = ns;
-      }
-      // ---- exp(-0.5 * 4^l * var_j): ex2 every 4th octave, fourth powers in between (<= 64 x the ex2.approx error)
-      if ((l & 3) == 0) {
         const float sc4 = -kHalfLog2e * (float)(1 << (2 * l));
         e[q] = make_float2(exp2f(sc4 * lv[q].x), exp2f(sc4 * lv[q].y));
+        S[q] = __fmul2_rn(e[q], make_float2(__sinf(rx), __sinf(ry)));
+        C[q] = __fmul2_rn(e[q], make_float2(__cosf(rx), __cosf(ry)));
       } else {
+        // ---- in between, angle doubling and e <- e^4 on the products themselves (six packed instructions):
+        //   S' = e^4 (-2 s c) = (-2 e^2 S) C ,  C' = e^4 (1 - 2 s^2) = e^4 + (-2 e^2 S) S
+        // S carries (-1)^(l & 3) sin: the sign that -2 s c leaves behind is folded into the weights of the
+        // odd-octave sine columns at upload time (pack_weight_kernel).  Error <= ~1e-5 (sin/cos) and <= 64 x the
+        // ex2.approx error (exp) at the last octave before a re-seed, below the fp16 resolution of the operand.
         const float2 e2 = __fmul2_rn(e[q], e[q]);
         e[q] = __fmul2_rn(e2, e2);
+        const float2 gS = __fmul2_rn(__fmul2_rn(e2, kNeg2), S[q]);
+        const float2 nC = __ffma2_rn(gS, S[q], e[q]);
+        S[q] = __fmul2_rn(gS, C[q]);
+        C[q] = nC;
       }
-      const float2 es = __fmul2_rn(e[q], s[q]), ec = __fmul2_rn(e[q], c[q]);
-      emit(PBASE + l * GS + 2 * q, es.x, ec.x);
-      if (2 * q + 1 < GS) emit(PBASE + l * GS + 2 * q + 1, es.y, ec.y);
+      emit(PBASE + l * GS + 2 * q, S[q].x, C[q].x);
+      if (2 * q + 1 < GS) emit(PBASE + l * GS + 2 * q + 1, S[q].y, C[q].y);
     }
   }
 }
