@@ -76,6 +76,7 @@ struct MlpProgram {
   int kbh;             // K-blocks of the hidden activation buffer (width / 64)
   int n_max;           // widest layer
   int param_floats;
+  int head_base;       // params[head_base ..) = head weights / biases (the part the cluster-pair kernel keeps on chip)
   LayerDev layers[kMaxLayers];
   HeadDev heads[kMaxHeads];
 };
@@ -288,6 +289,17 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+// Same for a K-major SWIZZLE_32B operand: [rows x 16] fp16 = 32 B per row, 8-row groups 256 B apart; the 16-byte half
+// of element (r, k) is (k >> 3) ^ ((r >> 2) & 1)  (Swizzle<1,4,3>).  Used for the 4 KB constant ones operand.
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                         // SWIZZLE_32B
   return d;
 }
 // Instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M=128.
@@ -801,6 +813,7 @@ mlp_tc_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ M
 // live in the leader; tcgen05.commit multicasts "stage free" / "accumulator ready" to both.
 constexpr int kPairMaxStagesW = 8;
 constexpr int kPairStagesX = 3;
+constexpr int kOnesBytes = kTileM * 32;               // constant ones operand: [128 x 16] fp16, SWIZZLE_32B
 constexpr int kPairProducers = 3;
 constexpr int kPairMaxKbh = 4;
 constexpr int kRowBiasVecs = 4;
@@ -814,11 +827,12 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_stage_bytes = prog.n_max * 64;               // this CTA's half of an [n_max x 64] fp16 chunk
   unsigned char* sH = smem;                                // [kbh][16 KB] activations (A operand of the next layer)
-  unsigned char* sOnes = sH + prog.kbh * kXChunkBytes;     // [16 KB] constant A chunk: columns 0, 1 = 1.0 (bias as a rank-2 update)
-  unsigned char* sRingW = sOnes + kXChunkBytes;            // [stages_w][w_stage_bytes]
+  unsigned char* sOnes = sH + prog.kbh * kXChunkBytes;     // [4 KB] constant A operand of the bias MMA: [128 x 16], columns 0, 1 = 1.0
+  unsigned char* sRingW = sOnes + kOnesBytes;              // [stages_w][w_stage_bytes]
   unsigned char* sRingX = sRingW + stages_w * w_stage_bytes;       // [kPairStagesX][16 KB]
-  float* sParams = reinterpret_cast<float*>(sRingX + kPairStagesX * kXChunkBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((prog.param_floats + 3) & ~3));
+  float* sParams = reinterpret_cast<float*>(sRingX + kPairStagesX * kXChunkBytes);   // head weights / biases only: the layer
+  const int head_floats = prog.param_floats - prog.head_base;                      // biases ride in the GEMM (bias chunk)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((head_floats + 3) & ~3));
   uint64_t* bar_wfull = bars;                              // [S] leader: both halves landed (own tx bytes + the peer's relay
                                                            //     arrive); peer: its own half landed
   uint64_t* bar_wempty = bar_wfull + kPairMaxStagesW;      // [S] multicast commit: stage consumed
@@ -840,12 +854,13 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   const int n_layers = prog.n_layers;
   const uint32_t S = (uint32_t)stages_w;
 
-  for (int i = threadIdx.x; i < prog.param_floats; i += kMlpThreads) sParams[i] = args.params[i];
+  for (int i = threadIdx.x; i < head_floats; i += kMlpThreads) sParams[i] = args.params[prog.head_base + i];
   // Bias: every layer's weight stream ends with one extra chunk whose K-columns 0 / 1 hold fp16 hi / lo parts of
   // the bias; multiplied by this constant operand it lands in the accumulator, so the epilogue adds nothing.
-  for (int i = threadIdx.x; i < kXChunkBytes / 16; i += kMlpThreads) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < kOnesBytes / 16; i += kMlpThreads) reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
-  if (threadIdx.x < kTileM) *reinterpret_cast<uint32_t*>(sOnes + tile_byte_offset(threadIdx.x, 0)) = 0x3c003c00u;   // (1.0h, 1.0h)
+  if (threadIdx.x < kTileM)      // (1.0h, 1.0h) in columns 0, 1 of row r: 16-byte half (r >> 2) & 1 of its 32-byte row
+    *reinterpret_cast<uint32_t*>(sOnes + threadIdx.x * 32 + (((threadIdx.x >> 2) & 1) << 4)) = 0x3c003c00u;
   fence_proxy_async();
   if (threadIdx.x == 0) {
     const uint32_t both = rank == 0 ? 2u : 1u;             // the leader's barriers also count the peer
@@ -937,7 +952,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       const uint32_t xfull0 = smem_u32(&bar_xfull[0]), xempty0 = smem_u32(&bar_xempty[0]);
       const uint32_t hready_a = smem_u32(&bar_hready[0]), tfull0 = smem_u32(&bar_tfull[0]);
       const uint32_t h16 = (smem_u32(sH) >> 4) & 0x3FFF, x16 = (smem_u32(sRingX) >> 4) & 0x3FFF;
-      const uint32_t w16 = (smem_u32(sRingW) >> 4) & 0x3FFF, ones16 = (smem_u32(sOnes) >> 4) & 0x3FFF;
+      const uint32_t w16 = (smem_u32(sRingW) >> 4) & 0x3FFF;
+      const uint64_t ones_desc = umma_desc_sw32(smem_u32(sOnes));
       const uint32_t wstage16 = (uint32_t)w_stage_bytes >> 4;
       for (int g = cluster; g < n_groups; g += n_clusters) {
         for (int l = 0; l < n_layers; ++l, ++u) {
@@ -962,7 +978,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             prev_had_h = kb_h > 0;
             tc_fence_after();
             if (elect_one()) {
-              tc_mma_f16_pair(acc, desc_hi | (uint64_t)ones16, desc_hi | (uint64_t)(w16 + ws * wstage16), idesc, 0u);
+              tc_mma_f16_pair(acc, ones_desc, desc_hi | (uint64_t)(w16 + ws * wstage16), idesc, 0u);
               tc_commit_pair_addr(wempty0 + 8u * ws);
             }
             if (++ws == S) { ws = 0; wpar ^= 1; }
@@ -1031,7 +1047,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     const int ch = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
     const uint32_t hready0 = mapa_u32(smem_u32(&bar_hready[0]), 0);
-    const uint32_t sparams_u32 = smem_u32(sParams);
+    const uint32_t sparams_u32 = smem_u32(sParams) - 4u * (uint32_t)prog.head_base;   // indexed with whole-block offsets
     const uint32_t headx_u32 = smem_u32(s_headx) + 16u * r;
     // this thread's 16-byte slots in a K-chunk of H: row r, 16-byte groups 4 ch .. 4 ch + 3 (128B swizzle)
     const uint32_t h_row = smem_u32(sH) + 128u * r;
@@ -1703,6 +1719,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
       return nullptr;
     }
   }
+  P.head_base = (int)poff;
   for (int h = 0; h < n_heads; ++h) {
     int owner = -1;
     for (int l = 0; l < n_layers; ++l) if (layers[l].head == h) owner = l;
@@ -1736,8 +1753,9 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   for (int l = 0; l < n_layers; ++l) pair_ok = pair_ok && (layers[l].out_dim % 64) == 0;
   for (int l = 0; l + 1 < n_layers; ++l) pair_ok = pair_ok && layers[l].out_dim == P.kbh * kKB;   // one hready phase count
   pair_ok = pair_ok && P.kbh <= kPairMaxKbh;
-  const size_t pair_fixed = 1024 + (size_t)(P.kbh + 1) * kXChunkBytes + (size_t)kPairStagesX * kXChunkBytes +
-                            (((size_t)poff + 3) & ~(size_t)3) * 4 + (kPairBars + 1) * 8 + 16 + kTileM * 4 * sizeof(float) +
+  const size_t pair_fixed = 1024 + (size_t)P.kbh * kXChunkBytes + kOnesBytes + (size_t)kPairStagesX * kXChunkBytes +
+                            (((size_t)(poff - (uint32_t)P.head_base) + 3) & ~(size_t)3) * 4 + (kPairBars + 1) * 8 + 16 +
+                            kTileM * 4 * sizeof(float) +
                             kRowBiasVecs * 128 * sizeof(float);
   int pair_stages = pair_fixed < 227 * 1024 ? (int)((227 * 1024 - pair_fixed) / ((size_t)nmax * 64)) : 0;
   if (pair_stages > kPairMaxStagesW) pair_stages = kPairMaxStagesW;
