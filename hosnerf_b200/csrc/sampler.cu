@@ -278,7 +278,7 @@ sample_intervals_kernel(const float* __restrict__ t, const float* __restrict__ l
 }
 
 // One resampling step of MipNeRF360.forward (S1 model.py:362-408), fused.
-__global__ void __launch_bounds__(kSamplerThreads)
+__global__ void __launch_bounds__(kSamplerThreads, 8)
 resample_level_kernel(const float* __restrict__ sdist, const float* __restrict__ weights, int M_in,
                       int dilate, float dilation, float anneal, float pad,
                       const float* __restrict__ u_base, const float* __restrict__ jitter,
@@ -393,6 +393,13 @@ int hos_resample_level(const float* sdist, const float* weights, int N, int M_in
   HOS_REQUIRE(S >= 2 && S <= kMaxKnots, "hos_resample_level: need 2 <= S <= %d", kMaxKnots);
   HOS_REQUIRE(!jitter || jitter_cols == 1 || jitter_cols == S, "hos_resample_level: jitter_cols must be 1 or S");
   if (N == 0) return HOS_OK;
+  // 8 CTAs of 20.6 KB static shared memory per SM need the large shared-memory carve-out (a preference, set once)
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    HOS_CUDA(cudaFuncSetAttribute(resample_level_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    carveout_set = true;
+  }
   resample_level_kernel<<<N, kSamplerThreads, 0, (cudaStream_t)stream>>>(
       sdist, weights, M_in, dilate, dilation, anneal, resample_padding, u_base, jitter, jitter_cols,
       max_jitter, S, dom_lo, dom_hi, s_near, s_far, sdist_out, tdist_out);
