@@ -817,7 +817,7 @@ constexpr int kOnesBytes = kTileM * 32;               // constant ones operand: 
 constexpr int kPairProducers = 3;
 constexpr int kPairMaxKbh = 4;
 constexpr int kRowBiasVecs = 4;
-constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 2 + kPairMaxKbh;
+constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 2 + kPairMaxKbh + 2;
 static_assert(kPairBars % 2 == 0, "s_headx behind the barriers is read as float4");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
@@ -842,6 +842,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   uint64_t* bar_tfull = bar_xempty + kPairStagesX;         // [2 accumulator buffers] multicast commit
   uint64_t* bar_hready = bar_tfull + 2;                    // [kbh] leader only: K-chunk c of the next A operand written by
                                                            //       the 16 epilogue warps of the pair
+  uint64_t* bar_tfree = bar_hready + kPairMaxKbh;          // [1] leader only: a head layer's epilogue has finished its deferred
+                                                           //     second pass over the accumulator (16 warp arrivals)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kPairBars);       // kPairBars is even: 16-byte aligned
   float* s_headx = reinterpret_cast<float*>(s_tmem + 4);   // [128][4], read as float4
   float* s_rowbias = s_headx + kTileM * 4;                 // [kRowBiasVecs][128] per-ray bias vectors of the current tile
@@ -871,6 +873,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) mbar_init(&bar_tfull[s], 1);
     for (int s = 0; s < kPairMaxKbh; ++s) mbar_init(&bar_hready[s], 2 * kEpiWarps);
+    mbar_init(&bar_tfree[0], 2 * kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -951,6 +954,9 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       const uint32_t wfull0 = smem_u32(&bar_wfull[0]), wempty0 = smem_u32(&bar_wempty[0]);
       const uint32_t xfull0 = smem_u32(&bar_xfull[0]), xempty0 = smem_u32(&bar_xempty[0]);
       const uint32_t hready_a = smem_u32(&bar_hready[0]), tfull0 = smem_u32(&bar_tfull[0]);
+      const uint32_t tfree_a = smem_u32(&bar_tfree[0]);
+      uint32_t tfpar = 0;
+      bool head_hist[2] = {false, false};
       const uint32_t h16 = (smem_u32(sH) >> 4) & 0x3FFF, x16 = (smem_u32(sRingX) >> 4) & 0x3FFF;
       const uint32_t w16 = (smem_u32(sRingW) >> 4) & 0x3FFF;
       const uint64_t ones_desc = umma_desc_sw32(smem_u32(sOnes));
@@ -973,6 +979,13 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             // chunks it waited for that epilogue's last chunk signal, so the buffer is free now; if unit u - 1 read only
             // features (first layer of a tile) nothing has ordered us after epilogue(u - 2) yet: then wait for the first
             // operand chunk of this unit as well (signalled by epilogue(u - 1), which runs after epilogue(u - 2)).
+            // A hidden layer with an fp32 head re-reads its accumulator after it has signalled all operand chunks
+            // (deferred head pass): its buffer is free only once bar_tfree completes.
+            if (head_hist[u & 1]) {
+              mbar_wait2_spin(tfree_a, tfpar, tfree_a, tfpar);
+              tfpar ^= 1u;
+            }
+            head_hist[u & 1] = L.head >= 0 && l != n_layers - 1 && !(L.rowbias && args.rowbias);
             if (u < 2 || prev_had_h) mbar_wait2_spin(wfull0 + 8u * ws, wpar, wfull0 + 8u * ws, wpar);
             else mbar_wait2_spin(wfull0 + 8u * ws, wpar, kb_h > 0 ? hready_a : xfull0 + 8u * xs, kb_h > 0 ? hpar : xpar);
             prev_had_h = kb_h > 0;
@@ -1047,6 +1060,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     const int ch = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
     const uint32_t hready0 = mapa_u32(smem_u32(&bar_hready[0]), 0);
+    const uint32_t tfree0 = mapa_u32(smem_u32(&bar_tfree[0]), 0);
     const uint32_t sparams_u32 = smem_u32(sParams) - 4u * (uint32_t)prog.head_base;   // indexed with whole-block offsets
     const uint32_t headx_u32 = smem_u32(s_headx) + 16u * r;
     // this thread's 16-byte slots in a K-chunk of H: row r, 16-byte groups 4 ch .. 4 ch + 3 (128B swizzle)
@@ -1148,14 +1162,31 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             if (more1) tmem_ld32_nowait(acc + (uint32_t)((c + 1) * 64), vb);
             store32(va, c);
             chunk_ready(c);
-            if (has_head) head32(va, c);
             if (more1) {
               tmem_wait_ld();
               if (c + 2 < nchunks) tmem_ld32_nowait(acc + (uint32_t)((c + 2) * 64), va);
               store32(vb, c + 1);
               chunk_ready(c + 1);
-              if (has_head) head32(vb, c + 1);
             }
+          }
+          if (has_head) {
+            // Deferred head pass: every operand chunk of the next layer is signalled; now read the (still intact) fp32
+            // accumulator once more for the head dot products, then hand the buffer back (bar_tfree).
+            tmem_ld32_nowait(acc, va);
+            for (int c = 0; c < nchunks; c += 2) {
+              tmem_wait_ld();
+              const bool more1 = c + 1 < nchunks;
+              if (more1) tmem_ld32_nowait(acc + (uint32_t)((c + 1) * 64), vb);
+              head32(va, c);
+              if (more1) {
+                tmem_wait_ld();
+                if (c + 2 < nchunks) tmem_ld32_nowait(acc + (uint32_t)((c + 2) * 64), va);
+                head32(vb, c + 1);
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tfree0);
           }
         } else {
           // ---------- general layer: per-row bias, fp32 output head, last layer (no activations stored)
