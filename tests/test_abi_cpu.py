@@ -83,3 +83,24 @@ def test_state_dict_contract():
     assert h.cnl_mlp.pts_linears[10].weight.shape == (256, 383)
     assert h.non_rigid_mlp.block_mlps[8].weight.shape == (128, 164)
     assert sum(p.numel() for p in h.parameters()) == 64673787
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/hosnerf_b200.h is the drop-in boundary: it must compile as C11 (no C++ or torch types in the
+    signatures) and a C program must link against the shared library."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "hosnerf_b200.h"\n'
+                   'int main(void) { hos_bkg_config cfg; (void)cfg; printf("%d\\n", hos_version()); return 0; }\n')
+    inc = os.path.join(root, "include")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", inc, str(src)])
+    exe = tmp_path / "abi"
+    libdir = os.path.join(root, "hosnerf_b200")
+    subprocess.check_call(["gcc", "-std=c11", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-l:libhosnerf_b200.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and int(out.stdout.strip()) >= 1
