@@ -104,3 +104,37 @@ def test_header_is_plain_c_and_links(tmp_path):
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0 and int(out.stdout.strip()) >= 1
+
+
+def test_render_bkg_workspace_query_needs_no_gpu(lib):
+    """hos_render_bkg_workspace validates the level configuration and sizes the caller's workspace on the host:
+    errors come back as status + hos_last_error, sizes follow the documented sub-buffers."""
+    import ctypes
+    from hosnerf_b200 import _lib
+    cfg = _lib.BkgConfig()
+    n = ctypes.c_size_t(0)
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 128, ctypes.byref(n)) != 0
+    assert b"n_levels" in lib.hos_last_error()
+    basis = (ctypes.c_float * 63)()
+    cfg.n_levels, cfg.deg_view, cfg.basis_host = 2, 4, basis
+    dummy = ctypes.c_void_p(0x1000)            # never dereferenced by the size query
+    for i, s in enumerate((64, 32)):
+        cfg.levels[i].mlp, cfg.levels[i].n_samples, cfg.levels[i].u_base = dummy, s, dummy
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 128, ctypes.byref(n)) != 0      # final level without view term
+    cfg.levels[1].view_W, cfg.levels[1].view_b, cfg.levels[1].view_dim = dummy, dummy, 128
+    cfg.levels[0].dilate = 1
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 128, ctypes.byref(n)) != 0      # level 0 cannot dilate
+    cfg.levels[0].dilate, cfg.levels[1].dilate = 0, 1
+    sizes = []
+    for rays in (0, 1, 128, 4096):
+        assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), rays, ctypes.byref(n)) == 0
+        sizes.append(n.value)
+    assert sizes == sorted(sizes) and sizes[0] >= 0
+
+    def expect(N, smax=64, slast=32, vdim=128, de=27):
+        al = lambda f: (f * 4 + 255) & ~255
+        return (al(N * 2) + al(N) + 2 * (al(N * (smax + 1)) + al(N * smax)) + al(N * (smax + 1)) + al(N * smax)
+                + al(N * slast * 3) + al(N * de) + al(N * vdim))
+    assert sizes[3] == expect(4096) and sizes[2] == expect(128)
+    cfg.levels[1].n_samples = 400                                                          # 3 S + 1 > 1024 knots
+    assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 128, ctypes.byref(n)) != 0
