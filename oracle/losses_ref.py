@@ -61,3 +61,40 @@ def stage1_objective(history, rgb, target, data_loss_mult=1.0, interlevel_loss_m
         + inter * np.float32(interlevel_loss_mult) + dist * np.float32(distortion_loss_mult)
     psnr = np.float32(-10.0) * np.log(mse) / np.float32(np.log(10.0))
     return {"loss": np.float32(loss), "rgbloss": mse, "interlevel": inter, "distortion": dist, "psnr": np.float32(psnr)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Differentiable (torch) forms of the same terms: the oracle of the BACKWARD contract.  Gradients flow into `w`
+# (and `w_env`); the edges are treated as constants, as in the reference, where sample positions are detached
+# (S1 model.py:405-406) and interlevel_loss detaches the fine histogram (:613-614).
+def lossfun_outer_t(t, w, t_env, w_env):
+    import torch
+    cy = torch.cat([torch.zeros_like(w_env[..., :1]), torch.cumsum(w_env, dim=-1)], dim=-1)
+    cnt = torch.searchsorted(t_env.contiguous(), t.contiguous(), right=True)
+    lo = torch.clamp(cnt - 1, min=0)
+    hi = torch.clamp(cnt, max=t_env.shape[-1] - 1)
+    w_outer = torch.gather(cy, -1, hi[..., 1:]) - torch.gather(cy, -1, lo[..., :-1])
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + float(EPS))
+
+
+def lossfun_distortion_t(t, w):
+    import torch
+    u = (t[..., 1:] + t[..., :-1]) / 2
+    pair = torch.abs(u[..., :, None] - u[..., None, :])
+    inter = torch.sum(w * torch.sum(w[..., None, :] * pair, dim=-1), dim=-1)
+    intra = torch.sum(w ** 2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+    return inter + intra
+
+
+def stage1_objective_t(history, rgb, target, data_loss_mult=1.0, interlevel_loss_mult=1.0, distortion_loss_mult=0.01,
+                       charb_padding=0.001):
+    """Differentiable objective of training_step (model.py:488-512); ``history`` holds torch tensors."""
+    import torch
+    c, w = history[-1]["sdist"], history[-1]["weights"]
+    inter = 0.0
+    for lvl in history[:-1]:
+        inter = inter + torch.mean(lossfun_outer_t(c.detach(), w.detach(), lvl["sdist"], lvl["weights"]))
+    dist = torch.mean(lossfun_distortion_t(c, w))
+    mse = torch.mean((rgb - target) ** 2)
+    loss = torch.sqrt(mse + charb_padding ** 2) * data_loss_mult + inter * interlevel_loss_mult + dist * distortion_loss_mult
+    return {"loss": loss, "rgbloss": mse, "interlevel": inter, "distortion": dist}
