@@ -47,3 +47,36 @@ def test_oracle_autograd_matches_reference_gradients():
         assert np.allclose(got[:16].numpy(), ref_head, rtol=2e-3, atol=2e-4 * float(G[f"gabsmax__{name}"]) + 1e-12), name
         checked += 1
     assert checked > 40
+
+
+def test_human_oracle_autograd_matches_reference_gradients():
+    """Stage-2 human-object network, training mode (time = 0): surrogate objective mean(rgb) + 0.1 * cycle term."""
+    from hosnerf_b200 import Network, default_cfg
+    from oracle import human_ref as HR
+    H = np.load(os.path.join(os.path.dirname(__file__), "golden", "human_s2_backward.npz"))
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    net = Network(default_cfg(), stage2=True)
+    synth.fill_params_(net, 0)
+    synth.boost_human_density_(net)
+    pnames = {k for k, _ in net.named_parameters()}
+    params = {k: v.detach().clone().requires_grad_(k in pnames and v.is_floating_point()) for k, v in net.state_dict().items()}
+    b = synth.make_human_batch(12)
+    res = HR.network_forward(params, b, stage2=True)
+    assert res["observe_pts"].shape[0] == int(H["n_cycle_pts"])
+    cyc = torch.mean(torch.sum((res["observe_pts"] - res["deform_pts_final"]) ** 2, 1) / 2.0)
+    loss = res["rgb"].mean() + 0.1 * cyc
+    assert np.allclose(float(loss.detach()), H["loss"], rtol=2e-5)
+    assert np.allclose(float(cyc.detach()), H["cycle"], rtol=2e-4)
+    loss.backward()
+    names = [str(n) for n in H["param_names"]]
+    assert sorted(names) == sorted(pnames)
+    checked = 0
+    for name in names:
+        g = params[name].grad
+        assert f"gnone__{name}" not in H.files and g is not None, name        # every parameter of the branch trains
+        ref_norm, ref_head = float(H[f"gnorm__{name}"]), H[f"ghead__{name}"]
+        got = g.reshape(-1)
+        assert abs(float(got.double().norm()) - ref_norm) <= 5e-4 * ref_norm + 1e-12, (name, float(got.double().norm()), ref_norm)
+        assert np.allclose(got[:16].numpy(), ref_head, rtol=5e-3, atol=5e-4 * float(H[f"gabsmax__{name}"]) + 1e-12), name
+        checked += 1
+    assert checked == 74
