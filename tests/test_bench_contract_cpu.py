@@ -31,3 +31,15 @@ def test_reference_arm_prints_the_contract_line():
 
 def test_reference_arm_other_ranks_do_no_work():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a machine without a CUDA device the product arm must exit non-zero and print no result line."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("needs a machine without a GPU")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline"],
+                         cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0
+    assert '"metric"' not in out.stdout
