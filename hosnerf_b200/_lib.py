@@ -83,6 +83,7 @@ SIGNATURES = {
                                 c_f, c_f, c_f, c_f, c_f]),
     "hos_rays_intersect_bbox": (c_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), c_f, c_f, c_l, c_i, c_f, c_f, c_f, c_f]),
     "hos_composite_mip360": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
+    "hos_composite_mip360_backward": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "hos_composite_s3": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_hp, c_f, c_f, c_i, c_i, c_i, c_fl,
                                c_f, c_f, c_f, c_f]),

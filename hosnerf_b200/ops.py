@@ -353,6 +353,19 @@ def composite_mip360(density, tdist, dirs, rgb=None, opaque_background=False, bg
     return w, out
 
 
+def composite_mip360_backward(density, tdist, dirs, rgb=None, g_weights=None, g_rgb_out=None, opaque_background=False, bg=1.0):
+    """Gradients of composite_mip360 w.r.t. density (and the per-sample rgb) for upstream dL/dweights and / or
+    dL/d(composited rgb)."""
+    for t, nm in ((density, "density"), (tdist, "tdist"), (dirs, "dirs"), (rgb, "rgb"), (g_weights, "g_weights"), (g_rgb_out, "g_rgb_out")):
+        _chk(t, nm)
+    n, s = density.shape
+    gd = torch.empty(n, s, device=density.device, dtype=_F32)
+    gc = torch.empty(n, s, 3, device=density.device, dtype=_F32) if (rgb is not None and g_rgb_out is not None) else None
+    _lib.call_unless_empty(n, "hos_composite_mip360_backward", _p(density), _p(tdist), _p(dirs), _p(rgb), _p(g_weights),
+                           _p(g_rgb_out), n, s, int(opaque_background), float(bg), _p(gd), _p(gc), _stream())
+    return gd, gc
+
+
 def composite_nerf(raw, mask, z, dirs, bgcolor=None, activate=True):
     _chk(raw, "raw"), _chk(mask, "mask"), _chk(z, "z"), _chk(dirs, "dirs")
     n, s = z.shape

@@ -356,3 +356,32 @@ def test_composite_s3_golden(golden):
     assert rel_err(rgb.cpu(), g["rgb"]) < TOL
     assert rel_err(hw.cpu()[g["idx_fg"]], g["human_w"]) < TOL
     assert float(hw.cpu()[~g["idx_fg"]].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------- training path: composite backward
+@pytest.mark.parametrize("opaque,with_rgb,S", [(True, True, 32), (False, True, 77), (True, False, 128), (False, False, 64)])
+def test_composite_mip360_backward_vs_autograd(opaque, with_rgb, S):
+    """hos_composite_mip360_backward against autograd through the oracle's compute_alpha_weights + volumetric_rendering
+    (S1 helper.py:198-238) for random upstream gradients on the weights and (final level) on the composited rgb."""
+    g = torch.Generator().manual_seed(31 + S)
+    n = 67
+    tdist = torch.sort(torch.rand(n, S + 1, generator=g) * 5 + 0.1, dim=-1).values
+    density = (torch.rand(n, S, generator=g) * 3).requires_grad_(True)
+    dirs = torch.randn(n, 3, generator=g)
+    rgb = torch.rand(n, S, 3, generator=g).requires_grad_(True)
+    g_w = torch.randn(n, S, generator=g)
+    g_out = torch.randn(n, 3, generator=g)
+    w = R.alpha_weights(density, tdist, dirs, opaque_background=opaque)[0]
+    loss = (w * g_w).sum()
+    if with_rgb:
+        loss = loss + (R.render_rgb(rgb, w, bg=1.0) * g_out).sum()
+    loss.backward()
+    gd, gc = ops.composite_mip360_backward(cu(density.detach()), cu(tdist), cu(dirs), cu(rgb.detach()) if with_rgb else None,
+                                           cu(g_w), cu(g_out) if with_rgb else None, opaque_background=opaque, bg=1.0)
+    assert rel_err(gd.cpu(), density.grad) < TOL
+    if with_rgb:
+        assert rel_err(gc.cpu(), rgb.grad) < TOL
+    else:
+        assert gc is None
+    if opaque:
+        assert float(gd[:, -1].abs().max()) == 0.0          # the opaque last interval is a constant
