@@ -91,6 +91,8 @@ SIGNATURES = {
     "hos_render_bkg": (c_i, [C.POINTER(BkgConfig), c_f, c_f, c_f, c_f, c_i, c_f, C.c_size_t, c_f, c_f, c_f, c_f]),
     "hos_lossfun_distortion": (c_i, [c_f, c_f, c_i, c_i, c_f, c_f]),
     "hos_lossfun_outer": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f]),
+    "hos_lossfun_distortion_backward": (c_i, [c_f, c_f, c_f, c_fl, c_i, c_i, c_f, c_f]),
+    "hos_lossfun_outer_backward": (c_i, [c_f, c_f, c_f, c_f, c_fl, c_i, c_i, c_i, c_f, c_f]),
     "hos_reduce_scaled": (c_i, [c_f, c_f, c_l, C.c_double, c_f, c_f]),
 }
 

@@ -424,6 +424,26 @@ def lossfun_outer(t, w, t_env, w_env, want_rows=False):
     return (loss, rows) if want_rows else loss
 
 
+def lossfun_distortion_backward(t, w, g_scalar=1.0, g_ray=None):
+    """d(g * lossfun_distortion)/dw: [N,S]; g = g_scalar (times g_ray[ray] when given)."""
+    _chk(t, "t"), _chk(w, "w"), _chk(g_ray, "g_ray")
+    n, s = w.shape
+    out = torch.empty(n, s, device=w.device, dtype=_F32)
+    _lib.call_unless_empty(n, "hos_lossfun_distortion_backward", _p(t), _p(w), _p(g_ray), float(g_scalar), n, s, _p(out), _stream())
+    return out
+
+
+def lossfun_outer_backward(t, w, t_env, w_env, g_scalar=1.0):
+    """d(g_scalar * sum(lossfun_outer))/dw_env: [N,S_env] (the fine histogram is a constant)."""
+    _chk(t, "t"), _chk(w, "w"), _chk(t_env, "t_env"), _chk(w_env, "w_env")
+    n, s = w.shape
+    se = w_env.shape[1]
+    out = torch.empty(n, se, device=w.device, dtype=_F32)
+    _lib.call_unless_empty(n, "hos_lossfun_outer_backward", _p(t), _p(w), _p(t_env), _p(w_env), float(g_scalar), n, s, se,
+                           _p(out), _stream())
+    return out
+
+
 def reduce_scaled(x, scale, y=None):
     """scale * sum(x) (or scale * sum((x - y)^2)) as a 0-d CUDA tensor: one CTA, fixed order, double accumulation."""
     _chk(x, "x"), _chk(y, "y")

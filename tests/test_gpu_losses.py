@@ -127,3 +127,30 @@ def test_loss_kernels_empty_and_errors():
         ops.lossfun_distortion(torch.zeros(2, 33), torch.zeros(2, 32))            # CPU tensors: no CPU path
     with pytest.raises(RuntimeError):
         ops.lossfun_distortion(torch.zeros(2, 2000, device="cuda"), torch.zeros(2, 1999, device="cuda"))   # S > 1024
+
+
+# ----------------------------------------------------------------------------- training path: loss backward kernels
+@pytest.mark.parametrize("pre,env", [("syn", ""), ("syn", "1"), ("big", "")])
+def test_lossfun_outer_backward_vs_autograd(pre, env):
+    """dL/dw_env of sum(lossfun_outer) against autograd through the differentiable oracle (oracle/losses_ref.py), on the
+    edge-case histograms of the golden fixture (coinciding / repeated edges, intervals outside the envelope, empty bins)."""
+    t, w = torch.from_numpy(G[f"{pre}_t"]), torch.from_numpy(G[f"{pre}_w"])
+    te = torch.from_numpy(G[f"{pre}_te{env}"])
+    we = torch.from_numpy(G[f"{pre}_we{env}"]).clone().requires_grad_(True)
+    (0.37 * L.lossfun_outer_t(t, w, te, we).sum()).backward()
+    got = ops.lossfun_outer_backward(t.cuda(), w.cuda(), te.cuda(), we.detach().cuda(), g_scalar=0.37).cpu()
+    scale = max(float(we.grad.abs().max()), 1e-6)
+    assert float((got - we.grad).abs().max()) <= 2e-5 * scale + 1e-9
+    assert torch.equal(got == 0, we.grad == 0) or float((got - we.grad).abs().max()) <= 1e-6 * scale
+
+
+@pytest.mark.parametrize("pre", ["syn", "big"])
+def test_lossfun_distortion_backward_vs_autograd(pre):
+    t = torch.from_numpy(G[f"{pre}_t"])
+    w = torch.from_numpy(G[f"{pre}_w"]).clone().requires_grad_(True)
+    g_ray = torch.rand(w.shape[0], generator=torch.Generator().manual_seed(2)) + 0.5
+    (0.01 * (L.lossfun_distortion_t(t, w) * g_ray).sum()).backward()
+    got = ops.lossfun_distortion_backward(t.cuda(), w.detach().cuda(), g_scalar=0.01, g_ray=g_ray.cuda()).cpu()
+    assert torch.allclose(got, w.grad, rtol=2e-5, atol=1e-9)
+    plain = ops.lossfun_distortion_backward(t.cuda(), w.detach().cuda()).cpu()           # g = 1
+    assert torch.allclose(plain * (0.01 * g_ray)[:, None], w.grad, rtol=2e-5, atol=1e-9)
