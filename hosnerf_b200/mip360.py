@@ -453,6 +453,8 @@ class MipNeRF360(nn.Module):
             weights, rgb_out = ops.composite_mip360(density, tdist, rays_d, rgb if (last and not self.stage3) else None,
                                                     self.opaque_background, bg)
             res = {"density": density, "rgb": rgb, "sdist": sdist, "weights": weights}
+            if getattr(self, "_keep_tdist", False):
+                res["_tdist"] = tdist          # for the backward of the composite (LitMipNeRF360.loss_gradients)
             if self.stage3:
                 res["tdist"] = tdist
             else:
@@ -713,6 +715,48 @@ class LitMipNeRF360(_LitBase):
             loss = data + inter * self.interlevel_loss_mult + dist * self.distortion_loss_mult
             psnr = -10.0 * torch.log(mse) / math.log(10.0)
         return {"loss": loss, "rgbloss": mse, "interlevel": inter, "distortion": dist, "psnr": psnr}
+
+    def loss_gradients(self, batch, randomized: bool = True, rands=None):
+        """The loss side of the stage-1 backward pass (S1 model.py:488-512), on device kernels: forward render, the
+        objective, and its gradient with respect to what the MLPs produced - per level dL/ddensity [N,S] and, for the
+        final level, dL/drgb [N,S,3].  Chain: loss terms -> dL/dweights (``hos_lossfun_*_backward``) and
+        dL/d(composited rgb) -> ``hos_composite_mip360_backward``.  The sample positions are constants (the reference
+        detaches them, model.py:405-406).  The MLP dgrad / wgrad that would consume these gradients is not built yet."""
+        m = self.model
+        with torch.no_grad():
+            m._keep_tdist = True
+            try:
+                rendered, hist = m(batch, self._frac(), randomized, True, self.near, self.far, rands=rands)
+            finally:
+                m._keep_tdist = False
+            rgb = rendered[-1]["rgb"].contiguous()
+            target = batch["target"].to(rgb.dtype).contiguous()
+            n = rgb.shape[0]
+            mse = ops.reduce_scaled(rgb, 1.0 / max(rgb.numel(), 1), y=target)
+            data = torch.sqrt(mse + self.charb_padding ** 2) * self.data_loss_mult
+            inter, dist = self.interlevel_loss(hist), self.distortion_loss(hist)
+            loss = data + inter * self.interlevel_loss_mult + dist * self.distortion_loss_mult
+            # d(data term)/d(composited rgb) = mult / (2 sqrt(mse + pad^2)) * 2 (rgb - target) / numel
+            g_out = ((rgb - target) * (self.data_loss_mult / (torch.sqrt(mse + self.charb_padding ** 2) * rgb.numel()))).contiguous()
+            c, w = hist[-1]["sdist"].contiguous(), hist[-1]["weights"].contiguous()
+            rays_d = batch["rays_d"].contiguous().float()
+            bg = m.bg_intensity_range[0]
+            grads = []
+            for lvl, h in enumerate(hist):
+                last = lvl == len(hist) - 1
+                tdist = h.pop("_tdist")
+                if last:
+                    g_w = ops.lossfun_distortion_backward(c, w, g_scalar=self.distortion_loss_mult / max(n, 1))
+                    gd, gc = ops.composite_mip360_backward(h["density"].contiguous(), tdist, rays_d, h["rgb"].contiguous(), g_w, g_out,
+                                                           m.opaque_background, bg)
+                    grads.append({"density": gd, "rgb": gc})
+                else:
+                    g_w = ops.lossfun_outer_backward(c, w, h["sdist"].contiguous(), h["weights"].contiguous(),
+                                                     g_scalar=self.interlevel_loss_mult / max(w.numel(), 1))
+                    gd, _ = ops.composite_mip360_backward(h["density"].contiguous(), tdist, rays_d, None, g_w, None,
+                                                          m.opaque_background, bg)
+                    grads.append({"density": gd})
+        return {"loss": loss, "rgbloss": mse, "interlevel": inter, "distortion": dist, "ray_history": hist, "grads": grads}
 
     def training_step(self, batch, batch_idx):
         raise NotImplementedError("hosnerf_b200: backward kernels are not part of this round (forward/eval only); "
