@@ -138,3 +138,18 @@ def test_render_bkg_workspace_query_needs_no_gpu(lib):
     assert sizes[3] == expect(4096) and sizes[2] == expect(128)
     cfg.levels[1].n_samples = 400                                                          # 3 S + 1 > 1024 knots
     assert lib.hos_render_bkg_workspace(ctypes.byref(cfg), 128, ctypes.byref(n)) != 0
+
+
+def test_host_entry_points_refuse_cpu_inputs():
+    """The reference-facing modules have no CPU path: CPU tensors / a module left on the CPU raise instead of falling back."""
+    from hosnerf_b200 import LitMipNeRF360, synth
+    lit = LitMipNeRF360("/nonexistent", num_levels=2, num_prop_samples=8, num_nerf_samples=8, nerf_netwidth=64)
+    b = synth.make_bkg_batch(4, seed=0)
+    with pytest.raises(RuntimeError):
+        lit.render_rays(b, 0)
+    with pytest.raises(RuntimeError):
+        list(lit.render_rays_stream(iter([b])))
+    with pytest.raises(RuntimeError):
+        lit.model.render_fused(b, 1.0, False, 0.1, 1e6)
+    with pytest.raises(NotImplementedError):
+        lit.training_step(b, 0)
