@@ -86,7 +86,7 @@ SIGNATURES = {
     "hos_composite_mip360_backward": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f]),
     "hos_composite_nerf": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_i, c_f, c_f, c_f, c_f, c_f]),
     "hos_composite_s3": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_hp, c_f, c_f, c_i, c_i, c_i, c_fl,
-                               c_f, c_f, c_f, c_f]),
+                               c_f, c_f, c_f, c_f, c_f]),
     "hos_render_bkg_workspace": (c_i, [C.POINTER(BkgConfig), c_i, C.POINTER(C.c_size_t)]),
     "hos_render_bkg": (c_i, [C.POINTER(BkgConfig), c_f, c_f, c_f, c_f, c_i, c_f, C.c_size_t, c_f, c_f, c_f, c_f]),
     "hos_lossfun_distortion": (c_i, [c_f, c_f, c_i, c_i, c_f, c_f]),

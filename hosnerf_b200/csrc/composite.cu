@@ -274,6 +274,7 @@ composite_s3_kernel(const float* __restrict__ bkg_rgb, const float* __restrict__
   __syncwarp();
   double carry = 1.0;
   float cr = 0.f, cg = 0.f, cb = 0.f;
+  int hrank = 0;                                     // human samples met so far along the merged (depth-sorted) ray
   for (int base = 0; base < tot; base += 32) {
     int i = base + lane;
     float alpha = 0.f, r = 0.f, g = 0.f, b = 0.f;
@@ -301,11 +302,15 @@ composite_s3_kernel(const float* __restrict__ bkg_rgb, const float* __restrict__
     double prev = shfl_up_d(inc, 1);
     float T = (float)(lane == 0 ? carry : prev);
     carry = __shfl_sync(0xffffffffu, inc, 31);
+    // model.py:1577,1588: human_weights = weights[total_order >= Sb].reshape(z_vals_human.shape) - the k-th human sample
+    // met in DEPTH order lands in column k (equal to the sample index only while the projected depths are monotone).
+    const unsigned hm = __ballot_sync(0xffffffffu, i < tot && src >= Sb);
     if (i < tot) {
       float w = alpha * T;
       cr += w * r; cg += w * g; cb += w * b;
-      if (human_w && src >= Sb) human_w[(size_t)ray * Sh + (src - Sb)] = w;
+      if (human_w && src >= Sb) human_w[(size_t)ray * Sh + hrank + __popc(hm & ((1u << lane) - 1u))] = w;
     }
+    hrank += __popc(hm);
   }
   cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
   if (lane == 0) { rgb_out[ray * 3] = cr; rgb_out[ray * 3 + 1] = cg; rgb_out[ray * 3 + 2] = cb; }
@@ -369,16 +374,16 @@ int hos_composite_s3(const float* bkg_rgb, const float* bkg_density, const float
                      const float* human_rgb, const float* human_density, const float* pts_mask,
                      const float* newsmpl_pts, const float* M_host, const float* rays_o,
                      const float* rays_d, int n, int Sb, int Sh, float thre_fg, float* rgb_out,
-                     uint8_t* is_fg, float* human_w, void* stream) {
+                     uint8_t* is_fg, float* human_w, int* flag_ws, void* stream) {
   HOS_ARCH_GUARD();
   HOS_REQUIRE(bkg_rgb && bkg_density && bkg_tdist && human_rgb && human_density && pts_mask && newsmpl_pts &&
               M_host && rays_o && rays_d && rgb_out, "hos_composite_s3: null pointer");
   HOS_REQUIRE(n >= 0 && Sb >= 1 && Sh >= 1 && Sb + Sh <= kS3MaxTot, "hos_composite_s3: need Sb+Sh <= %d", kS3MaxTot);
   if (n == 0) return HOS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static thread_local int* d_flag = nullptr;
-  if (!d_flag) HOS_CUDA(cudaMalloc(&d_flag, sizeof(int)));
-  HOS_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  HOS_REQUIRE(flag_ws, "hos_composite_s3: flag_ws (one int of caller-owned device memory) is NULL");
+  int* d_flag = flag_ws;                             // "any |rays_d| < 1e-5 in the batch" (model.py:1526), caller-owned:
+  HOS_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));   // no allocation in the library, per device, capture-safe
   any_small_dir_kernel<<<(n * 3 + 255) / 256, 256, 0, st>>>(rays_d, n * 3, d_flag);
   HOS_LAUNCH_CHECK();
   int n2 = 1;

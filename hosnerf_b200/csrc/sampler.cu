@@ -6,6 +6,8 @@
 // HBM traffic is the algorithmic minimum (read t/w once, write sdist/tdist once).
 #include <math_constants.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace hos {
@@ -394,11 +396,15 @@ int hos_resample_level(const float* sdist, const float* weights, int N, int M_in
   HOS_REQUIRE(!jitter || jitter_cols == 1 || jitter_cols == S, "hos_resample_level: jitter_cols must be 1 or S");
   if (N == 0) return HOS_OK;
   // 8 CTAs of 20.6 KB static shared memory per SM need the large shared-memory carve-out (a preference, set once)
-  static bool carveout_set = false;
-  if (!carveout_set) {
+  // (function attributes are per device: one bit per device ordinal, set with an atomic so concurrent host threads agree)
+  static std::atomic<unsigned long long> carveout_set{0ull};
+  int dev_ord = 0;
+  HOS_CUDA(cudaGetDevice(&dev_ord));
+  const unsigned long long bit = 1ull << (dev_ord & 63);
+  if (!(carveout_set.load(std::memory_order_relaxed) & bit)) {
     HOS_CUDA(cudaFuncSetAttribute(resample_level_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxShared));
-    carveout_set = true;
+    carveout_set.fetch_or(bit, std::memory_order_relaxed);
   }
   resample_level_kernel<<<N, kSamplerThreads, 0, (cudaStream_t)stream>>>(
       sdist, weights, M_in, dilate, dilation, anneal, resample_padding, u_base, jitter, jitter_cols,

@@ -537,6 +537,8 @@ class Network(nn.Module):
                 jitter = (torch.rand(n, S) if rand is None else rand).to(rays.device, torch.float32).contiguous()
 
             outs = {}
+            if n == 0:
+                raise RuntimeError("hosnerf_b200.Network: empty ray batch (the reference fails on it too: torch.cat of no chunks)")
             for c0 in range(0, n, cfg.chunk):
                 c1 = min(n, c0 + cfg.chunk)
                 z, pts = ops.human_samples(rays_o[c0:c1], rays_d[c0:c1], near[c0:c1], far[c0:c1], t_lin,
@@ -568,12 +570,12 @@ class Network(nn.Module):
                         if not cfg.ignore_non_rigid_motions:
                             xd = self._eval_non_rigid("nrf", self.non_rigid_forward_mlp, xd, cond, hann_w, precision)
                         ret["deform_pts_final"], ret["observe_pts"] = xd, observe
+                ret["_x_skel"], ret["_cnl_pts"] = x_skel, cnl          # stage-wise parity hooks (all chunks, like every other output)
                 for k, v in ret.items():
                     outs.setdefault(k, []).append(v)
             all_ret = {k: torch.cat(v, 0) for k, v in outs.items()}
             for k in all_ret:
-                if k not in ("deform_pts_prev_final", "deform_pts_final", "observe_pts"):
+                if k not in ("deform_pts_prev_final", "deform_pts_final", "observe_pts", "_x_skel", "_cnl_pts"):
                     all_ret[k] = torch.reshape(all_ret[k], list(rays_shape[:-1]) + list(all_ret[k].shape[1:]))
             all_ret["bgcolor"] = bgcolor
-            all_ret["_x_skel"], all_ret["_cnl_pts"] = x_skel, cnl
             return all_ret

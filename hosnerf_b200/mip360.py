@@ -138,7 +138,17 @@ class MipNeRF360MLP(nn.Module):
         return select_state_index(len(self.bkgd_stateembeds), time, self.transitions_times)
 
     def _versions(self):
-        return tuple(p._version for p in self.parameters()) + (self.pos_basis_t._version,)
+        """Cache key of everything derived from the parameters: in-place version AND storage identity
+        (``module.to(dev)``, ``.half()`` and ``param.data = ...`` replace the storage without bumping ``_version``)."""
+        ps = list(self.parameters()) + [self.pos_basis_t]
+        return tuple((p._version, p.data_ptr(), p.dtype) for p in ps)
+
+    def _slot(self, kind: str, state_idx: int, ver):
+        """Per-state cache slot (a multi-state sequence alternates between embeddings: one slot per state instead of
+        rebuilding - and freeing device buffers a captured CUDA graph may still point into - on every switch)."""
+        d = self._cache.setdefault(kind, {})
+        ent = d.get(state_idx)
+        return d, (ent[1] if ent is not None and ent[0] == ver else None)
 
     def _check_supported(self):
         if self.netdepth_condition != 1 or self.num_density_channels != 1:
@@ -147,9 +157,10 @@ class MipNeRF360MLP(nn.Module):
     def _folded(self, state_idx: int, _ver=None):
         """fp32 weights with the (constant per call) state embedding folded into the bias of
         every layer that sees the encoded input: W[:, ipe:ipe+64] @ e  (S1 model.py:208-209)."""
-        key = ("f32", state_idx, _ver if _ver is not None else self._versions())
-        if self._cache.get("f32_key") == key:
-            return self._cache["f32"]
+        ver = _ver if _ver is not None else self._versions()
+        slots, hit = self._slot("f32", state_idx, ver)
+        if hit is not None:
+            return hit
         self._check_supported()
         e = self.bkgd_stateembeds[state_idx].detach()
         F, nw = self.ipe_size, self.netwidth
@@ -173,19 +184,20 @@ class MipNeRF360MLP(nn.Module):
             Wr = self.rgb_layer.weight.detach() * self.rgb_premultiplier
             br = self.rgb_layer.bias.detach() * self.rgb_premultiplier + self.rgb_bias
             out["rgb"] = (Wr.contiguous(), br.contiguous())
-        self._cache["f32_key"], self._cache["f32"] = key, out
+        slots[state_idx] = (ver, out)
         return out
 
     def _fused(self, state_idx: int, _ver=None):
         """tcgen05 program + uploaded fp16 weights (rebuilt when any parameter changes)."""
-        key = ("f16", state_idx, _ver if _ver is not None else self._versions())
-        if self._cache.get("f16_key") == key:
-            return self._cache["f16"]
+        ver = _ver if _ver is not None else self._versions()
+        slots, hit = self._slot("f16", state_idx, ver)
+        if hit is not None:
+            return hit
         if self.netwidth > 256 or self.netwidth % 64 != 0:
             raise NotImplementedError(
                 f"hosnerf_b200: the fused tcgen05 MLP kernel supports widths <= 256 (got {self.netwidth}); "
                 "wide networks run layer by layer (_wide)")
-        f = self._folded(state_idx, _ver)
+        f = self._folded(state_idx, ver)
         F, nw = self.ipe_size, self.netwidth
         layers, heads = [], []
         for i in range(self.netdepth):
@@ -226,7 +238,8 @@ class MipNeRF360MLP(nn.Module):
                 mlp.set_layer(self.netdepth + 1, Wv1, None)
                 mlp.view_bias = bv
             mlp.set_head(1, *f["rgb"])
-        self._cache["f16_key"], self._cache["f16"] = key, mlp
+        mlp.folded = f                      # the view-term tensors a captured graph points into live as long as the program
+        slots[state_idx] = (ver, mlp)
         return mlp
 
     def _wide(self, state_idx: int, _ver=None):
@@ -234,13 +247,14 @@ class MipNeRF360MLP(nn.Module):
         S1 model.py:267-275): every pts_linear layer is one tensor-core GEMM over tiled fp16 activations
         (``ops.TiledLinear``), the density head rides in the last one's epilogue, and the narrow bottleneck + view
         layers run on the fused kernel."""
-        key = ("wide", state_idx, _ver if _ver is not None else self._versions())
-        if self._cache.get("wide_key") == key:
-            return self._cache["wide"]
+        ver = _ver if _ver is not None else self._versions()
+        slots, hit = self._slot("wide", state_idx, ver)
+        if hit is not None:
+            return hit
         if self.netwidth % 256 != 0:
             raise NotImplementedError(f"hosnerf_b200: fp16 mode needs netwidth <= 256 or a multiple of 256 (got {self.netwidth}); "
                                       "use precision='fp32' for this network")
-        f = self._folded(state_idx, _ver)
+        f = self._folded(state_idx, ver)
         F, nw = self.ipe_size, self.netwidth
         fast = (FUSE_IPE and self.pos_basis_t.shape[1] == 21 and self.max_deg_point - self.min_deg_point == 12
                 and self.min_deg_point == 0)      # features from the fast generator (kernel column order)
@@ -269,7 +283,7 @@ class MipNeRF360MLP(nn.Module):
         if fast:
             bh = self.pos_basis_t.detach().float().cpu().contiguous().reshape(-1).tolist()
             out["basis_host"] = (ctypes.c_float * len(bh))(*bh)
-        self._cache["wide_key"], self._cache["wide"] = key, out
+        slots[state_idx] = (ver, out)
         return out
 
     # ------------------------------------------------------------------ evaluation
@@ -396,6 +410,28 @@ class MipNeRF360(nn.Module):
             self._u_cache[key] = (u.to(device), float(mj))
         return self._u_cache[key]
 
+    def _host_time(self, time):
+        """``time`` only selects the state embedding: resolve a device tensor to a host float ONCE per call (every MLP of
+        every level would otherwise synchronise on it), and not at all for single-state models."""
+        if isinstance(time, torch.Tensor) and time.is_cuda and any(len(m.bkgd_stateembeds) > 1 for m in self.mlps):
+            return float(time.reshape(-1)[0]) if time.numel() else 0.0
+        return time
+
+    def _background(self, randomized: bool) -> float:
+        """Background intensity composited behind the last sample (S1 model.py:437-444): the midpoint of
+        ``bg_intensity_range`` when it is not randomised."""
+        lo, hi = self.bg_intensity_range[0], self.bg_intensity_range[1]
+        if lo == hi:
+            return float(lo)
+        if randomized:
+            raise NotImplementedError("hosnerf_b200: random background intensity is not built")
+        return (lo + hi) / 2.0
+
+    def _check_noise(self, randomized: bool):
+        if randomized and any(m.density_noise > 0 or m.bottleneck_noise > 0 for m in self.mlps):
+            raise NotImplementedError("hosnerf_b200: density_noise / bottleneck_noise > 0 with randomized=True is not built "
+                                      "(the reference adds rand_like noise, S1 model.py:226-241)")
+
     def forward(self, batch, train_frac, randomized, is_train, near, far, rands=None):
         rays_o = batch["rays_o"]
         if not rays_o.is_cuda:
@@ -409,7 +445,7 @@ class MipNeRF360(nn.Module):
         rays_d = batch["rays_d"].contiguous().float()
         viewdirs = batch["viewdirs"].contiguous().float()
         radii = batch["radii"].reshape(-1).contiguous().float()
-        time = batch["times"] if self.stage3 else batch["times"][0:1]
+        time = self._host_time(batch["times"] if self.stage3 else batch["times"][0:1])
         s_near, s_far = float(np.float32(1 / near)), float(np.float32(1 / far))
         if self.near_anneal_rate is None:
             lo = 0.0
@@ -427,11 +463,8 @@ class MipNeRF360(nn.Module):
         history, renderings = [], []
         anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) \
             if self.anneal_slope > 0 else 1.0
-        bg = self.bg_intensity_range[0]
-        if self.bg_intensity_range[0] != self.bg_intensity_range[1]:
-            if randomized:
-                raise NotImplementedError("hosnerf_b200: random background intensity is not built")
-            bg = (self.bg_intensity_range[0] + self.bg_intensity_range[1]) / 2.0
+        bg = self._background(randomized)
+        self._check_noise(randomized)
         for lvl in range(self.num_levels):
             is_prop = lvl < self.num_levels - 1
             s = self.num_prop_samples if is_prop else self.num_nerf_samples
@@ -473,6 +506,8 @@ class MipNeRF360(nn.Module):
         precision = precision or self.precision or _DEFAULT_PRECISION
         if precision != "fp16" or self.stage3 or ops.PROFILE is not None or not FUSE_IPE:
             return False
+        if self.num_levels > 4:                 # BKG_MAX_LEVELS of include/hosnerf_b200.h
+            return False
         if self.bg_intensity_range[0] != self.bg_intensity_range[1]:
             return False
         for i, m in enumerate(self.mlps):
@@ -507,7 +542,7 @@ class MipNeRF360(nn.Module):
         rays_d = batch["rays_d"].contiguous().float()
         viewdirs = batch["viewdirs"].contiguous().float()
         radii = batch["radii"].reshape(-1).contiguous().float()
-        time = batch["times"][0:1]
+        time = self._host_time(batch["times"][0:1])
         lo = 0.0 if self.near_anneal_rate is None else max(min(1 - train_frac / self.near_anneal_rate, 1), 0)
         anneal = (self.anneal_slope * train_frac) / ((self.anneal_slope - 1) * train_frac + 1) if self.anneal_slope > 0 else 1.0
         keep = []                                  # tensors the config points into
@@ -638,8 +673,13 @@ class LitMipNeRF360(_LitBase):
             with torch.cuda.graph(g, capture_error_mode="thread_local"):     # other threads (NCCL watchdog) may call CUDA
                 rgb = m.render_fused(static, frac, False, self.near, self.far, workspace=ws)
             _lib.LAUNCHES -= per_replay                      # the capture pass launched nothing
-            ent = cache[key] = (g, static, rgb, per_replay, ws)
-        g, static, rgb, per_replay, _ = ent
+            # The graph bakes in raw device pointers: packed weights / parameter blocks of each level's FusedMLP, its folded
+            # view-term tensors, the quantile tables.  The entry owns references to all of them, so a later switch to
+            # another state embedding (or a parameter update) can never free memory this graph still reads.
+            holds = [x._fused(st, x._versions()) for x, st in zip(m.mlps, states)]
+            holds += [m._u_cache[k] for k in list(m._u_cache) if isinstance(k, tuple)]
+            ent = cache[key] = (g, static, rgb, per_replay, ws, holds)
+        g, static, rgb, per_replay = ent[:4]
         for k in self._RAY_KEYS:
             static[k].copy_(hb[k], non_blocking=True)
         g.replay()
@@ -740,7 +780,7 @@ class LitMipNeRF360(_LitBase):
             g_out = ((rgb - target) * (self.data_loss_mult / (torch.sqrt(mse + self.charb_padding ** 2) * rgb.numel()))).contiguous()
             c, w = hist[-1]["sdist"].contiguous(), hist[-1]["weights"].contiguous()
             rays_d = batch["rays_d"].contiguous().float()
-            bg = m.bg_intensity_range[0]
+            bg = m._background(randomized)
             grads = []
             for lvl, h in enumerate(hist):
                 last = lvl == len(hist) - 1

@@ -382,6 +382,8 @@ def composite_nerf(raw, mask, z, dirs, bgcolor=None, activate=True):
 
 def composite_s3(bkg_rgb, bkg_density, bkg_tdist, human_rgb, human_density, pts_mask, newsmpl_pts, M,
                  rays_o, rays_d, thre_fg=5e-3, want_human_w=True):
+    """S3 model.py:1524-1596.  ``human_w`` [n,Sh]: composite weights of the human samples in depth order (the
+    reference's ``weights_onlyfg[human_pts_idx].reshape(...)``), rows of background rays zero."""
     for t, nm in ((bkg_rgb, "bkg_rgb"), (bkg_density, "bkg_density"), (bkg_tdist, "bkg_tdist"),
                   (human_rgb, "human_rgb"), (human_density, "human_density"), (pts_mask, "pts_mask"),
                   (newsmpl_pts, "newsmpl_pts"), (rays_o, "rays_o"), (rays_d, "rays_d")):
@@ -392,9 +394,10 @@ def composite_s3(bkg_rgb, bkg_density, bkg_tdist, human_rgb, human_density, pts_
     rgb = torch.empty(n, 3, device=dev, dtype=_F32)
     is_fg = torch.empty(n, device=dev, dtype=torch.uint8)
     hw = torch.empty(n, sh, device=dev, dtype=_F32) if want_human_w else None
+    flag = torch.empty(1, device=dev, dtype=torch.int32)       # scratch of the batch-wide small-direction test
     _lib.call_unless_empty(n, "hos_composite_s3", _p(bkg_rgb), _p(bkg_density), _p(bkg_tdist), _p(human_rgb), _p(human_density),
               _p(pts_mask), _p(newsmpl_pts), _host3(M, 16), _p(rays_o), _p(rays_d), n, sb, sh, thre_fg,
-              _p(rgb), _p(is_fg), _p(hw), _stream())
+              _p(rgb), _p(is_fg), _p(hw), _p(flag), _stream())
     return rgb, is_fg.bool(), hw
 
 

@@ -358,6 +358,25 @@ def test_composite_s3_golden(golden):
     assert float(hw.cpu()[~g["idx_fg"]].abs().max()) == 0.0
 
 
+def test_composite_s3_nonmonotone_human_depth_vs_oracle(golden):
+    """The human weights come back in DEPTH order (S3 model.py:1577,1588), which differs from sample order as soon as
+    the projected human depths are not monotone: shuffle the human samples of every ray and compare with the oracle."""
+    g = golden("s3_composite")
+    gen = torch.Generator().manual_seed(5)
+    n, sh = g["human_density"].shape
+    perm = torch.stack([torch.randperm(sh, generator=gen) for _ in range(n)])
+    take = lambda x: torch.gather(x, 1, perm.view(n, sh, *([1] * (x.dim() - 2))).expand_as(x))
+    h_rgb, h_den, mask, pts = take(g["human_rgb"]), take(g["human_density"]), take(g["pts_mask"]), take(g["newsmpl_pts"])
+    ref_rgb, ref_fg, ref_hw, _ = HR.composite_s3(g["bkg_rgb"], g["bkg_density"], g["bkg_tdist"], h_rgb, h_den, mask, pts, g["M"],
+                                                 g["rays_o_bkg"], g["rays_d_bkg"])
+    rgb, is_fg, hw = ops.composite_s3(cu(g["bkg_rgb"]), cu(g["bkg_density"]), cu(g["bkg_tdist"]), cu(h_rgb), cu(h_den),
+                                      cu(mask), cu(pts), g["M"], cu(g["rays_o_bkg"]), cu(g["rays_d_bkg"]))
+    assert torch.equal(is_fg.cpu(), ref_fg)
+    assert rel_err(rgb.cpu(), ref_rgb) < TOL
+    assert rel_err(rgb.cpu(), g["rgb"]) < TOL                    # the composite itself does not depend on the sample order
+    assert rel_err(hw.cpu()[ref_fg], ref_hw) < TOL
+
+
 # ----------------------------------------------------------------------------- training path: composite backward
 @pytest.mark.parametrize("opaque,with_rgb,S", [(True, True, 32), (False, True, 77), (True, False, 128), (False, False, 64)])
 def test_composite_mip360_backward_vs_autograd(opaque, with_rgb, S):

@@ -195,6 +195,32 @@ def test_render_rays_stream_matches_per_batch_calls():
         list(LitMipNeRF360("/nonexistent").render_rays_stream(iter(host)))      # module on the CPU: no CPU path
 
 
+def test_render_rays_stream_alternating_states():
+    """A captured graph points into the packed weights of ONE state embedding.  Streaming frames whose times select
+    state A, B, A, B, A (and a second pass over the same sequence) must replay every graph against live memory and
+    reproduce the plain per-batch calls."""
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "transitions_times.json"), "w") as f:
+            json.dump({"f0": {"time": 0.25}, "f1": {"time": 0.6}}, f)
+        lit = LitMipNeRF360(td, opaque_background=True, precision="fp16", num_levels=2, num_prop_samples=64,
+                            num_nerf_samples=32, nerf_netwidth=256)
+    synth.fill_params_(lit.model, 0)
+    lit = lit.to(DEV)
+    times = [0.1, 0.4, 0.1, 0.9, 0.4, 0.1]
+    host = []
+    for i, t in enumerate(times):
+        hb = synth.make_bkg_batch(256, seed=40 + (i % 2))
+        hb["times"] = torch.full_like(hb["times"], t)
+        host.append({k: v.contiguous().pin_memory() for k, v in hb.items()})
+    want = [lit.render_rays({k: v.to(DEV) for k, v in hb.items()}, 0)["rgb"].cpu() for hb in host]
+    assert not torch.equal(want[0], want[1])             # the states really differ
+    for _ in range(2):
+        got = [o.clone() for o in lit.render_rays_stream(iter(host))]
+        torch.empty(64 << 20, dtype=torch.uint8, device=DEV).fill_(0xFF)     # scribble over anything that was freed
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("levels,randomized", [(2, False), (3, False), (3, True)])
 def test_render_fused_one_call_matches_level_loop(levels, randomized):
     """hos_render_bkg (the whole level loop behind one C call) returns bit-for-bit what MipNeRF360.forward computes
