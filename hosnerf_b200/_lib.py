@@ -43,6 +43,16 @@ class BkgConfig(C.Structure):     # hos_bkg_config
                 ("mlp_events", C.POINTER(C.c_void_p))]
 
 
+class GemmTmaDesc(C.Structure):      # hos_gemm_tma_desc
+    _fields_ = [("mode", c_i), ("rows", c_l),
+                ("a0_hi", c_f), ("a0_lo", c_f), ("k0", c_i), ("lda0", c_i),
+                ("a1_hi", c_f), ("a1_lo", c_f), ("k1", c_i), ("lda1", c_i),
+                ("w0_hi", c_f), ("w0_lo", c_f), ("ldw0", c_i),
+                ("w1_hi", c_f), ("w1_lo", c_f), ("ldw1", c_i),
+                ("n", c_i), ("bias", c_f), ("relu", c_i), ("mask", c_f), ("ld_mask", c_i),
+                ("y_hi", c_f), ("y_lo", c_f), ("ldy", c_i), ("y_f32", c_f), ("ldy32", c_i)]
+
+
 # name -> (restype, argtypes); mirrors include/hosnerf_b200.h one to one
 SIGNATURES = {
     "hos_last_error": (C.c_char_p, []),
@@ -79,6 +89,10 @@ SIGNATURES = {
     "hos_gemm_set_weight": (c_i, [C.c_void_p, c_f, c_f, c_f]),
     "hos_gemm_set_head": (c_i, [C.c_void_p, c_i, c_f, c_f, c_f]),
     "hos_gemm_forward": (c_i, [C.c_void_p, c_f, c_f, c_l, c_i, c_f, c_f, c_i, c_fl, c_f]),
+    "hos_gemm_tma": (c_i, [C.POINTER(GemmTmaDesc), c_f]),
+    "hos_wgrad_tma": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_l, c_f, c_i, c_i, c_f]),
+    "hos_colsum_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_i, c_f, c_i, c_f]),
+    "hos_head_dgrad": (c_i, [c_f, c_i, c_f, c_i, c_f, c_i, c_f, c_i, c_l, c_i, c_f, c_i, c_f]),
     "hos_rays_from_krt": (c_i, [c_i, c_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), c_i, c_i,
                                 c_f, c_f, c_f, c_f, c_f]),
     "hos_rays_intersect_bbox": (c_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), c_f, c_f, c_l, c_i, c_f, c_f, c_f, c_f]),

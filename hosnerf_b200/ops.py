@@ -455,3 +455,109 @@ def reduce_scaled(x, scale, y=None):
     out = torch.zeros((), device=x.device, dtype=_F32)
     _lib.call_unless_empty(x.numel(), "hos_reduce_scaled", _p(x), _p(y), x.numel(), float(scale), _p(out), _stream())
     return out
+
+
+# ----------------------------------------------------------------------------- row-major fp16 layer GEMMs (csrc/gemm_tc.cu)
+_F16 = torch.float16
+
+
+def _chk16(t, name):
+    """fp16 CUDA matrix, unit column stride, 16-byte aligned base and pitch (what a TMA tensor map needs)."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != _F16 or t.dim() != 2:
+        raise RuntimeError(f"hosnerf_b200: `{name}` must be a 2-D CUDA fp16 tensor")
+    if t.stride(1) != 1 or (t.stride(0) * 2) % 16 != 0 or t.data_ptr() % 16 != 0:
+        raise RuntimeError(f"hosnerf_b200: `{name}` needs unit column stride and a 16-byte aligned base / pitch (stride {t.stride()})")
+    return t
+
+
+def split16(x):
+    """fp32 -> (hi, lo) fp16 planes with hi + lo = x to ~22 bits."""
+    hi = x.to(_F16)
+    return hi, (x - hi.float()).to(_F16)
+
+
+def _pair(t):
+    return t if isinstance(t, (tuple, list)) else (t, None)
+
+
+def gemm_tma(a0, w0, n, a1=None, w1=None, bias=None, relu=False, mask=None, mode=0, out16=True, out_lo=False, out32=False,
+             y16=None):
+    """mode 0: Y = act([A0 | A1] [W0 | W1]^T + bias) with W* [n, k*];  mode 1: Y = (A0 W0) .* (mask > 0) with W0 [k0, n].
+    Operands are fp16 matrices or (hi, lo) pairs of them (split precision: all operands must then be pairs).
+    Returns (y_hi or None, y_lo or None, y_f32 or None)."""
+    (a0h, a0l), (w0h, w0l) = _pair(a0), _pair(w0)
+    (a1h, a1l), (w1h, w1l) = _pair(a1), _pair(w1)
+    for t, nm in ((a0h, "a0"), (a0l, "a0_lo"), (w0h, "w0"), (w0l, "w0_lo"), (a1h, "a1"), (a1l, "a1_lo"), (w1h, "w1"),
+                  (w1l, "w1_lo"), (mask, "mask")):
+        _chk16(t, nm)
+    _chk(bias, "bias")
+    rows, k0 = a0h.shape
+    k1 = 0 if a1h is None else a1h.shape[1]
+    dev = a0h.device
+    if mode == 0:
+        assert w0h.shape == (n, k0) and (w1h is None or w1h.shape == (n, k1)), (w0h.shape, n, k0, k1)
+    else:
+        assert w0h.shape[0] == k0 and w0h.shape[1] >= n and a1h is None, (w0h.shape, n, k0)
+    n_pad = (n + 7) // 8 * 8
+    if out16 and y16 is None:
+        y16 = torch.empty(rows, n_pad, device=dev, dtype=_F16)
+    ylo = torch.empty(rows, n_pad, device=dev, dtype=_F16) if (out16 and out_lo) else None
+    y32 = torch.empty(rows, n_pad, device=dev, dtype=_F32) if out32 else None
+    d = _lib.GemmTmaDesc()
+    d.mode, d.rows = mode, rows
+    d.a0_hi, d.a0_lo, d.k0, d.lda0 = _p(a0h), _p(a0l), k0, a0h.stride(0)
+    if a1h is not None:
+        d.a1_hi, d.a1_lo, d.k1, d.lda1 = _p(a1h), _p(a1l), k1, a1h.stride(0)
+        d.w1_hi, d.w1_lo, d.ldw1 = _p(w1h), _p(w1l), w1h.stride(0)
+    d.w0_hi, d.w0_lo, d.ldw0 = _p(w0h), _p(w0l), w0h.stride(0)
+    d.n, d.bias, d.relu = n_pad, _p(bias), int(relu)
+    if bias is not None:
+        assert bias.numel() >= n_pad or n_pad == n, "bias shorter than the padded width"
+    if mask is not None:
+        d.mask, d.ld_mask = _p(mask), mask.stride(0)
+    if y16 is not None:
+        d.y_hi, d.y_lo, d.ldy = _p(y16), _p(ylo), y16.stride(0)
+    if y32 is not None:
+        d.y_f32, d.ldy32 = _p(y32), y32.stride(0)
+    _lib.call_unless_empty(rows, "hos_gemm_tma", C.byref(d), _stream())
+    return y16, ylo, y32
+
+
+def wgrad_tma(p, q, out, transpose_out=False):
+    """out[i, j] += sum_rows p[row, i] q[row, j]  (out fp32 [m, nq], or [nq, m] with transpose_out; any column-sliced view)."""
+    _chk16(p, "p"), _chk16(q, "q")
+    assert out.dtype == _F32 and out.is_cuda and out.stride(1) == 1
+    rows, m = p.shape
+    nq = q.shape[1]
+    assert q.shape[0] == rows and tuple(out.shape) == ((nq, m) if transpose_out else (m, nq)), (p.shape, q.shape, out.shape)
+    for i0 in range(0, m, 256):
+        for j0 in range(0, nq, 512):
+            mi, nj = min(256, m - i0), min(512, nq - j0)
+            o = out[j0:j0 + nj, i0:i0 + mi] if transpose_out else out[i0:i0 + mi, j0:j0 + nj]
+            _lib.call_unless_empty(rows, "hos_wgrad_tma", p[:, i0:].data_ptr(), mi, p.stride(0), q[:, j0:].data_ptr(), nj,
+                                   q.stride(0), rows, o.data_ptr(), out.stride(0), int(transpose_out), _stream())
+    return out
+
+
+def colsum_f16(x, out, g=None):
+    """out[h, c] += sum_rows g[row, h] x[row, c]  (g None: out[c] += column sums)."""
+    _chk16(x, "x"), _chk(g, "g")
+    rows, n = x.shape
+    hn = 0 if g is None else g.shape[1]
+    assert out.dtype == _F32 and out.is_cuda and (n % 2) == 0
+    ld_out = out.stride(0) if out.dim() == 2 else n
+    _lib.call_unless_empty(rows, "hos_colsum_f16", _p(x), rows, n, x.stride(0), _p(g), hn, out.data_ptr(), ld_out, _stream())
+    return out
+
+
+def head_dgrad(g, W, n, add=None, mask=None):
+    """fp16 Y[rows, n] = (g [rows, hn] @ W [hn, n] + add) .* (mask > 0)."""
+    _chk(g, "g"), _chk16(add, "add"), _chk16(mask, "mask")
+    assert W.dtype == _F32 and W.is_cuda and W.stride(1) == 1 and g.dim() == 2 and W.shape[0] == g.shape[1]
+    rows, hn = g.shape
+    y = torch.empty(rows, n, device=g.device, dtype=_F16)
+    _lib.call_unless_empty(rows, "hos_head_dgrad", _p(g), hn, W.data_ptr(), W.stride(0), _p(add), 0 if add is None else add.stride(0),
+                           _p(mask), 0 if mask is None else mask.stride(0), rows, n, _p(y), n, _stream())
+    return y
