@@ -49,8 +49,9 @@ class GemmTmaDesc(C.Structure):      # hos_gemm_tma_desc
                 ("a1_hi", c_f), ("a1_lo", c_f), ("k1", c_i), ("lda1", c_i),
                 ("w0_hi", c_f), ("w0_lo", c_f), ("ldw0", c_i),
                 ("w1_hi", c_f), ("w1_lo", c_f), ("ldw1", c_i),
-                ("n", c_i), ("bias", c_f), ("relu", c_i), ("mask", c_f), ("ld_mask", c_i),
-                ("y_hi", c_f), ("y_lo", c_f), ("ldy", c_i), ("y_f32", c_f), ("ldy32", c_i)]
+                ("n", c_i), ("bias", c_f), ("rowbias", c_f), ("rowbias_div", c_i), ("relu", c_i), ("mask", c_f), ("ld_mask", c_i),
+                ("y_hi", c_f), ("y_lo", c_f), ("ldy", c_i), ("y_f32", c_f), ("ldy32", c_i),
+                ("hn", c_i), ("head_w", c_f), ("head_b", c_f), ("head_post", c_i), ("head_shift", c_fl), ("head_out", c_f)]
 
 
 # name -> (restype, argtypes); mirrors include/hosnerf_b200.h one to one

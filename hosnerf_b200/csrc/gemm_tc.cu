@@ -37,7 +37,6 @@ constexpr int kG2EpiWarp0 = 4, kG2EpiWarps = 8, kG2AWarp0 = 12;
 constexpr int kG2BProducers = 3, kG2AProducers = 4;
 constexpr int kG2MaxStages = 6;
 constexpr int kG2Bars = 2 * kG2MaxStages + 4;
-constexpr int kG2MaxBias = 1024;
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -77,13 +76,26 @@ __device__ __forceinline__ void g2_wait(uint64_t* bar, uint32_t parity, int tag,
 #define G2_WAIT(ns, bar, par, tag, x, y) mbar_wait_guard<ns>(bar, par)
 #endif
 
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(smem_u32(src))
+               : "memory");
+}
+
 struct G2Args {
   __half* y_hi;
   __half* y_lo;
   float* y_f32;
   const float* bias;
+  const float* rowbias;
   const __half* mask;
+  const float* head_w;      // [hn][n] fp32
+  const float* head_b;      // [hn] or null
+  float* head_out;          // [rows][hn]
+  float head_shift;
+  int hn, head_post;
   int64_t rows;
+  int rowbias_div;
   int ldy, ldy32, ld_mask;
   int ntiles;
   int n;            // valid output columns
@@ -96,7 +108,7 @@ struct G2Args {
 };
 
 struct G2Maps {
-  CUtensorMap a0[2], a1[2], b0[2], b1[2];     // [hi, lo]
+  CUtensorMap a0[2], a1[2], b0[2], b1[2], y[2];     // [hi, lo]
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
@@ -108,8 +120,9 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
   const int stage_bytes = planes * (kXChunkBytes + b_bytes);   // [A_hi][A_lo][B_hi][B_lo]
   const int S = args.stages;
   unsigned char* sRing = smem;
-  float* sBias = reinterpret_cast<float*>(sRing + (size_t)S * stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kG2MaxBias);
+  unsigned char* sStage = sRing + (size_t)S * stage_bytes;  // [1 or 2 planes][16 KB] output staging for the TMA stores
+  float* s_headx = reinterpret_cast<float*>(sStage + (args.y_lo ? 2 : 1) * kXChunkBytes);     // [128][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_headx + kTileM * 4);
   uint64_t* bar_full = bars;                                // leader: A + B of both CTAs landed (2 tx arrivals + 2 relays); peer: its own two
   uint64_t* bar_empty = bar_full + kG2MaxStages;            // multicast commit: stage consumed
   uint64_t* bar_tfull = bar_empty + kG2MaxStages;           // [2] multicast commit: accumulator buffer complete
@@ -123,7 +136,6 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
   const int KB = args.kb0 + args.kb1;
   const int nblk = args.nblk;
 
-  for (int i = threadIdx.x; i < kG2MaxBias; i += kG2Threads) sBias[i] = (args.bias && i < args.n) ? args.bias[i] : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kG2MaxStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * kG2EpiWarps); }
@@ -253,39 +265,66 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
       }
     }
   } else if (warp >= kG2EpiWarp0 && warp < kG2EpiWarp0 + kG2EpiWarps) {
-    // ===================== epilogue (8 warps): bias, ReLU / mask, fp16 hi (+ lo) and / or fp32 row-major stores ==========
+    // ===================== epilogue (8 warps) =====================
+    // bias / per-ray bias / ReLU / mask on the fp32 accumulator; the fp16 result (hi plane, optionally the residual lo
+    // plane) is staged in shared memory in the swizzled box layout and leaves through TMA stores (one [128 x 64] box per
+    // plane and 64 output columns: full-line writes instead of 32 scattered 16-byte stores per warp instruction);
+    // optional fp32 copy and an fp32 head (<= 4 outputs, e.g. the density layer) straight from the registers.
     const int q = warp & 3;
     const int ch = (warp - kG2EpiWarp0) >> 2;
     const int r = q * 32 + lane;
+    const bool epi_leader = threadIdx.x == kG2EpiWarp0 * 32;
     const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
-    const uint32_t sbias_u32 = smem_u32(sBias);
+    const uint32_t st_row = smem_u32(sStage) + 128u * (uint32_t)r;
+    uint32_t st_off[4];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) st_off[gq] = st_row + ((uint32_t)((4 * ch + gq) ^ (r & 7)) << 4);
+    const bool has_head = args.hn > 0;
     uint32_t u = 0;
+    bool stage_busy = false;
     for (int g = cluster; g < n_groups; g += n_clusters) {
       const int tile = 2 * g + (int)rank;
       const int64_t row = (int64_t)tile * kTileM + r;
-      const bool row_ok = row < args.rows;
+      const bool row_ok = row < args.rows, tile_ok = tile < args.ntiles;
+      float hacc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int j = 0; j < nblk; ++j, ++u) {
         const uint32_t acc = tmem_base + (u & 1) * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
         G2_WAIT(20, &bar_tfull[u & 1], (u >> 1) & 1, 4, (int)u, 0);
         tc_fence_after();
         for (int c = 0; c < args.n_blk / 64; ++c) {
-          const int n0 = j * args.n_blk + c * 64 + ch * 32;           // first of this thread's 32 output columns
+          const int nc0 = j * args.n_blk + c * 64;                    // first column of this 64-column chunk
+          const int n0 = nc0 + ch * 32;                               // first of this thread's 32 output columns
           uint32_t v[32];
           tmem_ld32_nowait(acc + (uint32_t)(c * 64), v);
           tmem_wait_ld();
-          if (!row_ok || n0 >= args.n) continue;
+          if (nc0 >= args.n) continue;                                // uniform over the CTA: whole chunk beyond the matrix
+          const bool col_ok = n0 < args.n;
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bb = lds128(sbias_u32 + 4u * (uint32_t)(n0 & (kG2MaxBias - 1)) + 16u * i);
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x; f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z; f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (args.bias && col_ok) {
+            const float4* b4 = reinterpret_cast<const float4*>(args.bias + n0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (n0 + i * 4 >= args.n) break;
+              const float4 bb = __ldg(b4 + i);
+              f[4 * i + 0] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+            }
+          }
+          if (args.rowbias && row_ok && col_ok) {           // per-ray term (view-direction encoding), fp32
+            const float4* rb = reinterpret_cast<const float4*>(args.rowbias + (row / args.rowbias_div) * args.n + n0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (n0 + i * 4 >= args.n) break;
+              const float4 bb = __ldg(rb + i);
+              f[4 * i + 0] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+            }
           }
           if (args.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (args.mask) {                                  // dgrad through a ReLU: keep where the saved activation is positive
+          if (args.mask && row_ok && col_ok) {              // dgrad through a ReLU: keep where the saved activation is positive
             const uint4* mp = reinterpret_cast<const uint4*>(args.mask + row * args.ld_mask + n0);
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
@@ -301,11 +340,11 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
             }
           }
           if (args.y_hi) {
-            uint4* dh = reinterpret_cast<uint4*>(args.y_hi + row * args.ldy + n0);
-            uint4* dl = args.y_lo ? reinterpret_cast<uint4*>(args.y_lo + row * args.ldy + n0) : nullptr;
+            // the staging buffer is free once the previous chunk's TMA stores have read it
+            if (stage_busy && epi_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
-              if (n0 + gq * 8 >= args.n) break;
               uint32_t ph[4], pl[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -315,11 +354,19 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
                 const __half2 l2 = __floats2half2_rn(x0 - __low2float(h2), x1 - __high2float(h2));
                 pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
               }
-              dh[gq] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              if (dl) dl[gq] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              sts128(st_off[gq], ph[0], ph[1], ph[2], ph[3]);
+              if (args.y_lo) sts128(st_off[gq] + kXChunkBytes, pl[0], pl[1], pl[2], pl[3]);
             }
+            fence_proxy_async();                            // generic-proxy stores -> visible to the TMA engine
+            asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+            if (epi_leader && tile_ok) {
+              tma_store_2d(&maps.y[0], sStage, nc0, tile * kTileM);
+              if (args.y_lo) tma_store_2d(&maps.y[1], sStage + kXChunkBytes, nc0, tile * kTileM);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            stage_busy = true;
           }
-          if (args.y_f32) {
+          if (args.y_f32 && row_ok && col_ok) {
             float4* d32 = reinterpret_cast<float4*>(args.y_f32 + row * args.ldy32 + n0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -327,12 +374,55 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
               d32[i] = make_float4(f[4 * i + 0], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             }
           }
+          if (has_head && col_ok) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              if (h < args.hn) {
+                const float4* w4 = reinterpret_cast<const float4*>(args.head_w + (size_t)h * args.n + n0);
+                float a = hacc[h];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if (n0 + i * 4 >= args.n) break;
+                  const float4 w = __ldg(w4 + i);
+                  a = fmaf(f[4 * i + 0], w.x, a); a = fmaf(f[4 * i + 1], w.y, a);
+                  a = fmaf(f[4 * i + 2], w.z, a); a = fmaf(f[4 * i + 3], w.w, a);
+                }
+                hacc[h] = a;
+              }
+            }
+          }
         }
         tc_fence_before();          // TMEM loads ordered before the arrive
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(tempty0 + 8u * (u & 1));
       }
+      if (has_head) {                           // combine the two column halves of this tile's rows, then post-process
+        if (ch == 1) sts128(smem_u32(s_headx) + 16u * r, __float_as_uint(hacc[0]), __float_as_uint(hacc[1]), __float_as_uint(hacc[2]),
+                            __float_as_uint(hacc[3]));
+        asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+        if (ch == 0 && row_ok) {
+          const float4 o4 = lds128(smem_u32(s_headx) + 16u * r);
+          hacc[0] += o4.x; hacc[1] += o4.y; hacc[2] += o4.z; hacc[3] += o4.w;
+          float* o = args.head_out + row * args.hn;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            if (h >= args.hn) break;
+            float x = hacc[h] + (args.head_b ? __ldg(args.head_b + h) : 0.f);
+            if (args.head_post == 1) {
+              const float z = x + args.head_shift;
+              x = z > 20.f ? z : log1pf(expf(z));
+            } else if (args.head_post == 2) {
+              x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * args.head_shift) - args.head_shift;
+            } else if (args.head_post == 4) {
+              x = (h < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+            }
+            o[h] = x;
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+      }
     }
+    if (stage_busy && epi_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();
@@ -616,11 +706,16 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
   HOS_REQUIRE(d->k1 == 0 || (d->a1_hi && d->w1_hi), "hos_gemm_tma: second input needs A1 and W1");
   const bool split = d->a0_lo != nullptr;
   HOS_REQUIRE(!split || (d->w0_lo && (d->k1 == 0 || (d->a1_lo && d->w1_lo))), "hos_gemm_tma: split precision needs every lo plane");
-  HOS_REQUIRE(d->y_hi || d->y_f32, "hos_gemm_tma: nothing to write");
+  HOS_REQUIRE(d->y_hi || d->y_f32 || d->hn > 0, "hos_gemm_tma: nothing to write");
+  HOS_REQUIRE(!d->y_lo || d->y_hi, "hos_gemm_tma: y_lo needs y_hi");
   HOS_REQUIRE(!d->y_hi || ((d->ldy % 8) == 0 && (reinterpret_cast<uintptr_t>(d->y_hi) & 15) == 0), "hos_gemm_tma: y pitch / alignment");
   HOS_REQUIRE(!d->y_f32 || ((d->ldy32 % 4) == 0 && (reinterpret_cast<uintptr_t>(d->y_f32) & 15) == 0), "hos_gemm_tma: y_f32 pitch / alignment");
   HOS_REQUIRE(!d->mask || ((d->ld_mask % 8) == 0 && (reinterpret_cast<uintptr_t>(d->mask) & 15) == 0), "hos_gemm_tma: mask pitch / alignment");
-  HOS_REQUIRE(!d->bias || d->n <= kG2MaxBias, "hos_gemm_tma: bias supports n <= %d", kG2MaxBias);
+  HOS_REQUIRE(!d->rowbias || ((d->n % 4) == 0 && (reinterpret_cast<uintptr_t>(d->rowbias) & 15) == 0), "hos_gemm_tma: rowbias alignment");
+  HOS_REQUIRE(!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "hos_gemm_tma: bias must be 16-byte aligned");
+  HOS_REQUIRE(d->hn >= 0 && d->hn <= 4 && (d->hn == 0 || (d->head_w && d->head_out && (d->n % 4) == 0 &&
+                                                        (reinterpret_cast<uintptr_t>(d->head_w) & 15) == 0)),
+              "hos_gemm_tma: head needs hn <= 4, head_w [hn, n] (16-byte aligned) and head_out");
   if (d->rows == 0) return HOS_OK;
   G2Args a;
   memset(&a, 0, sizeof(a));
@@ -628,6 +723,9 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
   memset(&maps, 0, sizeof(maps));
   a.y_hi = (__half*)d->y_hi; a.y_lo = (__half*)d->y_lo; a.y_f32 = d->y_f32;
   a.bias = d->bias; a.mask = (const __half*)d->mask;
+  a.rowbias = d->rowbias; a.rowbias_div = d->rowbias_div < 1 ? 1 : d->rowbias_div;
+  a.head_w = d->head_w; a.head_b = d->head_b; a.head_out = d->head_out; a.head_shift = d->head_shift;
+  a.hn = d->hn; a.head_post = d->head_post;
   a.rows = d->rows; a.ldy = d->ldy; a.ldy32 = d->ldy32; a.ld_mask = d->ld_mask;
   a.ntiles = (int)((d->rows + kTileM - 1) / kTileM);
   a.n = d->n;
@@ -638,7 +736,7 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
   a.relu = d->relu; a.split = split; a.b_mn = d->mode == 1;
   const int planes = split ? 2 : 1;
   const int stage_bytes = planes * (kXChunkBytes + a.n_blk * 64);
-  const size_t fixed = 1024 + kG2MaxBias * 4 + kG2Bars * 8 + 64;
+  const size_t fixed = 1024 + (size_t)(d->y_lo ? 2 : 1) * kXChunkBytes + kTileM * 4 * sizeof(float) + kG2Bars * 8 + 64;
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kG2MaxStages) stages = kG2MaxStages;
   { const char* e = getenv("HOS_G2_STAGES"); if (e) stages = atoi(e); }
@@ -663,6 +761,10 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
       else rc = make_map(&maps.b1[pl], w1, d->k1, d->n, d->ldw1, 64);
       if (rc != HOS_OK) return rc;
     }
+  }
+  if (d->y_hi) {
+    if ((rc = make_map(&maps.y[0], d->y_hi, d->rows, d->n, d->ldy, kTileM)) != HOS_OK) return rc;
+    if (d->y_lo && (rc = make_map(&maps.y[1], d->y_lo, d->rows, d->n, d->ldy, kTileM)) != HOS_OK) return rc;
   }
   static thread_local int attr_dev = -1;
   int dev = 0;

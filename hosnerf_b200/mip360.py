@@ -14,6 +14,10 @@ Two precision modes (``precision=`` keyword / ``set_precision``):
                  "1e-4 rel" parity gate against the oracle.
   * ``"fp16"`` - IPE features + MLP on the tcgen05 tensor cores (fp16 operands, fp32
                  accumulate, activations never leave the SM); widths <= 256.
+  * ``"fp16x3"`` - split precision on the tensor cores: every fp32 operand is carried as an
+                 fp16 hi + lo pair and each layer runs as three tcgen05 passes (hi*hi + lo*hi +
+                 hi*lo, fp32 accumulate; ``hos_gemm_tma``), features from the accurate fp32
+                 encoder.  Meets the same 1e-4 gate as ``"fp32"`` at tensor-core speed.
 Sampler and composite are identical (fp32) in both modes.
 
 Not in this round: autograd (the kernels are forward-only; ``training_step`` raises).
@@ -45,6 +49,7 @@ except Exception:  # pragma: no cover - gin is absent in the build image
 
 EPS = 1.1920929e-07
 _DEFAULT_PRECISION = "fp32"
+PRECISIONS = ("fp32", "fp16", "fp16x3")
 # fp16 mode: generate the IPE features inside the tcgen05 MLP kernel (False: materialise them in HBM
 # with hos_ipe_features first - kept for A/B measurements and as the accurate-sin/cos variant)
 FUSE_IPE = os.environ.get("HOSNERF_UNFUSED_IPE", "0") != "1"
@@ -53,7 +58,7 @@ MERGE_BOTTLENECK = os.environ.get("HOSNERF_KEEP_BOTTLENECK", "0") != "1"
 
 def set_precision(p: str):
     global _DEFAULT_PRECISION
-    assert p in ("fp32", "fp16")
+    assert p in PRECISIONS
     _DEFAULT_PRECISION = p
 
 
@@ -286,6 +291,29 @@ class MipNeRF360MLP(nn.Module):
         slots[state_idx] = (ver, out)
         return out
 
+    def _x3(self, state_idx: int, _ver=None):
+        """Split-precision operands of every layer: (hi, lo) fp16 pairs of the folded fp32 weights (``precision="fp16x3"``)."""
+        ver = _ver if _ver is not None else self._versions()
+        slots, hit = self._slot("x3", state_idx, ver)
+        if hit is not None:
+            return hit
+        f = self._folded(state_idx, ver)
+        F, nw = self.ipe_size, self.netwidth
+        if nw % 8 != 0:
+            raise NotImplementedError("hosnerf_b200: fp16x3 mode needs netwidth % 8 == 0")
+        sp = lambda W: tuple(t.contiguous() for t in ops.split16(W.contiguous()))
+        out = {"layers": []}
+        for i, (W, b, skip) in enumerate(f["layers"]):
+            if skip:          # _folded orders the skip layer's columns [h | x]
+                out["layers"].append((sp(W[:, :nw]), sp(W[:, nw:nw + F]), b))
+            else:
+                out["layers"].append((sp(W), None, b))
+        if not self.disable_rgb:
+            out["bottleneck"] = (sp(f["bottleneck"][0]), f["bottleneck"][1])
+            out["views"] = sp(f["views"][2])
+        slots[state_idx] = (ver, out)
+        return out
+
     # ------------------------------------------------------------------ evaluation
     def eval_samples(self, tdist, rays_o, rays_d, radii, viewdirs, time, precision: str):
         """tdist [N,S+1] -> density [N,S], rgb [N,S,3] (zeros for proposal MLPs).  Covers
@@ -295,6 +323,33 @@ class MipNeRF360MLP(nn.Module):
         ver = self._versions()                  # one pass over the parameters per call (the caches below all key on it)
         f = self._folded(st, ver)
         basis = self.pos_basis_t
+        if precision == "fp16x3":
+            x3 = self._x3(st, ver)
+            rows = n * s
+            fs = ops.ipe_features(tdist, rays_o, rays_d, radii, basis, self.min_deg_point, self.max_deg_point, "split")
+            feat = (fs[0], fs[1])
+            x, dens = feat, None
+            nl = len(x3["layers"])
+            for i, (Wh, Wx, b) in enumerate(x3["layers"]):
+                last = i == nl - 1
+                kw = dict(bias=b, relu=True, out_lo=True, out16=not (last and self.disable_rgb))
+                if last:                    # density layer from the un-rounded fp32 accumulator, same pass
+                    kw["head"] = (f["density"][0], f["density"][1], 1, float(self.density_bias))
+                if Wx is not None:
+                    kw.update(a1=feat, w1=Wx)
+                res = ops.gemm_tma(x, Wh, self.netwidth, **kw)
+                x = (res[0], res[1])
+                if last:
+                    dens = res[3]
+            density = dens.view(n, s)
+            if self.disable_rgb:
+                return density, torch.zeros(n, s, 3, device=tdist.device)
+            bh, bl, _ = ops.gemm_tma(x, x3["bottleneck"][0], self.bottleneck_width, bias=x3["bottleneck"][1], out_lo=True)
+            de = ops.pos_enc(viewdirs, 0, self.deg_view, True)
+            rowbias = ops.linear_f32(de, f["views"][3], f["views"][1])                # per-ray view term + bias, fp32
+            rgb = ops.gemm_tma((bh, bl), x3["views"], self.netwidth_condition, relu=True, rowbias=rowbias, rowbias_div=s,
+                               out16=False, head=(f["rgb"][0], f["rgb"][1], 2, float(self.rgb_padding)))[3].view(n, s, 3)
+            return density, rgb
         if precision == "fp16" and self.netwidth > 256:
             wide = self._wide(st, ver)
             rows = n * s

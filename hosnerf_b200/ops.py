@@ -105,6 +105,8 @@ def ipe_features(tdist, rays_o, rays_d, radii, basis, min_deg=0, max_deg=12, out
         feat, ld, code = torch.empty(n * s, width, device=dev, dtype=_F32), width, 0
     elif out == "fp16":
         feat, ld, code = torch.empty(n * s, width, device=dev, dtype=torch.float16), width, 1
+    elif out == "split":      # [2, rows, width] fp16: hi plane, residual plane
+        feat, ld, code = torch.empty(2, n * s, width, device=dev, dtype=torch.float16), width, 3
     elif out == "tiled":
         feat, ld, code = torch.empty(tiled_bytes(n * s, width), device=dev, dtype=torch.uint8), 0, 2
     else:
@@ -483,10 +485,11 @@ def _pair(t):
 
 
 def gemm_tma(a0, w0, n, a1=None, w1=None, bias=None, relu=False, mask=None, mode=0, out16=True, out_lo=False, out32=False,
-             y16=None):
+             y16=None, rowbias=None, rowbias_div=1, head=None):
     """mode 0: Y = act([A0 | A1] [W0 | W1]^T + bias) with W* [n, k*];  mode 1: Y = (A0 W0) .* (mask > 0) with W0 [k0, n].
     Operands are fp16 matrices or (hi, lo) pairs of them (split precision: all operands must then be pairs).
-    Returns (y_hi or None, y_lo or None, y_f32 or None)."""
+    ``head`` = (W [hn, n] fp32, b [hn] or None, post, shift): an fp32 head evaluated in the epilogue; its [rows, hn] result is
+    appended to the returned tuple.  Returns (y_hi or None, y_lo or None, y_f32 or None[, head_out])."""
     (a0h, a0l), (w0h, w0l) = _pair(a0), _pair(w0)
     (a1h, a1l), (w1h, w1l) = _pair(a1), _pair(w1)
     for t, nm in ((a0h, "a0"), (a0l, "a0_lo"), (w0h, "w0"), (w0l, "w0_lo"), (a1h, "a1"), (a1l, "a1_lo"), (w1h, "w1"),
@@ -517,12 +520,23 @@ def gemm_tma(a0, w0, n, a1=None, w1=None, bias=None, relu=False, mask=None, mode
         assert bias.numel() >= n_pad or n_pad == n, "bias shorter than the padded width"
     if mask is not None:
         d.mask, d.ld_mask = _p(mask), mask.stride(0)
+    if rowbias is not None:
+        _chk(rowbias, "rowbias")
+        assert rowbias.shape[-1] == n_pad and rowbias.shape[0] * rowbias_div >= rows
+        d.rowbias, d.rowbias_div = _p(rowbias), int(rowbias_div)
     if y16 is not None:
         d.y_hi, d.y_lo, d.ldy = _p(y16), _p(ylo), y16.stride(0)
     if y32 is not None:
         d.y_f32, d.ldy32 = _p(y32), y32.stride(0)
+    hout = None
+    if head is not None:
+        hw, hb, post, shift = head
+        _chk(hw, "head_w"), _chk(hb, "head_b")
+        assert hw.shape == (hw.shape[0], n_pad) and hw.shape[0] <= 4
+        hout = torch.empty(rows, hw.shape[0], device=dev, dtype=_F32)
+        d.hn, d.head_w, d.head_b, d.head_post, d.head_shift, d.head_out = hw.shape[0], _p(hw), _p(hb), int(post), float(shift), _p(hout)
     _lib.call_unless_empty(rows, "hos_gemm_tma", C.byref(d), _stream())
-    return y16, ylo, y32
+    return (y16, ylo, y32) if head is None else (y16, ylo, y32, hout)
 
 
 def wgrad_tma(p, q, out, transpose_out=False):
