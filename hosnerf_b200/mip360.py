@@ -309,8 +309,12 @@ class MipNeRF360MLP(nn.Module):
             else:
                 out["layers"].append((sp(W), None, b))
         if not self.disable_rgb:
-            out["bottleneck"] = (sp(f["bottleneck"][0]), f["bottleneck"][1])
-            out["views"] = sp(f["views"][2])
+            # bottleneck -> view layer is one linear map (no activation in between, S1 model.py:238-248): merged in fp64,
+            #   Wv[:, :bw] (Wb h + bb) = (Wv[:, :bw] Wb) h + Wv[:, :bw] bb,  which removes one 256-wide layer pass
+            Wb, bb = f["bottleneck"]
+            Wv1, bv = f["views"][2], f["views"][1]
+            out["views"] = sp((Wv1.double() @ Wb.double()).float())
+            out["view_bias"] = (bv.double() + Wv1.double() @ bb.double()).float().contiguous()
         slots[state_idx] = (ver, out)
         return out
 
@@ -344,10 +348,9 @@ class MipNeRF360MLP(nn.Module):
             density = dens.view(n, s)
             if self.disable_rgb:
                 return density, torch.zeros(n, s, 3, device=tdist.device)
-            bh, bl, _ = ops.gemm_tma(x, x3["bottleneck"][0], self.bottleneck_width, bias=x3["bottleneck"][1], out_lo=True)
             de = ops.pos_enc(viewdirs, 0, self.deg_view, True)
-            rowbias = ops.linear_f32(de, f["views"][3], f["views"][1])                # per-ray view term + bias, fp32
-            rgb = ops.gemm_tma((bh, bl), x3["views"], self.netwidth_condition, relu=True, rowbias=rowbias, rowbias_div=s,
+            rowbias = ops.linear_f32(de, f["views"][3], x3["view_bias"])              # per-ray view term + bias, fp32
+            rgb = ops.gemm_tma(x, x3["views"], self.netwidth_condition, relu=True, rowbias=rowbias, rowbias_div=s,
                                out16=False, head=(f["rgb"][0], f["rgb"][1], 2, float(self.rgb_padding)))[3].view(n, s, 3)
             return density, rgb
         if precision == "fp16" and self.netwidth > 256:

@@ -105,6 +105,8 @@ def ipe_features(tdist, rays_o, rays_d, radii, basis, min_deg=0, max_deg=12, out
         feat, ld, code = torch.empty(n * s, width, device=dev, dtype=_F32), width, 0
     elif out == "fp16":
         feat, ld, code = torch.empty(n * s, width, device=dev, dtype=torch.float16), width, 1
+    elif out == "f16op":      # fp16 row-major operand plane of the layer GEMMs (fast pairwise evaluation)
+        feat, ld, code = torch.empty(n * s, width, device=dev, dtype=torch.float16), width, 4
     elif out == "split":      # [2, rows, width] fp16: hi plane, residual plane
         feat, ld, code = torch.empty(2, n * s, width, device=dev, dtype=torch.float16), width, 3
     elif out == "tiled":

@@ -199,6 +199,23 @@ def test_ipe_vs_oracle_large():
     assert frac < 5e-3 and float(err.max()) < 5e-2
 
 
+def test_ipe_operand_planes_match_fp32_features():
+    """out_dtype 3 / 4 (pairwise sin / cos from one double-precision reduction, staged coalesced stores): hi + lo reproduces
+    the fp32 feature kernel to a few 1e-7 absolute, the single plane is its fp16 rounding."""
+    b = synth.make_bkg_batch(300, seed=4)
+    sd = torch.sort(torch.rand(300, 65, generator=torch.Generator().manual_seed(2)), -1).values
+    tdist = cu(R.s_to_t(sd, 0.1, 1e6))
+    args = (tdist, cu(b["rays_o"]), cu(b["rays_d"]), cu(b["radii"].reshape(-1)), cu(R.icosahedron_basis(2)), 0, 12)
+    f32 = ops.ipe_features(*args, "fp32")
+    sp = ops.ipe_features(*args, "split")
+    op = ops.ipe_features(*args, "f16op")
+    rec = sp[0].float() + sp[1].float()
+    print("ipe split: max |hi + lo - fp32|", float((rec - f32).abs().max()))
+    assert float((rec - f32).abs().max()) < 5e-7
+    assert torch.equal(op, sp[0])
+    assert float((op.float() - f32).abs().max()) < 6e-4          # fp16 rounding of values in [-1, 1]
+
+
 def test_ipe_tiled_matches_rowmajor():
     b = synth.make_bkg_batch(70, seed=4)
     sd = torch.sort(torch.rand(70, 33, generator=torch.Generator().manual_seed(2)), -1).values
