@@ -20,7 +20,8 @@ Two precision modes (``precision=`` keyword / ``set_precision``):
                  encoder.  Meets the same 1e-4 gate as ``"fp32"`` at tensor-core speed.
 Sampler and composite are identical (fp32) in both modes.
 
-Not in this round: autograd (the kernels are forward-only; ``training_step`` raises).
+Training: under autograd ``MipNeRF360.forward(is_train=True)`` is one ``train.RenderFn`` node (fp16 tensor-core layer
+GEMMs with saved activations; backward = composite backward + MLP dgrad / wgrad kernels), see train.py.
 """
 from __future__ import annotations
 
@@ -491,11 +492,42 @@ class MipNeRF360(nn.Module):
                                       "(the reference adds rand_like noise, S1 model.py:226-241)")
 
     def forward(self, batch, train_frac, randomized, is_train, near, far, rands=None):
+        """S1 model.py:331-461.  Under autograd with ``is_train`` the call is one ``train.RenderFn`` node: the weights of
+        every level and the final rgb carry a ``grad_fn`` whose backward runs the library's composite / MLP backward
+        kernels, so the reference's ``training_step`` works on this module unchanged."""
         rays_o = batch["rays_o"]
         if not rays_o.is_cuda:
             raise RuntimeError("hosnerf_b200.MipNeRF360: inputs must be CUDA tensors (no CPU fallback)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and is_train:
-            raise NotImplementedError("hosnerf_b200 kernels are forward-only in this round; call under torch.no_grad()")
+        if torch.is_grad_enabled() and is_train and any(p.requires_grad for p in self.parameters()):
+            return self._forward_autograd(batch, train_frac, randomized, near, far, rands)
+        return self._forward_impl(batch, train_frac, randomized, is_train, near, far, rands)
+
+    def _forward_autograd(self, batch, train_frac, randomized, near, far, rands):
+        from . import train
+        named = [(k, p) for k, p in self.named_parameters()]
+        names = tuple(k for k, _ in named)
+        res = train.RenderFn.apply(self, batch, train_frac, randomized, near, far, rands, names, *[p for _, p in named])
+        L = self.num_levels
+        ws = res[1:1 + L]
+        aux = res[1 + L:1 + 4 * L]
+        tds = res[1 + 4 * L:]
+        n = batch["rays_o"].shape[0]
+        bg = self._background(randomized)
+        history, renderings = [], []
+        for lvl in range(L):
+            last = lvl == L - 1
+            h = {"density": aux[3 * lvl], "rgb": aux[3 * lvl + 1], "sdist": aux[3 * lvl + 2], "weights": ws[lvl]}
+            if self.stage3:
+                h["tdist"] = tds[lvl]
+            elif last:
+                renderings.append({"rgb": res[0]})
+            else:
+                renderings.append({"rgb": (torch.clip(1 - ws[lvl].sum(-1, keepdim=True), min=0) * bg).expand(n, 3)})
+            history.append(h)
+        return renderings, history
+
+    def _forward_impl(self, batch, train_frac, randomized, is_train, near, far, rands=None, train_ctx=None):
+        rays_o = batch["rays_o"]
         precision = self.precision or _DEFAULT_PRECISION
         n = rays_o.shape[0]
         dev = rays_o.device
@@ -539,12 +571,20 @@ class MipNeRF360(nn.Module):
             sdist, tdist = ops.resample_level(sdist, weights, dilate, dilation, float(anneal),
                                               float(self.resample_padding), u_base, jitter, max_jitter,
                                               float(lo), float(hi), s_near, s_far)
-            density, rgb = self.mlps[lvl].eval_samples(tdist, rays_o, rays_d, radii, viewdirs, time, precision)
+            if train_ctx is not None:          # fp16 layer GEMMs with saved activations (train.mlp_forward_train)
+                from . import train
+                mlp = self.mlps[lvl]
+                density, rgb, c = train.mlp_forward_train(mlp, tdist, rays_o, rays_d, radii, viewdirs, mlp._state_index(time))
+                train_ctx.append(c)
+                if rgb is None:
+                    rgb = torch.zeros(n, s, 3, device=dev)
+            else:
+                density, rgb = self.mlps[lvl].eval_samples(tdist, rays_o, rays_d, radii, viewdirs, time, precision)
             last = not is_prop
             weights, rgb_out = ops.composite_mip360(density, tdist, rays_d, rgb if (last and not self.stage3) else None,
                                                     self.opaque_background, bg)
             res = {"density": density, "rgb": rgb, "sdist": sdist, "weights": weights}
-            if getattr(self, "_keep_tdist", False):
+            if getattr(self, "_keep_tdist", False) or train_ctx is not None:
                 res["_tdist"] = tdist          # for the backward of the composite (LitMipNeRF360.loss_gradients)
             if self.stage3:
                 res["tdist"] = tdist
@@ -856,9 +896,56 @@ class LitMipNeRF360(_LitBase):
                     grads.append({"density": gd})
         return {"loss": loss, "rgbloss": mse, "interlevel": inter, "distortion": dist, "ray_history": hist, "grads": grads}
 
+    def training_objective(self, batch, randomized: bool = True, rands=None):
+        """The stage-1 objective of S1 model.py:491-514 with an autograd graph: Charbonnier data term + interlevel +
+        distortion.  ``loss.backward()`` runs ``train.RenderFn.backward`` (composite / MLP backward kernels)."""
+        from . import train
+        rendered, hist = self.model(batch, self._frac(), randomized, True, self.near, self.far, rands=rands)
+        rgb = rendered[-1]["rgb"]
+        target = batch["target"].to(rgb.dtype)
+        mse = torch.mean((rgb - target) ** 2)
+        loss = torch.sqrt(mse + self.charb_padding ** 2) * self.data_loss_mult
+        c, w = hist[-1]["sdist"].detach(), hist[-1]["weights"].detach()
+        inter = 0.0
+        for lvl in hist[:-1]:
+            inter = inter + train.lossfun_outer_sum(c, w, lvl["sdist"].detach(), lvl["weights"]) / max(w.numel(), 1)
+        dist = train.lossfun_distortion(hist[-1]["sdist"].detach(), hist[-1]["weights"]).mean()
+        loss = loss + inter * self.interlevel_loss_mult + dist * self.distortion_loss_mult
+        return {"loss": loss, "rgbloss": mse.detach(), "interlevel": inter, "distortion": dist,
+                "psnr": -10.0 * torch.log(mse.detach()) / math.log(10.0)}
+
     def training_step(self, batch, batch_idx):
-        raise NotImplementedError("hosnerf_b200: backward kernels are not part of this round (forward/eval only); "
-                                  "loss_terms() evaluates the objective's forward value")
+        """S1 model.py:491-514."""
+        out = self.training_objective(batch, randomized=True)
+        if hasattr(self, "log") and getattr(self, "_trainer", None) is not None:
+            self.log("train/loss", out["loss"].item(), on_step=True, prog_bar=True)
+            self.log("train/psnr", out["psnr"].item(), on_step=True, prog_bar=True)
+        return out["loss"]
+
+    def lr_at(self, step: int, max_steps: int) -> float:
+        """Learning-rate schedule of S1 model.py:541-569: log-linear decay lr_init -> lr_final with a sine warm-up."""
+        if self.lr_delay_steps > 0:
+            delay = self.lr_delay_mult + (1 - self.lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / self.lr_delay_steps, 0), 1))
+        else:
+            delay = 1.0
+        t = min(max(step / max_steps, 0), 1)
+        return delay * math.exp(math.log(self.lr_init) * (1 - t) + math.log(self.lr_final) * t)
+
+    def optimizer_step(self, epoch=None, batch_idx=None, optimizer=None, optimizer_idx=None, optimizer_closure=None,
+                       on_tpu=None, using_native_amp=None, using_lbfgs=None, step=None, max_steps=None):
+        """S1 model.py:541-569 (``step`` / ``max_steps`` default to the Lightning trainer's / gin's values)."""
+        if step is None:
+            step = self.trainer.global_step
+        if max_steps is None:
+            try:
+                import gin  # type: ignore
+                max_steps = gin.query_parameter("run.max_steps")
+            except Exception:
+                max_steps = self.trainer.max_steps
+        lr = self.lr_at(step, max_steps)
+        for pg in optimizer.param_groups:
+            pg["lr"] = lr
+        optimizer.step(closure=optimizer_closure)
 
     def configure_optimizers(self):
         return torch.optim.Adam(params=self.parameters(), lr=self.lr_init, betas=(0.9, 0.999))

@@ -1,0 +1,265 @@
+"""Training path of the background branch: forward with saved activations and the hand-written backward of
+``MipNeRF360MLP`` (S1 model.py:212-259) on the tensor cores - what the reference gets from autograd when
+``training_step`` (S1 model.py:491-514) calls ``loss.backward()``.
+
+Every 256/1024-wide layer is one ``hos_gemm_tma`` launch over row-major fp16 activations (forward: bias + ReLU in the
+epilogue, density / rgb heads from the fp32 accumulator; data gradient: W consumed as an MN-major operand, ReLU mask in the
+epilogue) and one ``hos_wgrad_tma`` launch (reduction over the rows through MN-major descriptors, fp32 atomics); bias
+gradients and the <= 4-wide heads run on two small SIMT kernels.  Gradients travel in fp16 with a power-of-two loss scale
+chosen on the device (no host synchronisation) and are unscaled in fp32.
+
+The sample positions are constants of the backward pass (``stop_level_grad``, S1 model.py:405-406) and the Gaussians are
+detached by the reference itself (helper.py:57-60), so nothing flows into the sampler or the encoder: the chain is
+loss -> composite -> (density, rgb) -> MLP parameters (+ the state embedding, through the bias it is folded into).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+_F16 = torch.float16
+
+
+def _h(t):
+    return t.detach().to(_F16).contiguous()
+
+
+def mlp_forward_train(m, tdist, rays_o, rays_d, radii, viewdirs, state_idx: int):
+    """One MipNeRF360MLP on [N, S] intervals with everything the backward needs kept: returns (density [N,S], rgb [N,S,3]
+    or None, ctx)."""
+    n, s = tdist.shape[0], tdist.shape[1] - 1
+    rows = n * s
+    F, nw = m.ipe_size, m.netwidth
+    e = m.bkgd_stateembeds[state_idx].detach()
+    feat = ops.ipe_features(tdist, rays_o, rays_d, radii, m.pos_basis_t, m.min_deg_point, m.max_deg_point, "f16op")
+    hs, x = [], feat
+    dens = None
+    nl = len(m.pts_linear)
+    for i, lin in enumerate(m.pts_linear):
+        W, b = lin.weight.detach(), lin.bias.detach()
+        last = i == nl - 1
+        kw = dict(relu=True)
+        if last:
+            kw["head"] = (m.density_layer.weight.detach().contiguous(), m.density_layer.bias.detach().contiguous(), 1,
+                          float(m.density_bias))
+        if i == 0:
+            res = ops.gemm_tma(x, _h(W[:, :F]), nw, bias=(b + W[:, F:] @ e).contiguous(), **kw)
+        elif m._skip_inputs(i):
+            res = ops.gemm_tma(x, _h(W[:, :nw]), nw, a1=feat, w1=_h(W[:, nw:nw + F]), bias=(b + W[:, nw + F:] @ e).contiguous(), **kw)
+        else:
+            res = ops.gemm_tma(x, _h(W), nw, bias=b.contiguous(), **kw)
+        x = res[0]
+        hs.append(x)
+        if last:
+            dens = res[3]
+    ctx = {"m": m, "state": state_idx, "n": n, "s": s, "feat": feat, "hs": hs, "density": dens}
+    if m.disable_rgb:
+        return dens.view(n, s), None, ctx
+    bw = m.bottleneck_width
+    bott = ops.gemm_tma(x, _h(m.bottleneck_layer.weight), bw, bias=m.bottleneck_layer.bias.detach().contiguous())[0]
+    de = ops.pos_enc(viewdirs, 0, m.deg_view, True)
+    Wv, bv = m.views_linear[0].weight.detach(), m.views_linear[0].bias.detach()
+    rowterm = ops.linear_f32(de, Wv[:, bw:].contiguous(), bv.contiguous())
+    Wr = (m.rgb_layer.weight.detach() * m.rgb_premultiplier).contiguous()
+    br = (m.rgb_layer.bias.detach() * m.rgb_premultiplier + m.rgb_bias).contiguous()
+    v, _, _, rgb = ops.gemm_tma(bott, _h(Wv[:, :bw]), m.netwidth_condition, relu=True, rowbias=rowterm, rowbias_div=s,
+                                head=(Wr, br, 2, float(m.rgb_padding)))
+    ctx.update(bott=bott, de=de, v=v, rgb=rgb)
+    return dens.view(n, s), rgb.view(n, s, 3), ctx
+
+
+def _loss_scale(*gs):
+    """Power-of-two scale (device tensor) that lifts the largest upstream gradient to ~2^8: the fp16 gradient planes keep
+    ~3.5 decades below it before flushing and two decades of head-room above it."""
+    mx = torch.stack([g.detach().abs().max() for g in gs if g is not None]).max().clamp_min(1e-30)
+    return torch.exp2(torch.floor(8.0 - torch.log2(mx))).clamp(2.0 ** -20, 2.0 ** 40)
+
+
+def mlp_backward(ctx, g_density, g_rgb, grads: dict):
+    """Accumulate parameter gradients of one MLP into ``grads`` (name -> fp32 tensor shaped like the parameter), given
+    dL/ddensity [N,S] and dL/drgb [N,S,3] (or None for a proposal MLP)."""
+    m = ctx["m"]
+    rows = ctx["n"] * ctx["s"]
+    F, nw = m.ipe_size, m.netwidth
+    dev = g_density.device
+    feat, hs = ctx["feat"], ctx["hs"]
+    h_last = hs[-1]
+    e = m.bkgd_stateembeds[ctx["state"]].detach()
+
+    def acc(name, shape):
+        if name not in grads:
+            grads[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
+        return grads[name]
+
+    scale = _loss_scale(g_density, g_rgb)
+    inv = 1.0 / scale
+    # density = softplus(raw + bias): d/draw = sigmoid = 1 - exp(-density)
+    g_raw = (g_density.reshape(rows, 1) * (1.0 - torch.exp(-ctx["density"])) * scale).contiguous()
+    Wd = m.density_layer.weight.detach().contiguous()
+    # scaled gradient buffers of this MLP (unscaled into `grads` at the end)
+    sg = {}
+
+    def sacc(name, shape):
+        if name not in sg:
+            sg[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
+        return sg[name]
+
+    ops.colsum_f16(h_last, sacc("density_layer.weight", Wd.shape), g=g_raw)
+    sacc("density_layer.bias", (1,)).add_(g_raw.sum(0))
+    add = None
+    if g_rgb is not None and not m.disable_rgb:
+        bw, cw = m.bottleneck_width, m.netwidth_condition
+        pad = float(m.rgb_padding)
+        sgm = (ctx["rgb"] + pad) / (1.0 + 2.0 * pad)
+        g_pre = (g_rgb.reshape(rows, 3) * ((1.0 + 2.0 * pad) * scale) * sgm * (1.0 - sgm)).contiguous()     # wrt premult * lin + bias
+        Wr_eff = (m.rgb_layer.weight.detach() * m.rgb_premultiplier).contiguous()
+        v, bott, de = ctx["v"], ctx["bott"], ctx["de"]
+        gWr = torch.zeros(3, cw, device=dev)
+        ops.colsum_f16(v, gWr, g=g_pre)
+        sacc("rgb_layer.weight", (3, cw)).add_(gWr * m.rgb_premultiplier)
+        sacc("rgb_layer.bias", (3,)).add_(g_pre.sum(0) * m.rgb_premultiplier)
+        g_zv = ops.head_dgrad(g_pre, Wr_eff, cw, mask=v)                                    # [rows, cw] fp16, ReLU-masked
+        Wv = m.views_linear[0].weight.detach()
+        gWv = sacc("views_linear.0.weight", Wv.shape)
+        ops.wgrad_tma(bott, g_zv, gWv[:, :bw], transpose_out=True)
+        g_row = g_zv.view(ctx["n"], ctx["s"], cw).sum(1, dtype=torch.float32)               # per-ray term
+        gWv[:, bw:].add_(g_row.t() @ de)
+        sacc("views_linear.0.bias", (cw,)).add_(g_row.sum(0))
+        g_bott = ops.gemm_tma(g_zv, _h(Wv[:, :bw]), bw, mode=1)[0]                           # [rows, bw]
+        Wb = m.bottleneck_layer.weight.detach()
+        ops.wgrad_tma(g_bott, h_last, sacc("bottleneck_layer.weight", Wb.shape))
+        ops.colsum_f16(g_bott, sacc("bottleneck_layer.bias", (bw,)))
+        add = ops.gemm_tma(g_bott, _h(Wb), nw, mode=1)[0]                                    # d/dh_last through the bottleneck
+    g_z = ops.head_dgrad(g_raw, Wd, nw, add=add, mask=h_last)                                # + density head, ReLU mask of the last layer
+    g_e = sacc("bkgd_stateembeds.%d" % ctx["state"], e.shape)
+    for i in range(len(m.pts_linear) - 1, -1, -1):
+        lin = m.pts_linear[i]
+        W = lin.weight.detach()
+        gW = sacc(f"pts_linear.{i}.weight", W.shape)
+        gb = sacc(f"pts_linear.{i}.bias", (nw,))
+        ops.colsum_f16(g_z, gb)
+        if i == 0:
+            ops.wgrad_tma(g_z, feat, gW[:, :F])
+            emb0 = F
+        elif m._skip_inputs(i):
+            ops.wgrad_tma(g_z, hs[i - 1], gW[:, :nw])
+            ops.wgrad_tma(g_z, feat, gW[:, nw:nw + F])
+            emb0 = nw + F
+        else:
+            ops.wgrad_tma(g_z, hs[i - 1], gW)
+            emb0 = None
+        if emb0 is not None:        # the embedding rides in the bias: rank-1 weight gradient, and its own gradient
+            gW[:, emb0:].add_(torch.outer(gb, e))
+            g_e.add_(W[:, emb0:].t() @ gb)
+        if i > 0:
+            g_z = ops.gemm_tma(g_z, _h(W[:, :nw]), nw, mode=1, mask=hs[i - 1])[0]
+    for k, v_ in sg.items():
+        acc(k, v_.shape).add_(v_ * inv)
+    return grads
+
+
+class RenderFn(torch.autograd.Function):
+    """``MipNeRF360.forward`` as one autograd node: outputs the composited rgb of the final level and every level's weights
+    (what the stage-1 objective reads, S1 model.py:491-514, 609-625); the backward runs composite backward -> MLP backward on
+    the library's kernels and hands one gradient per parameter to autograd, so ``loss.backward()``, Lightning and any torch
+    optimiser work unchanged."""
+
+    @staticmethod
+    def forward(ctx, model, batch, train_frac, randomized, near, far, rands, names, *params):
+        saved = []
+        rend, hist = model._forward_impl(batch, train_frac, randomized, True, near, far, rands, train_ctx=saved)
+        ctx.model, ctx.saved, ctx.names = model, saved, names
+        ctx.rays_d = batch["rays_d"].contiguous().float()
+        ctx.bg = model._background(randomized)
+        ctx.levels = len(hist)
+        ctx.tdists = [h.pop("_tdist") for h in hist]
+        ctx.hist = hist
+        ctx.stage3 = model.stage3
+        L = len(hist)
+        aux = []
+        for h in hist:
+            aux += [h["density"], h["rgb"], h["sdist"]]
+        rgb_final = rend[-1]["rgb"] if not model.stage3 else torch.zeros(0, device=ctx.rays_d.device)
+        # stage 3 composites outside (together with the human samples): there the final level's per-sample density / rgb
+        # carry the gradient instead of the composited colour
+        nondiff = [a for i, a in enumerate(aux) if not (model.stage3 and i in (3 * (L - 1), 3 * (L - 1) + 1))] + ctx.tdists
+        if model.stage3:
+            nondiff.append(rgb_final)
+        ctx.mark_non_differentiable(*nondiff)
+        return tuple([rgb_final] + [h["weights"] for h in hist] + aux + ctx.tdists)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        m = ctx.model
+        L = ctx.levels
+        grads = {}
+        g_out, g_ws = gouts[0], gouts[1:1 + L]
+        g_dens_last = g_rgb_last = None
+        if ctx.stage3:
+            g_out = None
+            g_dens_last, g_rgb_last = gouts[1 + L + 3 * (L - 1)], gouts[1 + L + 3 * (L - 1) + 1]
+        for lvl in range(L):
+            h = ctx.hist[lvl]
+            last = lvl == L - 1
+            g_w = g_ws[lvl]
+            gd = gc = None
+            want_rgb = last and not ctx.stage3 and g_out is not None
+            if g_w is not None or want_rgb:
+                g_w = (g_w if g_w is not None else torch.zeros_like(h["weights"])).contiguous().float()
+                gd, gc = ops.composite_mip360_backward(h["density"].contiguous(), ctx.tdists[lvl], ctx.rays_d,
+                                                       h["rgb"].contiguous() if want_rgb else None, g_w,
+                                                       g_out.contiguous().float() if want_rgb else None, m.opaque_background, ctx.bg)
+            if last and ctx.stage3:
+                if g_dens_last is not None:
+                    gd = g_dens_last.contiguous().float() if gd is None else gd + g_dens_last
+                gc = None if g_rgb_last is None else g_rgb_last.contiguous().float()
+            if gd is None and gc is None:
+                continue
+            if gd is None:
+                gd = torch.zeros_like(h["density"])
+            sub = {}
+            mlp_backward(ctx.saved[lvl], gd.contiguous(), gc, sub)
+            for k, v in sub.items():
+                grads[f"mlps.{lvl}.{k}"] = v
+        ctx.saved = None
+        return (None,) * 8 + tuple(grads.get(nm) for nm in ctx.names)
+
+
+class _DistortionFn(torch.autograd.Function):
+    """helper.lossfun_distortion (S1 helper.py:122-128) per ray, gradient w.r.t. the weights only (positions are detached)."""
+
+    @staticmethod
+    def forward(ctx, t, w):
+        t, w = t.contiguous(), w.contiguous()
+        ctx.save_for_backward(t, w)
+        return ops.lossfun_distortion(t, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, w = ctx.saved_tensors
+        return None, ops.lossfun_distortion_backward(t, w, 1.0, g_ray=g.contiguous())
+
+
+class _OuterSumFn(torch.autograd.Function):
+    """sum(helper.lossfun_outer(t, w, t_env, w_env)) (S1 helper.py:92-120), gradient w.r.t. the envelope weights."""
+
+    @staticmethod
+    def forward(ctx, t, w, t_env, w_env):
+        t, w, t_env, w_env = t.contiguous(), w.contiguous(), t_env.contiguous(), w_env.contiguous()
+        ctx.save_for_backward(t, w, t_env, w_env)
+        _, rows = ops.lossfun_outer(t, w, t_env, w_env, want_rows=True)
+        return ops.reduce_scaled(rows, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        t, w, t_env, w_env = ctx.saved_tensors
+        return None, None, None, ops.lossfun_outer_backward(t, w, t_env, w_env, 1.0) * g
+
+
+def lossfun_distortion(t, w):
+    return _DistortionFn.apply(t, w)
+
+
+def lossfun_outer_sum(t, w, t_env, w_env):
+    return _OuterSumFn.apply(t, w, t_env, w_env)
