@@ -118,44 +118,195 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def cpu_reference_steps(n_rays, steps, warmup, threads):
-    """Time the oracle (reference algorithm, torch CPU fp32) on `n_rays` rays of the workload."""
+def cpu_reference_steps(n_rays, steps, warmup, threads, prefer_ref=True):
+    """Time the reference's own CPU implementation of the path on `n_rays` rays of the workload: the UNMODIFIED reference
+    modules from oracle/_ref (copied there by recipe, oracle/ref_loader.py) when present, else the oracle port.
+    Returns (seconds per step, kind)."""
     from hosnerf_b200 import MipNeRF360, synth
-    from oracle import mip360_ref as R
     torch.set_num_threads(threads)
-    net = MipNeRF360("/nonexistent", **MODEL_KW)
-    synth.fill_params_(net, 0)
-    sd = {k: v.detach() for k, v in net.state_dict().items()}
     batch = synth.make_bkg_batch(n_rays, seed=1)
+    kind = "port"
+    fwd = None
+    if prefer_ref:
+        try:
+            from oracle import ref_loader
+            if ref_loader.available():
+                _, M = ref_loader.load_s1()
+                ref = ref_loader.build_reference_net(M, nerf_netwidth=MODEL_KW["nerf_netwidth"], num_levels=MODEL_KW["num_levels"],
+                                                     num_prop_samples=S_PROP, num_nerf_samples=S_NERF, opaque_background=True)
+                synth.fill_params_(ref, 0)
+                fwd = lambda: ref(batch, 1.0, False, False, NEAR, FAR)
+                kind = "reference"
+        except Exception as e:          # fall back to the port, say why
+            print(f"[bench] reference modules unusable ({e!r}); timing the oracle port", file=sys.stderr)
+    if fwd is None:
+        from oracle import mip360_ref as R
+        net = MipNeRF360("/nonexistent", **MODEL_KW)
+        synth.fill_params_(net, 0)
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        fwd = lambda: R.mip360_forward(sd, batch, 1.0, False, NEAR, FAR, num_levels=2, num_prop_samples=S_PROP, num_nerf_samples=S_NERF)
     times = []
-    with torch.no_grad():
+    import warnings
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            R.mip360_forward(sd, batch, 1.0, False, NEAR, FAR, num_levels=2, num_prop_samples=S_PROP,
-                             num_nerf_samples=S_NERF)
+            fwd()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+    return sum(times) / len(times), kind
 
 
 def run_reference(args):
+    """Reference arm: LitMipNeRF360.render_rays's body (MipNeRF360.forward, eval mode) of the unmodified reference on the
+    host CPU, all cores, on the SAME 4096-ray batch shape as the product arm.  A step takes ~10 s, so the number of timed
+    steps is capped (stated in the line)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = 512
-    sec = cpu_reference_steps(n, args.steps, min(args.warmup, 1), threads)
+    n = N_RAYS
+    steps, warm = max(1, min(args.steps, 3)), 1
+    sec, kind = cpu_reference_steps(n, steps, warm, threads)
     value = n * SAMPLES_PER_RAY / sec
     line = {"impl": "reference", "metric": "ray_samples_per_s", "value": value, "unit": "ray-samples/s",
-            "rays_per_s": n / sec, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "rays_per_s": n / sec, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step": n, "samples_per_ray": SAMPLES_PER_RAY,
-                       "note": "bounded sample of the same workload (512 of 4096 rays per step)"},
-            "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} rays x {SAMPLES_PER_RAY} samples per step, {args.steps} steps, torch CPU fp32"},
+                       "note": f"full {n}-ray batch per step; {steps} timed step(s) after {warm} warm-up (a step is ~10 s of CPU work); "
+                               "one CPU process regardless of --gpus"},
+            "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": threads, "kind": kind,
+                             "sample": f"{n} rays x {SAMPLES_PER_RAY} samples per step, {steps} steps, torch CPU fp32, "
+                                       + ("unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port")},
             "e2e": {"value": value, "unit": "ray-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def parity_check(lit, dev, n=256):
+    """In-run parity record (outside every timed region): the mode being benchmarked against the CPU oracle on a
+    256-ray slice of the workload."""
+    from hosnerf_b200 import synth
+    from oracle import mip360_ref as R
+    b = synth.make_bkg_batch(n, seed=1)
+    sd = {k: v.detach().cpu() for k, v in lit.model.state_dict().items()}
+    with torch.no_grad():
+        ref, _ = R.mip360_forward(sd, b, 1.0, False, NEAR, FAR, num_levels=2, num_prop_samples=S_PROP, num_nerf_samples=S_NERF)
+        out = lit.render_rays({k: v.to(dev) for k, v in b.items()}, 0)["rgb"].cpu()
+    ref = ref[-1]["rgb"]
+    scale = ref.double().abs().clamp(min=0.1 * float(ref.abs().max()))
+    return {"mode": lit.model.precision, "rays": n, "max_abs_rgb": float((out - ref).abs().max()),
+            "max_rel_rgb": float(((out.double() - ref.double()).abs() / scale).max()),
+            "against": "CPU oracle (oracle/mip360_ref.py, golden-pinned to the reference), same rays and weights"}
+
+
+def time_steps(fn, K, W, flush=None):
+    """Device time of K calls of fn (CUDA events on the current stream, summed), after W warm-ups."""
+    for _ in range(W):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        if flush is not None:
+            flush.zero_()
+        ev[i][0].record()
+        fn()
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev)
+
+
+def accurate_arm(dev, resident, flush, K):
+    """The split-precision tensor-core mode (fp16x3) on the same workload: throughput + its own parity record."""
+    from hosnerf_b200 import LitMipNeRF360, synth
+    lit = LitMipNeRF360("/nonexistent", precision="fp16x3", **MODEL_KW)
+    synth.fill_params_(lit.model, 0)
+    lit = lit.to(dev)
+    ms = time_steps(lambda: lit.render_rays(resident, 0), K, 3, flush)
+    flops = N_RAYS * (S_PROP * FLOP_PROP + S_NERF * FLOP_NERF)
+    return {"precision": "fp16x3", "value": N_RAYS * SAMPLES_PER_RAY * K / (ms * 1e-3), "unit": "ray-samples/s",
+            "ms_per_step": ms / K, "steps": K, "mlp_tflops_effective": flops * K / (ms * 1e-3) / 1e12,
+            "note": "hi+lo fp16 operands, 3 tcgen05 passes per product (hos_gemm_tma), whole step; algorithmic MLP FLOPs / step time",
+            "parity": parity_check(lit, dev)}
+
+
+def train_arm(dev, rank, world, K):
+    """One stage-1 training step per iteration on every rank's own 4096 rays (S1 model.py:491-514): forward with saved
+    activations, objective, backward on the library's kernels, ONE flat gradient buffer all-reduced over NCCL (bucketed per
+    MLP, asynchronous: the NeRF MLP's bucket travels while the proposal MLP's backward runs), Adam update."""
+    import torch.distributed as dist
+    from hosnerf_b200 import LitMipNeRF360, _lib, synth
+    from hosnerf_b200.dist import FlatGrads
+    lit = LitMipNeRF360("/nonexistent", **MODEL_KW)
+    synth.fill_params_(lit.model, 0)
+    lit = lit.to(dev)
+    lit._train_frac = 0.5
+    batch = {k: v.to(dev) for k, v in synth.make_bkg_batch(N_RAYS, seed=100 + rank).items()}
+    batch["target"] = torch.rand(N_RAYS, 3, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+    sink = FlatGrads(lit.model, bucket_of=lambda name: int(name.split(".")[1]))
+    lit.model._grad_sink = sink
+    opt = torch.optim.Adam(lit.parameters(), lr=1e-4, fused=True)
+    wait_ms = []
+
+    def step():
+        sink.zero_()
+        loss = lit.training_objective(batch, randomized=True)["loss"]
+        loss.backward()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sink.finish()
+        e1.record()
+        wait_ms.append((e0, e1))
+        opt.step()
+        return loss
+
+    W = 3
+    for _ in range(W):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wait_ms.clear()
+    l0 = _lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    exposed = sum(a.elapsed_time(b) for a, b in wait_ms) / K
+    launches = _lib.LAUNCHES - l0
+    # the collective alone (same buffer), for its bus bandwidth
+    ar_ms = None
+    if world > 1:
+        for _ in range(3):
+            dist.all_reduce(sink.flat)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            dist.all_reduce(sink.flat)
+        b.record()
+        torch.cuda.synchronize()
+        ar_ms = a.elapsed_time(b) / 10
+    tt = torch.tensor([ms, exposed, ar_ms or 0.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, exposed, ar = float(tt[0]), float(tt[1]), float(tt[2])
+    fwd_flops = N_RAYS * (S_PROP * FLOP_PROP + S_NERF * FLOP_NERF)
+    out = {"workload": "C2 shape, stage-1 training step (fwd + objective + bwd + grad all-reduce + Adam), 4096 rays per GPU",
+           "value": N_RAYS * SAMPLES_PER_RAY * K * world / (ms * 1e-3), "unit": "ray-samples/s", "rays_per_s": N_RAYS * K * world / (ms * 1e-3),
+           "ms_per_step": ms / K, "steps": K, "loss": float(loss), "gpu_launches": launches,
+           "mlp_tflops_effective_per_gpu": 3 * fwd_flops * K / (ms * 1e-3) / 1e12,
+           "flops_note": "3 x forward MLP FLOPs (forward + data gradient + weight gradient) per step / step time",
+           "grad_bytes": sink.nbytes,
+           "collective": "none (1 GPU)" if world == 1 else
+           {"op": "ncclAllReduce(sum) on one flat fp32 gradient buffer, 2 buckets (NeRF MLP, proposal MLP), asynchronous",
+            "exposed_ms_per_step": exposed, "standalone_ms": ar,
+            "bus_gbs": (2 * (world - 1) / world) * sink.nbytes / (ar * 1e-3) / 1e9 if ar else None}}
+    lit.model._grad_sink = None
+    return out
 
 
 def main():
@@ -164,7 +315,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp16x3"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity / accurate-mode / training-step sub-measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mlp-variant", type=int, default=0, help="A/B: 0 auto, 1 single-CTA MLP kernel, 2 cluster-pair kernel")
     args = ap.parse_args()
@@ -274,6 +426,17 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = out.numel() * out.element_size()
 
+    # ---------------- sub-measurements that explain / qualify the headline (each outside the timed regions above) ------
+    extras = None
+    if not args.no_extras:
+        extras = {}
+        Kx = max(3, min(K, 10))
+        train = train_arm(dev, rank, world, Kx)                  # every rank takes part (collective)
+        if rank == 0:
+            extras["train"] = train
+            extras["parity"] = parity_check(lit, dev)
+            if world == 1 and args.precision != "fp16x3":
+                extras["accurate"] = accurate_arm(dev, resident, flush, Kx)
     tt = torch.tensor([dev_ms, e2e_s * 1e3, e2e_sync_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -312,12 +475,16 @@ def main():
             "clocks": sampler.summary(),
             "wall_ms_per_step_incl_flush": t_wall * 1e3 / K,
         }
+        line["dtype"] = {"fp16": "f16", "fp32": "f32", "fp16x3": "f16x3"}[args.precision]
+        if extras is not None:
+            line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n = 2048
-            sec = cpu_reference_steps(n, 6, 1, threads)          # about 10 s of host work on the box's cores
+            sec, kind = cpu_reference_steps(n, 2, 1, threads)          # about 15 s of host work on the box's cores
             line["cpu_baseline"] = {"value": n * SAMPLES_PER_RAY / sec, "unit": "ray-samples/s", "cores": threads,
-                                    "kind": "port", "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 6 timed passes, torch CPU fp32 oracle"}
+                                    "kind": kind, "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 2 timed passes, torch CPU fp32, "
+                                    + ("unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port")}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

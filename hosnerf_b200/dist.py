@@ -5,7 +5,9 @@ places the reference communicates:
   * eval: every rank renders the rays  i = rank (mod world)  of a padded frame and the results are
     re-interleaved after an all_gather - S1/src/data/sampler.py:44-46 (DDPSequnetialSampler),
     S1/src/data/interface.py:152-156 (padding), S1/src/model/interface.py:30-39 (alter_gather_cat).
-  * training (next round): one flat all-reduce of the gradient buffer per step.
+  * training: the gradients live in ONE flat fp32 buffer (``FlatGrads``; every ``param.grad`` is a view into it) that is
+    all-reduced once per step - S1/run.py:141-156 (DDP) - bucketed per MLP so the collective of the level whose backward
+    has finished overlaps the backward of the next one.
 
 Works with any backend (NCCL on the B200 box, gloo in the CPU tests)."""
 from __future__ import annotations
@@ -78,3 +80,60 @@ def allreduce_flat_(tensors, average: bool = True):
         n = t.numel()
         t.copy_(flat[off:off + n].view_as(t))
         off += n
+
+
+class FlatGrads:
+    """All gradients of ``module`` in one flat fp32 buffer, ``param.grad`` being views into it, grouped in buckets
+    (``bucket_of(name) -> int``; default: one bucket).  ``reduce_bucket(b)`` starts an asynchronous all-reduce of one bucket
+    (on the communication stream, ordered after the kernels already enqueued on the current stream); ``finish()`` waits for
+    all of them and averages.  With world size 1 both are no-ops."""
+
+    def __init__(self, module, bucket_of=None):
+        named = [(k, p) for k, p in module.named_parameters() if p.requires_grad]
+        bucket_of = bucket_of or (lambda name: 0)
+        self.order = sorted(range(len(named)), key=lambda i: (bucket_of(named[i][0]), i))
+        total = sum(p.numel() for _, p in named)
+        dev = named[0][1].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.views, self.ranges = {}, {}
+        off = 0
+        for i in self.order:
+            name, p = named[i]
+            n = p.numel()
+            v = self.flat[off:off + n].view_as(p)
+            p.grad = v
+            self.views[name] = v
+            b = bucket_of(name)
+            lo, hi = self.ranges.get(b, (off, off))
+            self.ranges[b] = (min(lo, off), off + n)
+            off += n
+        self.works, self.reduced = [], set()
+        self.nbytes = total * 4
+
+    def zero_(self):
+        self.flat.zero_()
+        self.reduced = set()
+
+    def add_(self, name, g):
+        self.views[name].add_(g)
+
+    def reduce_bucket(self, b):
+        _, w = world()
+        if w == 1 or b not in self.ranges or b in self.reduced:
+            return
+        self.reduced.add(b)
+        lo, hi = self.ranges[b]
+        self.works.append(dist.all_reduce(self.flat[lo:hi], async_op=True))
+
+    def reduce_all(self):
+        for b in sorted(self.ranges):
+            self.reduce_bucket(b)
+
+    def finish(self, average: bool = True):
+        _, w = world()
+        self.reduce_all()                      # buckets whose backward produced nothing still take part in the collective
+        for wk in self.works:
+            wk.wait()
+        self.works = []
+        if w > 1 and average:
+            self.flat.div_(w)

@@ -199,7 +199,8 @@ class RenderFn(torch.autograd.Function):
         if ctx.stage3:
             g_out = None
             g_dens_last, g_rgb_last = gouts[1 + L + 3 * (L - 1)], gouts[1 + L + 3 * (L - 1) + 1]
-        for lvl in range(L):
+        sink = getattr(m, "_grad_sink", None)        # dist.FlatGrads: accumulate in place + bucketed asynchronous all-reduce
+        for lvl in range(L - 1, -1, -1):             # the NeRF MLP (largest bucket) first: its collective overlaps the rest
             h = ctx.hist[lvl]
             last = lvl == L - 1
             g_w = g_ws[lvl]
@@ -221,7 +222,12 @@ class RenderFn(torch.autograd.Function):
             sub = {}
             mlp_backward(ctx.saved[lvl], gd.contiguous(), gc, sub)
             for k, v in sub.items():
-                grads[f"mlps.{lvl}.{k}"] = v
+                if sink is not None:
+                    sink.add_(f"mlps.{lvl}.{k}", v)
+                else:
+                    grads[f"mlps.{lvl}.{k}"] = v
+            if sink is not None:
+                sink.reduce_bucket(lvl)
         ctx.saved = None
         return (None,) * 8 + tuple(grads.get(nm) for nm in ctx.names)
 

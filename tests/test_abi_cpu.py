@@ -151,5 +151,6 @@ def test_host_entry_points_refuse_cpu_inputs():
         list(lit.render_rays_stream(iter([b])))
     with pytest.raises(RuntimeError):
         lit.model.render_fused(b, 1.0, False, 0.1, 1e6)
-    with pytest.raises(NotImplementedError):
+    b["target"] = torch.zeros(b["rays_o"].shape[0], 3)
+    with pytest.raises(RuntimeError, match="CUDA"):       # the training step has no CPU path either
         lit.training_step(b, 0)

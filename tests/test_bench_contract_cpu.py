@@ -1,5 +1,6 @@
-"""bench.py contract pieces that run without a GPU: the reference arm (`--impl reference`: the oracle port timed on the
-host cores) prints one JSON line with the keys the driver reads, and rank != 0 exits without work."""
+"""bench.py contract pieces that run without a GPU: the reference arm (`--impl reference`: the unmodified reference modules
+from oracle/_ref - or the oracle port where they are absent - timed on the host cores) prints one JSON line with the keys the
+driver reads, and rank != 0 exits without work."""
 import json
 import os
 import subprocess
@@ -23,9 +24,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "ray_samples_per_s" and d["unit"] == "ray-samples/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["config"]["workload"].startswith("C2")
+    assert d["config"]["workload"].startswith("C2") and d["config"]["rays_per_step"] == 4096
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

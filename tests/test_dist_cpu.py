@@ -34,6 +34,18 @@ def _worker(rank, world, port, n_rays, mode, q):
         grads = [torch.full((5,), float(rank + 1)), torch.full((2, 3), float(10 * (rank + 1)))]
         hd.allreduce_flat_(grads, average=True)
         ok = ok and torch.allclose(grads[0], torch.full((5,), 1.5)) and torch.allclose(grads[1], torch.full((2, 3), 15.0))
+        # FlatGrads: param.grad are views of one flat buffer, buckets reduced asynchronously, averaged in finish()
+        net = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 2))
+        fg = hd.FlatGrads(net, bucket_of=lambda name: int(name.split(".")[0]))
+        assert fg.flat.numel() == sum(p.numel() for p in net.parameters()) and sorted(fg.ranges) == [0, 1]
+        for name, p in net.named_parameters():
+            assert p.grad.data_ptr() == fg.views[name].data_ptr()
+            fg.add_(name, torch.full_like(p, float(rank + 1)))
+        fg.reduce_bucket(1)                    # one bucket early (overlap), the other picked up by finish()
+        fg.finish()
+        ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in net.parameters())
+        fg.zero_()
+        ok = ok and float(fg.flat.abs().max()) == 0.0 and not fg.reduced
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
