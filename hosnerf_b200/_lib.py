@@ -91,7 +91,7 @@ SIGNATURES = {
     "hos_gemm_set_head": (c_i, [C.c_void_p, c_i, c_f, c_f, c_f]),
     "hos_gemm_forward": (c_i, [C.c_void_p, c_f, c_f, c_l, c_i, c_f, c_f, c_i, c_fl, c_f]),
     "hos_gemm_tma": (c_i, [C.POINTER(GemmTmaDesc), c_f]),
-    "hos_wgrad_tma": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_l, c_f, c_i, c_i, c_f]),
+    "hos_wgrad_tma": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_l, c_f, c_i, c_i, c_f, c_f]),
     "hos_colsum_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_i, c_f, c_i, c_f]),
     "hos_head_dgrad": (c_i, [c_f, c_i, c_f, c_i, c_f, c_i, c_f, c_i, c_l, c_i, c_f, c_i, c_f]),
     "hos_rays_from_krt": (c_i, [c_i, c_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), c_i, c_i,

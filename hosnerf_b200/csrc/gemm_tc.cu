@@ -36,7 +36,7 @@ constexpr int kG2Threads = 512;
 constexpr int kG2EpiWarp0 = 4, kG2EpiWarps = 8, kG2AWarp0 = 12;
 constexpr int kG2BProducers = 3, kG2AProducers = 4;
 constexpr int kG2MaxStages = 6;
-constexpr int kG2Bars = 2 * kG2MaxStages + 4;
+constexpr int kG2Bars = 2 * kG2MaxStages + 4 + 4;      // + [3] mask tiles landed (+ pad)
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -104,11 +104,14 @@ struct G2Args {
   int kb0, kb1;     // 64-wide K chunks read from A0 / A1
   int relu, split, b_mn;
   int stages;
+  int nbuf_out;     // output staging buffers (TMA stores in flight + 1)
+  int bias_smem;    // bias of the current 256-column block staged in shared memory
   int dbg;
 };
 
 struct G2Maps {
   CUtensorMap a0[2], a1[2], b0[2], b1[2], y[2];     // [hi, lo]
+  CUtensorMap mask;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
@@ -121,12 +124,15 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
   const int S = args.stages;
   unsigned char* sRing = smem;
   unsigned char* sStage = sRing + (size_t)S * stage_bytes;  // [1 or 2 planes][16 KB] output staging for the TMA stores
-  float* s_headx = reinterpret_cast<float*>(sStage + (args.y_lo ? 2 : 1) * kXChunkBytes);     // [128][4]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_headx + kTileM * 4);
+  const int out_buf_bytes = (args.y_lo ? 2 : 1) * kXChunkBytes;
+  float* s_headx = reinterpret_cast<float*>(sStage + (size_t)args.nbuf_out * out_buf_bytes);     // [128][4]
+  float* sBias = s_headx + kTileM * 4;                      // [256] bias of the current column block (bias_smem)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (args.bias_smem ? 256 : 0));
   uint64_t* bar_full = bars;                                // leader: A + B of both CTAs landed (2 tx arrivals + 2 relays); peer: its own two
   uint64_t* bar_empty = bar_full + kG2MaxStages;            // multicast commit: stage consumed
   uint64_t* bar_tfull = bar_empty + kG2MaxStages;           // [2] multicast commit: accumulator buffer complete
   uint64_t* bar_tempty = bar_tfull + 2;                     // [2] leader only: drained by the 16 epilogue warps of the pair
+  uint64_t* bar_mask = bar_tempty + 2;                      // [3] ReLU-mask tile landed in output staging buffer b (data gradient)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kG2Bars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,9 +142,11 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
   const int KB = args.kb0 + args.kb1;
   const int nblk = args.nblk;
 
+  if (args.bias_smem && threadIdx.x < 256) sBias[threadIdx.x] = (args.bias && (int)threadIdx.x < args.n) ? args.bias[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kG2MaxStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * kG2EpiWarps); }
+    for (int s = 0; s < 3; ++s) mbar_init(&bar_mask[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -170,7 +178,8 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
           for (int kb = 0; kb < KB; ++kb, ++ci) {
             if (ci % P != p) continue;
             const uint32_t st = ci % (uint32_t)S, use = ci / (uint32_t)S;
-            G2_WAIT(100, &bar_empty[st], (use & 1) ^ 1, 1, (int)ci, (int)st);
+            if (args.dbg & 2) mbar_wait_guard<0>(&bar_empty[st], (use & 1) ^ 1);
+            else G2_WAIT(100, &bar_empty[st], (use & 1) ^ 1, 1, (int)ci, (int)st);
             unsigned char* stage = sRing + (size_t)st * stage_bytes;
             const bool first = kb < args.kb0;
             const int kc = (first ? kb : kb - args.kb0) * kKB;
@@ -193,7 +202,8 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
               }
             }
             if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
-              G2_WAIT(100, &bar_full[st], use & 1, 2, (int)ci, (int)st);
+              if (args.dbg & 2) mbar_wait_guard<0>(&bar_full[st], use & 1);
+              else G2_WAIT(100, &bar_full[st], use & 1, 2, (int)ci, (int)st);
               mbar_arrive_remote(mapa_u32(smem_u32(&bar_full[st]), 0));
             }
           }
@@ -282,6 +292,26 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
     const bool has_head = args.hn > 0;
     uint32_t u = 0;
     bool stage_busy = false;
+    int ob = 0;
+    // Data gradient: the ReLU mask (the layer's saved fp16 input) arrives by TMA, one [128 x 64] tile per output chunk, straight
+    // into the staging buffer the chunk's result will be written to (every thread reads exactly the 16-byte slots it then
+    // overwrites); the tile of chunk i + 1 is requested while chunk i is processed.  (Per-thread global loads of the mask -
+    // 32 different lines per warp instruction - kept the L1 tag stage busy for twice the chunk's tensor time.)
+    const int nchunk = args.n_blk / 64;
+    uint32_t mpar = 0;                                      // per staging buffer: parity of the next mask phase
+    auto next_chunk = [&](int& g2, int& j2, int& c2) {      // advance (g2, j2, c2) to the next chunk that stages output
+      ++c2;
+      if (c2 >= nchunk || j2 * args.n_blk + c2 * 64 >= args.n) {
+        c2 = 0;
+        if (++j2 >= nblk) { j2 = 0; g2 += n_clusters; }
+      }
+      return g2 < n_groups;
+    };
+    auto request_mask = [&](int g2, int j2, int c2, int buf) {
+      mbar_expect_tx(&bar_mask[buf], (uint32_t)kXChunkBytes);
+      tma_load_2d(sStage + (size_t)buf * out_buf_bytes, &maps.mask, j2 * args.n_blk + c2 * 64, (2 * g2 + (int)rank) * kTileM, &bar_mask[buf]);
+    };
+    if (args.mask && epi_leader && cluster < n_groups) request_mask(cluster, 0, 0, 0);
     for (int g = cluster; g < n_groups; g += n_clusters) {
       const int tile = 2 * g + (int)rank;
       const int64_t row = (int64_t)tile * kTileM + r;
@@ -289,6 +319,12 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
       float hacc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int j = 0; j < nblk; ++j, ++u) {
         const uint32_t acc = tmem_base + (u & 1) * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        if (args.bias_smem && nblk > 1) {       // several column blocks: restage this block's bias (block 0 was staged at start-up)
+          asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+          const int e = threadIdx.x - kG2EpiWarp0 * 32, col = j * args.n_blk + e;
+          sBias[e] = (args.bias && col < args.n) ? __ldg(args.bias + col) : 0.f;
+          asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+        }
         G2_WAIT(20, &bar_tfull[u & 1], (u >> 1) & 1, 4, (int)u, 0);
         tc_fence_after();
         for (int c = 0; c < args.n_blk / 64; ++c) {
@@ -302,7 +338,15 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (args.bias && col_ok) {
+          if (args.bias_smem) {
+            // (global bias loads in this loop cost a quarter of the kernel: 8 dependent L1 round trips per chunk per warp)
+            const uint32_t sb = smem_u32(sBias) + 4u * (uint32_t)(c * 64 + ch * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = lds128(sb + 16u * i);
+              f[4 * i + 0] += bb.x; f[4 * i + 1] += bb.y; f[4 * i + 2] += bb.z; f[4 * i + 3] += bb.w;
+            }
+          } else if (args.bias && col_ok) {
             const float4* b4 = reinterpret_cast<const float4*>(args.bias + n0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -324,13 +368,21 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (args.mask && row_ok && col_ok) {              // dgrad through a ReLU: keep where the saved activation is positive
-            const uint4* mp = reinterpret_cast<const uint4*>(args.mask + row * args.ld_mask + n0);
+          const uint32_t ob_off = (uint32_t)ob * (uint32_t)out_buf_bytes;
+          if (args.mask) {                                  // dgrad through a ReLU: keep where the saved activation is positive
+            if (epi_leader) {
+              int g2 = g, j2 = j, c2 = c;
+              if (next_chunk(g2, j2, c2)) {
+                if (stage_busy) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer ob + 1: store of chunk i - 2 has read it
+                request_mask(g2, j2, c2, ob + 1 == args.nbuf_out ? 0 : ob + 1);
+              }
+            }
+            mbar_wait_guard<20>(&bar_mask[ob], (mpar >> ob) & 1u);
+            mpar ^= 1u << ob;
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
-              if (n0 + gq * 8 >= args.n) break;
-              const uint4 mv = __ldg(mp + gq);
-              const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+              const float4 mv4 = lds128(st_off[gq] + ob_off);
+              const uint32_t w[4] = {__float_as_uint(mv4.x), __float_as_uint(mv4.y), __float_as_uint(mv4.z), __float_as_uint(mv4.w)};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const __half2 h2 = *reinterpret_cast<const __half2*>(&w[i]);
@@ -340,9 +392,15 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
             }
           }
           if (args.y_hi) {
-            // the staging buffer is free once the previous chunk's TMA stores have read it
-            if (stage_busy && epi_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+            if (!args.mask) {
+              // staging buffer `ob` is free once the TMA stores issued nbuf_out chunks ago have read it
+              if (stage_busy && epi_leader) {
+                if (args.nbuf_out >= 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                else if (args.nbuf_out == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              }
+              asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
+            }
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
               uint32_t ph[4], pl[4];
@@ -354,17 +412,18 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
                 const __half2 l2 = __floats2half2_rn(x0 - __low2float(h2), x1 - __high2float(h2));
                 pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
               }
-              sts128(st_off[gq], ph[0], ph[1], ph[2], ph[3]);
-              if (args.y_lo) sts128(st_off[gq] + kXChunkBytes, pl[0], pl[1], pl[2], pl[3]);
+              sts128(st_off[gq] + ob_off, ph[0], ph[1], ph[2], ph[3]);
+              if (args.y_lo) sts128(st_off[gq] + ob_off + kXChunkBytes, pl[0], pl[1], pl[2], pl[3]);
             }
             fence_proxy_async();                            // generic-proxy stores -> visible to the TMA engine
             asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");
             if (epi_leader && tile_ok) {
-              tma_store_2d(&maps.y[0], sStage, nc0, tile * kTileM);
-              if (args.y_lo) tma_store_2d(&maps.y[1], sStage + kXChunkBytes, nc0, tile * kTileM);
-              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              tma_store_2d(&maps.y[0], sStage + ob_off, nc0, tile * kTileM);
+              if (args.y_lo) tma_store_2d(&maps.y[1], sStage + ob_off + kXChunkBytes, nc0, tile * kTileM);
             }
+            if (epi_leader) asm volatile("cp.async.bulk.commit_group;" ::: "memory");     // one group per chunk, even when empty
             stage_busy = true;
+            if (++ob == args.nbuf_out) ob = 0;
           }
           if (args.y_f32 && row_ok && col_ok) {
             float4* d32 = reinterpret_cast<float4*>(args.y_f32 + row * args.ldy32 + n0);
@@ -443,6 +502,7 @@ constexpr int kWgStages = 2;
 
 struct WgArgs {
   float* out;
+  float* colsum;      // optional [m]: += column sums of P (the bias gradient when P is dL/dZ), fp32 atomics
   int64_t rows;
   int ld_out;
   int ntiles;
@@ -474,7 +534,12 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
   const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], 1); }
+    // a stage is free when its MMAs have retired (multicast commit) and, with column sums requested, when the 8 epilogue
+    // warps of this CTA have read the P tile out of it
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&bar_full[s], rank == 0 ? 4u : 2u);
+      mbar_init(&bar_empty[s], args.colsum ? 1u + kG2EpiWarps : 1u);
+    }
     mbar_init(&bar_done[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -548,6 +613,32 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
     const int q = warp & 3;
     const int ch = (warp - kG2EpiWarp0) >> 2;
     const int i = (int)rank * 128 + q * 32 + lane;            // P column = output row
+    if (args.colsum) {
+      // While the tensor core works, these warps add up the columns of every P tile straight from the staged (swizzled)
+      // boxes: thread -> column e & 127 of this CTA's 128, rows [64 (e >> 7), +64).  The bias gradient costs no extra pass.
+      const int e = threadIdx.x - kG2EpiWarp0 * 32;
+      const int col = e & 127, r0 = (e >> 7) * 64;
+      const uint32_t cbase = (uint32_t)(col >> 6) * kXChunkBytes + (uint32_t)(col & 7) * 2u;
+      const uint32_t cg = (uint32_t)((col & 63) >> 3);
+      float acc = 0.f;
+      uint32_t st = 0, par = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait_guard<40>(&bar_full[st], par);
+        const uint32_t sbase = smem_u32(sRing + (size_t)st * stage_bytes) + cbase;
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) {
+          const uint32_t r = (uint32_t)(r0 + rr);
+          unsigned short hv;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(sbase + r * 128u + ((cg ^ (r & 7u)) << 4)));
+          acc += __half2float(__ushort_as_half(hv));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[st]);
+        if (++st == kWgStages) { st = 0; par ^= 1; }
+      }
+      const int pc = (int)rank * 128 + col;
+      if (pc < args.m) atomicAdd(args.colsum + pc, acc);
+    }
     mbar_wait_guard<200>(&bar_done[0], 0);
     tc_fence_after();
     for (int a = 0; a < nacc; ++a) {
@@ -612,29 +703,47 @@ colsum_f16_kernel(const __half* __restrict__ X, int64_t rows, int n, int ld, con
 __global__ void __launch_bounds__(256)
 head_dgrad_kernel(const float* __restrict__ g, int hn, const float* __restrict__ W, int ldw, const __half* __restrict__ add,
                   int ld_add, const __half* __restrict__ mask, int ld_mask, int64_t rows, int n, __half* __restrict__ Y, int ldy) {
-  const int cpr = n >> 1;                                    // column pairs per row
-  const int64_t total = rows * cpr;
+  const int vpr = n >> 3;                                    // 16-byte vectors (8 columns) per row
+  const int64_t total = rows * vpr;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / cpr;
-    const int c = 2 * (int)(i % cpr);
-    float y0 = 0.f, y1 = 0.f;
+    const int64_t row = i / vpr;
+    const int c = 8 * (int)(i - row * vpr);
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int h = 0; h < 4; ++h)
       if (h < hn) {
         const float gv = __ldg(g + row * hn + h);
-        y0 = fmaf(gv, __ldg(W + (size_t)h * ldw + c), y0);
-        y1 = fmaf(gv, __ldg(W + (size_t)h * ldw + c + 1), y1);
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ldw + c));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (size_t)h * ldw + c) + 1);
+        y[0] = fmaf(gv, w0.x, y[0]); y[1] = fmaf(gv, w0.y, y[1]); y[2] = fmaf(gv, w0.z, y[2]); y[3] = fmaf(gv, w0.w, y[3]);
+        y[4] = fmaf(gv, w1.x, y[4]); y[5] = fmaf(gv, w1.y, y[5]); y[6] = fmaf(gv, w1.z, y[6]); y[7] = fmaf(gv, w1.w, y[7]);
       }
     if (add) {
-      const __half2 a2 = *reinterpret_cast<const __half2*>(add + row * ld_add + c);
-      y0 += __low2float(a2); y1 += __high2float(a2);
+      const uint4 av = __ldg(reinterpret_cast<const uint4*>(add + row * ld_add + c));
+      const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2 a2 = *reinterpret_cast<const __half2*>(&aw[k]);
+        y[2 * k] += __low2float(a2); y[2 * k + 1] += __high2float(a2);
+      }
     }
     if (mask) {
-      const __half2 m2 = *reinterpret_cast<const __half2*>(mask + row * ld_mask + c);
-      if (!(__low2float(m2) > 0.f)) y0 = 0.f;
-      if (!(__high2float(m2) > 0.f)) y1 = 0.f;
+      const uint4 mv = __ldg(reinterpret_cast<const uint4*>(mask + row * ld_mask + c));
+      const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2 m2 = *reinterpret_cast<const __half2*>(&mw[k]);
+        if (!(__low2float(m2) > 0.f)) y[2 * k] = 0.f;
+        if (!(__high2float(m2) > 0.f)) y[2 * k + 1] = 0.f;
+      }
     }
-    *reinterpret_cast<__half2*>(Y + row * ldy + c) = __floats2half2_rn(y0, y1);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __half2 h2 = __floats2half2_rn(y[2 * k], y[2 * k + 1]);
+      o[k] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    *reinterpret_cast<uint4*>(Y + row * ldy + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -736,9 +845,15 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
   a.relu = d->relu; a.split = split; a.b_mn = d->mode == 1;
   const int planes = split ? 2 : 1;
   const int stage_bytes = planes * (kXChunkBytes + a.n_blk * 64);
-  const size_t fixed = 1024 + (size_t)(d->y_lo ? 2 : 1) * kXChunkBytes + kTileM * 4 * sizeof(float) + kG2Bars * 8 + 64;
+  // split precision: the 64 KB stages leave room for one staging buffer (its epilogue is far shorter than its MMAs);
+  // single plane: three staging buffers so that two chunks' TMA stores stay in flight behind the epilogue
+  a.nbuf_out = !d->y_hi ? 0 : (split ? 1 : 3);
+  a.bias_smem = !split && d->bias != nullptr;
+  const size_t fixed = 1024 + (size_t)a.nbuf_out * (d->y_lo ? 2 : 1) * kXChunkBytes + kTileM * 4 * sizeof(float) +
+                       (a.bias_smem ? 1024 : 0) + kG2Bars * 8 + 64;
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > kG2MaxStages) stages = kG2MaxStages;
+  HOS_REQUIRE(stages >= 2, "hos_gemm_tma: shared memory budget leaves %d pipeline stages", stages);
   { const char* e = getenv("HOS_G2_STAGES"); if (e) stages = atoi(e); }
   a.stages = stages;
   { const char* e = getenv("HOS_G2_DBG"); a.dbg = e ? atoi(e) : 0; }
@@ -762,6 +877,10 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
       if (rc != HOS_OK) return rc;
     }
   }
+  if (d->mask) {
+    HOS_REQUIRE(d->y_hi && !split && a.nbuf_out >= 3, "hos_gemm_tma: a mask needs the single-plane fp16 output path");
+    if ((rc = make_map(&maps.mask, d->mask, d->rows, d->n, d->ld_mask, kTileM)) != HOS_OK) return rc;
+  }
   if (d->y_hi) {
     if ((rc = make_map(&maps.y[0], d->y_hi, d->rows, d->n, d->ldy, kTileM)) != HOS_OK) return rc;
     if (d->y_lo && (rc = make_map(&maps.y[1], d->y_lo, d->rows, d->n, d->ldy, kTileM)) != HOS_OK) return rc;
@@ -784,7 +903,7 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
 }
 
 int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq, int64_t rows, float* out, int ld_out,
-                  int transpose_out, void* stream) {
+                  int transpose_out, float* colsum_p, void* stream) {
   HOS_ARCH_GUARD();
   HOS_REQUIRE(p && q && out && m >= 1 && m <= 256 && nq >= 1 && nq <= 512 && rows >= 0 && ld_out >= 1,
               "hos_wgrad_tma: need P [rows, m <= 256], Q [rows, nq <= 512] and out");
@@ -793,7 +912,7 @@ int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq,
   memset(&a, 0, sizeof(a));
   WgMaps maps;
   memset(&maps, 0, sizeof(maps));
-  a.out = out; a.rows = rows; a.ld_out = ld_out;
+  a.out = out; a.rows = rows; a.ld_out = ld_out; a.colsum = colsum_p;
   a.ntiles = (int)((rows + kTileM - 1) / kTileM);
   a.m = m; a.nq = nq; a.nacc = nq > 256 ? 2 : 1; a.transpose_out = transpose_out;
   int rc;
@@ -831,11 +950,13 @@ int hos_colsum_f16(const void* x, int64_t rows, int n, int ld, const float* g, i
 int hos_head_dgrad(const float* g, int hn, const float* W, int ldw, const void* add, int ld_add, const void* mask, int ld_mask,
                    int64_t rows, int n, void* y, int ldy, void* stream) {
   HOS_ARCH_GUARD();
-  HOS_REQUIRE(g && W && y && hn >= 1 && hn <= 4 && n >= 2 && (n % 2) == 0 && (ldy % 2) == 0 && (!mask || (ld_mask % 2) == 0) &&
-                  (!add || (ld_add % 2) == 0),
-              "hos_head_dgrad: hn <= 4, n and pitches even");
+  HOS_REQUIRE(g && W && y && hn >= 1 && hn <= 4 && n >= 8 && (n % 8) == 0 && (ldy % 8) == 0 && (ldw % 4) == 0 &&
+                  (!mask || (ld_mask % 8) == 0) && (!add || (ld_add % 8) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(add) |
+                    reinterpret_cast<uintptr_t>(mask)) & 15) == 0,
+              "hos_head_dgrad: hn <= 4, n and the fp16 pitches multiples of 8, ldw of 4, 16-byte aligned pointers");
   if (rows == 0) return HOS_OK;
-  const int64_t total = rows * (n / 2);
+  const int64_t total = rows * (n / 8);
   const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   head_dgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, hn, W, ldw, (const __half*)add, ld_add, (const __half*)mask, ld_mask,
                                                           rows, n, (__half*)y, ldy);

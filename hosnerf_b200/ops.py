@@ -541,19 +541,22 @@ def gemm_tma(a0, w0, n, a1=None, w1=None, bias=None, relu=False, mask=None, mode
     return (y16, ylo, y32) if head is None else (y16, ylo, y32, hout)
 
 
-def wgrad_tma(p, q, out, transpose_out=False):
-    """out[i, j] += sum_rows p[row, i] q[row, j]  (out fp32 [m, nq], or [nq, m] with transpose_out; any column-sliced view)."""
+def wgrad_tma(p, q, out, transpose_out=False, colsum=None):
+    """out[i, j] += sum_rows p[row, i] q[row, j]  (out fp32 [m, nq], or [nq, m] with transpose_out; any column-sliced view).
+    ``colsum`` (fp32 [m], optional): += column sums of p in the same pass (bias gradient when p = dL/dZ)."""
     _chk16(p, "p"), _chk16(q, "q")
     assert out.dtype == _F32 and out.is_cuda and out.stride(1) == 1
     rows, m = p.shape
     nq = q.shape[1]
     assert q.shape[0] == rows and tuple(out.shape) == ((nq, m) if transpose_out else (m, nq)), (p.shape, q.shape, out.shape)
+    assert colsum is None or (colsum.dtype == _F32 and colsum.is_cuda and colsum.numel() == m and colsum.is_contiguous())
     for i0 in range(0, m, 256):
         for j0 in range(0, nq, 512):
             mi, nj = min(256, m - i0), min(512, nq - j0)
             o = out[j0:j0 + nj, i0:i0 + mi] if transpose_out else out[i0:i0 + mi, j0:j0 + nj]
+            cs = colsum[i0:].data_ptr() if (colsum is not None and j0 == 0) else None
             _lib.call_unless_empty(rows, "hos_wgrad_tma", p[:, i0:].data_ptr(), mi, p.stride(0), q[:, j0:].data_ptr(), nj,
-                                   q.stride(0), rows, o.data_ptr(), out.stride(0), int(transpose_out), _stream())
+                                   q.stride(0), rows, o.data_ptr(), out.stride(0), int(transpose_out), cs, _stream())
     return out
 
 
@@ -573,6 +576,8 @@ def head_dgrad(g, W, n, add=None, mask=None):
     _chk(g, "g"), _chk16(add, "add"), _chk16(mask, "mask")
     assert W.dtype == _F32 and W.is_cuda and W.stride(1) == 1 and g.dim() == 2 and W.shape[0] == g.shape[1]
     rows, hn = g.shape
+    if W.stride(0) % 4 != 0 or W.data_ptr() % 16 != 0:
+        W = W.contiguous()
     y = torch.empty(rows, n, device=g.device, dtype=_F16)
     _lib.call_unless_empty(rows, "hos_head_dgrad", _p(g), hn, W.data_ptr(), W.stride(0), _p(add), 0 if add is None else add.stride(0),
                            _p(mask), 0 if mask is None else mask.stride(0), rows, n, _p(y), n, _stream())

@@ -128,8 +128,7 @@ def mlp_backward(ctx, g_density, g_rgb, grads: dict):
         sacc("views_linear.0.bias", (cw,)).add_(g_row.sum(0))
         g_bott = ops.gemm_tma(g_zv, _h(Wv[:, :bw]), bw, mode=1)[0]                           # [rows, bw]
         Wb = m.bottleneck_layer.weight.detach()
-        ops.wgrad_tma(g_bott, h_last, sacc("bottleneck_layer.weight", Wb.shape))
-        ops.colsum_f16(g_bott, sacc("bottleneck_layer.bias", (bw,)))
+        ops.wgrad_tma(g_bott, h_last, sacc("bottleneck_layer.weight", Wb.shape), colsum=sacc("bottleneck_layer.bias", (bw,)))
         add = ops.gemm_tma(g_bott, _h(Wb), nw, mode=1)[0]                                    # d/dh_last through the bottleneck
     g_z = ops.head_dgrad(g_raw, Wd, nw, add=add, mask=h_last)                                # + density head, ReLU mask of the last layer
     g_e = sacc("bkgd_stateembeds.%d" % ctx["state"], e.shape)
@@ -137,17 +136,16 @@ def mlp_backward(ctx, g_density, g_rgb, grads: dict):
         lin = m.pts_linear[i]
         W = lin.weight.detach()
         gW = sacc(f"pts_linear.{i}.weight", W.shape)
-        gb = sacc(f"pts_linear.{i}.bias", (nw,))
-        ops.colsum_f16(g_z, gb)
+        gb = sacc(f"pts_linear.{i}.bias", (nw,))         # bias gradient = column sums of dL/dZ: rides in the weight-gradient pass
         if i == 0:
-            ops.wgrad_tma(g_z, feat, gW[:, :F])
+            ops.wgrad_tma(g_z, feat, gW[:, :F], colsum=gb)
             emb0 = F
         elif m._skip_inputs(i):
-            ops.wgrad_tma(g_z, hs[i - 1], gW[:, :nw])
+            ops.wgrad_tma(g_z, hs[i - 1], gW[:, :nw], colsum=gb)
             ops.wgrad_tma(g_z, feat, gW[:, nw:nw + F])
             emb0 = nw + F
         else:
-            ops.wgrad_tma(g_z, hs[i - 1], gW)
+            ops.wgrad_tma(g_z, hs[i - 1], gW, colsum=gb)
             emb0 = None
         if emb0 is not None:        # the embedding rides in the bias: rank-1 weight gradient, and its own gradient
             gW[:, emb0:].add_(torch.outer(gb, e))

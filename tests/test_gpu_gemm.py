@@ -81,7 +81,9 @@ def test_wgrad(rows, m, nq, tr):
     q = torch.randn(rows, nq, device="cuda", generator=g).half()
     base = torch.randn((nq, m) if tr else (m, nq), device="cuda", generator=g)
     out = base.clone()
-    ops.wgrad_tma(p, q, out, transpose_out=tr)
+    cs = torch.ones(m, device="cuda")
+    ops.wgrad_tma(p, q, out, transpose_out=tr, colsum=cs)
+    assert _rel(cs, 1.0 + p.double().sum(0)) < 1e-5, _rel(cs, 1.0 + p.double().sum(0))
     ref = p.double().t() @ q.double()
     ref = base.double() + (ref.t() if tr else ref)
     assert _rel(out, ref) < 1e-5, _rel(out, ref)
