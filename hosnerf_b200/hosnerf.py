@@ -10,14 +10,15 @@ from . import ops
 
 def render_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dict, newsmpl_to_scale_world,
                          near_bkg: float = 0.1, far_bkg: float = 1e6, train_frac: float = 1.0,
-                         randomized: bool = False, thre_fg: float = 5e-3, rands=None):
+                         randomized: bool = False, thre_fg: float = 5e-3, rands=None, cycle_outputs: bool = False):
     """bkg_model: hosnerf_b200.MipNeRF360(stage3=True); human_net: hosnerf_b200.Network.
     batch_bkg: rays_o, rays_d, viewdirs, radii, times (scale-world frame); batch_human: the kwargs of
     Network.forward (rays in the new-SMPL frame, pose, bbox, ...).  Returns dict(rgb [n,3], idx_fg [n],
     human_weights [n,S_h], ray_history, net_output)."""
     with torch.no_grad():
         _, ray_history = bkg_model(batch_bkg, train_frac, randomized, False, near_bkg, far_bkg, rands=rands)
-        net_output = human_net(**batch_human)
+        # the cycle side path only feeds the training loss: render loops skip it (pass cycle_outputs=True to get it)
+        net_output = human_net(**batch_human, cycle_outputs=cycle_outputs)
         h = ray_history[-1]
         n = h["density"].shape[0]
         s_h = net_output["human_density"].shape[-1]

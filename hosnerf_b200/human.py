@@ -276,12 +276,41 @@ def hann_window_weights(n_freqs, iter_val, kick_in_iter, full_band_iter):
     return torch.stack([x.reshape(()) for x in w]).float()
 
 
+# The second plug-in seam of the reference: ``cfg.<component>.module`` names the python file a component class is loaded from
+# (S3/core/nets/human_nerf/component_factory.py:12-40).  This package ships one kernel-backed implementation per component:
+# a config that names the reference's default module gets it; a config that swaps a component for something else must not
+# silently get the built-in one.
+_BUILTIN_MODULES = {
+    "embedder": "core.nets.human_nerf.embedders.fourier",
+    "non_rigid_embedder": "core.nets.human_nerf.embedders.hannw_fourier",
+    "canonical_mlp": "core.nets.human_nerf.canonical_mlps.mlp_rgb_sigma",
+    "mweight_volume": "core.nets.human_nerf.mweight_vol_decoders.deconv_vol_decoder",
+    "non_rigid_motion_mlp": "core.nets.human_nerf.non_rigid_motion_mlps.mlp_offset",
+    "non_rigid_forward_mlp": "core.nets.human_nerf.non_rigid_motion_mlps.mlp_forward_offset",
+    "pose_decoder": "core.nets.human_nerf.pose_decoders.mlp_delta_body_pose",
+}
+
+
+def check_component_modules(cfg):
+    """Raise if ``cfg.<component>.module`` asks for a component implementation other than the reference default."""
+    for comp, default in _BUILTIN_MODULES.items():
+        node = cfg.get(comp) if hasattr(cfg, "get") else getattr(cfg, comp, None)
+        mod = None
+        if node is not None:
+            mod = node.get("module") if hasattr(node, "get") else getattr(node, "module", None)
+        if mod is not None and str(mod) != default:
+            raise NotImplementedError(
+                f"hosnerf_b200.Network: cfg.{comp}.module = {mod!r} selects a component this package has no kernels for "
+                f"(built in: {default!r}, S3 component_factory.py:12-40)")
+
+
 # ----------------------------------------------------------------------------- Network
 class Network(nn.Module):
     """S3 network.py:27-698.  ``stage2=True`` gives the S2 return dict (rgb/alpha/depth/weights)."""
 
     def __init__(self, cfg, stage2: bool = False, precision=None):
         super().__init__()
+        check_component_modules(cfg)
         self.cfg = cfg
         self.stage2 = stage2
         self.precision = precision
@@ -480,8 +509,7 @@ class Network(nn.Module):
         time = kwargs.get("time", 0.0)
         if is_train and torch.is_grad_enabled():
             raise NotImplementedError("hosnerf_b200 kernels are forward-only in this round; call under torch.no_grad()")
-        if is_train and float(time) > 0.005:
-            raise NotImplementedError("hosnerf_b200: the flow side path (prev-frame forward warp) is not built yet")
+        flow = is_train and float(time) > 0.005           # flow side path: previous-frame forward warp (network.py:474-502)
         precision = self.precision or _m._DEFAULT_PRECISION
         cfg = self.cfg
         with torch.no_grad():
@@ -494,6 +522,8 @@ class Network(nn.Module):
                 return (id(x), x._version) if isinstance(x, torch.Tensor) else ("v", x)
             frame_inputs = [dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, iter_val, time,
                             kwargs["cnl_bbox_min_xyz"], kwargs["cnl_bbox_scale_xyz"]]
+            if flow:
+                frame_inputs += [kwargs["dst_Rs_prev"], kwargs["dst_Ts_prev"], kwargs["dst_posevec_prev"]]
             fkey = (tuple(tag(x) for x in frame_inputs), str(rays.device),
                     self._versions([self.pose_decoder, self.mweight_vol_decoder]), len(self.human_stateembeds))
             fr = self._cache.get("frame")
@@ -508,7 +538,16 @@ class Network(nn.Module):
                                              cfg.non_rigid_motion_mlp.full_band_iter).to(rays.device)
                 cond = torch.zeros_like(posevec) * posevec if it < cfg.non_rigid_motion_mlp.kick_in_iter else posevec
                 Rb, Tb, Rf, Tf = self.motion_basis_computer(Rs_h, Ts_h, cnl_gtfms[None, ...])
-                fr = dict(key=fkey, refs=frame_inputs, it=it, hann_w=hann_w, cond=cond, Rb=Rb, Tb=Tb, Rf=Rf, Tf=Tf,
+                prev = None
+                if flow:        # previous frame: refined pose -> forward motion bases, its own condition code (network.py:609-637)
+                    Rp, Tp = kwargs["dst_Rs_prev"][None, ...].detach().cpu(), kwargs["dst_Ts_prev"][None, ...].detach().cpu()
+                    pv = kwargs["dst_posevec_prev"][None, ...]
+                    if it >= cfg.pose_decoder.get("kick_in_iter", 0):
+                        Rp, Tp = self._correct_pose(Rp, Tp, pv.detach().cpu())
+                    _, _, Rfp, Tfp = self.motion_basis_computer(Rp, Tp, cnl_gtfms[None, ...])
+                    prev = dict(Rf=Rfp, Tf=Tfp,
+                                cond=torch.zeros_like(pv) * pv if it < cfg.non_rigid_motion_mlp.kick_in_iter else pv)
+                fr = dict(key=fkey, refs=frame_inputs, it=it, hann_w=hann_w, cond=cond, Rb=Rb, Tb=Tb, Rf=Rf, Tf=Tf, prev=prev,
                           vol=self._volume(motion_weights_priors[None, ...]),
                           state_idx=select_state_index(len(self.human_stateembeds), time, self.transitions_times),
                           bbox_min=kwargs["cnl_bbox_min_xyz"].detach().cpu().reshape(-1).tolist(),
@@ -555,14 +594,21 @@ class Network(nn.Module):
                     rgb, acc, w, depth = ops.composite_nerf(raw, mask, z, rays_d[c0:c1], bgcolor, activate=True)
                     ret.update(rgb=rgb, alpha=acc, depth=depth, weights=w)
                 else:
-                    ret.update(human_rgb=raw[..., :3], human_density=raw[..., 3], newsmpl_pts=pts,
-                               pts_mask=mask, z_vals=z, rays_d=rays_d[c0:c1])
+                    ret.update(human_rgb=raw[..., :3], human_density=raw[..., 3], newsmpl_pts=pts, pts_mask=mask)
+                    if not flow:                        # the reference's train-mode dict drops them (network.py:538-547)
+                        ret.update(z_vals=z, rays_d=rays_d[c0:c1])
+                if flow:
+                    pf = fr["prev"]
+                    xp, _ = ops.lbs_forward(cnl.reshape(-1, 3).contiguous(), pf["Rf"][0], pf["Tf"][0], vol, bbox_min, bbox_scale)
+                    if not cfg.ignore_non_rigid_motions:
+                        xp = self._eval_non_rigid("nrf_prev", self.non_rigid_forward_mlp, xp, pf["cond"], hann_w, precision)
+                    ret["deform_pts_prev_final"] = xp.view(c1 - c0, S, 3)
                 # cycle-consistency side path (network.py:505-536): forward warp of the points the motion
-                # field considers foreground.  The reference evaluates it in eval too (its outputs are only
-                # read by the training loss); here it runs when asked for (default: training calls).
+                # field considers foreground.  Evaluated on every call like the reference does (its outputs are
+                # only read by the training loss, so render loops may pass cycle_outputs=False - an extension).
                 ret["deform_pts_final"] = pts[0, 0, :][None, :]
                 ret["observe_pts"] = pts[0, 0, :][None, :]
-                if kwargs.get("cycle_outputs", is_train):
+                if kwargs.get("cycle_outputs", True):
                     sel = mask.reshape(-1) > 0.005
                     if bool(sel.any()):
                         observe = pts.reshape(-1, 3)[sel].contiguous()

@@ -272,8 +272,9 @@ def composite_s3(bkg_rgb, bkg_density, bkg_tdist, human_rgb, human_density, pts_
 def network_forward(sd, batch, *, n_samples=128, kick_in_iter=100000, full_band_iter=200000,
                     pose_kick_in_iter=20000, rand=None, stage2=False, transitions_times=None):
     """Restates Network.forward/_render_rays (S3 network.py:427-698; S2 returns the
-    composited rgb/alpha/depth/weights instead, S2 network.py:537-556).  Eval path:
-    is_train False or time <= 0.005 (no flow side path)."""
+    composited rgb/alpha/depth/weights instead, S2 network.py:537-556).  With ``is_train`` and
+    ``time > 0.005`` the flow side path (network.py:474-502, 609-631) adds ``deform_pts_prev_final``
+    and the S3 dict drops z_vals / rays_d (network.py:538-547)."""
     rays_o, rays_d = batch["rays"][0].reshape(-1, 3).float(), batch["rays"][1].reshape(-1, 3).float()
     iter_val = batch["iter_val"]
     dst_Rs, dst_Ts = batch["dst_Rs"], batch["dst_Ts"]
@@ -306,12 +307,27 @@ def network_forward(sd, batch, *, n_samples=128, kick_in_iter=100000, full_band_
     else:
         observe = deform = pts[0, 0, :][None, :]
     out = {"deform_pts_final": deform, "observe_pts": observe, "bgcolor": batch["bgcolor"]}
+    # flow side path: ALL canonical points warped forward with the PREVIOUS frame's pose (network.py:474-502)
+    flow = bool(batch.get("is_train", False)) and float(batch["time"]) > 0.005
+    if flow:
+        Rs_p, Ts_p = batch["dst_Rs_prev"], batch["dst_Ts_prev"]
+        if iter_val >= pose_kick_in_iter:
+            Rs_p, Ts_p = pose_refine(sd, batch["dst_posevec_prev"], Rs_p, Ts_p)
+        _, _, Rf_p, Tf_p = motion_bases(Rs_p, Ts_p, batch["cnl_gtfms"])
+        cond_p = batch["dst_posevec_prev"][None]
+        if iter_val < kick_in_iter:
+            cond_p = torch.zeros_like(cond_p) * cond_p
+        xd_p, _ = lbs_forward(cnl, Rf_p, Tf_p, vol, batch["cnl_bbox_min_xyz"], batch["cnl_bbox_scale_xyz"])
+        pe_p = hann_embed(xd_p, 6, iter_val, kick_in_iter, full_band_iter)
+        out["deform_pts_prev_final"] = non_rigid_mlp(sd, "non_rigid_forward_mlp.", pe_p, xd_p, cond_p).reshape(pts.shape)
     if stage2:
         rgb, acc, w, depth = raw2outputs_s2(raw, mask, z, rays_d, batch["bgcolor"])
         out.update(rgb=rgb, alpha=acc, depth=depth, weights=w)
     else:
         out.update(human_rgb=torch.sigmoid(raw[..., :3]), human_density=F.relu(raw[..., 3]),
-                   newsmpl_pts=pts, pts_mask=mask[..., 0], z_vals=z, rays_d=rays_d)
+                   newsmpl_pts=pts, pts_mask=mask[..., 0])
+        if not flow:
+            out.update(z_vals=z, rays_d=rays_d)
     out["_x_skel"] = x_skel.reshape(pts.shape)
     out["_cnl_pts"] = cnl.reshape(pts.shape)
     out["_raw"] = raw

@@ -8,11 +8,11 @@ hn = Network(default_cfg(), stage2=False, precision="fp16")
 synth.fill_params_(hn, 0); synth.boost_human_density_(hn); hn = hn.to(dev)
 with torch.no_grad():
     for _ in range(3):
-        hn(**hb)
+        hn(**hb, cycle_outputs=False)
     torch.cuda.synchronize()
     import time
     t0 = time.perf_counter()
     for _ in range(5):
-        hn(**hb)
+        hn(**hb, cycle_outputs=False)
     torch.cuda.synchronize()
     print("ms/step wall", (time.perf_counter() - t0) / 5 * 1e3)

@@ -71,7 +71,7 @@ def render_frame():
         if k > 0:
             kw = dict(hb)
             kw.update(rays=torch.stack([oc[hit], dc[hit]], 0), near=near[:, None], far=far[:, None])
-            out = human(**kw)
+            out = human(**kw, cycle_outputs=False)
             h_rgb[hit], h_den[hit] = out["human_rgb"].reshape(k, S_h, 3), out["human_density"].reshape(k, S_h)
             h_msk[hit], h_pts[hit] = out["pts_mask"].reshape(k, S_h), out["newsmpl_pts"].reshape(k, S_h, 3)
         rgb[c0:c1], _, _ = ops.composite_s3(h["rgb"].contiguous(), h["density"].contiguous(), h["tdist"].contiguous(), h_rgb, h_den,

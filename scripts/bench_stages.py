@@ -87,7 +87,7 @@ for prec in ("fp16", "fp32"):
     synth.boost_human_density_(hn)
     hn = hn.to(dev)
     with torch.no_grad():
-        ms = timeit(lambda: hn(**hb), reps=5)
+        ms = timeit(lambda: hn(**hb, cycle_outputs=False), reps=5)
     print(f"C3 human branch (Network.forward, {n_h} rays x 128 samples, {prec}): {ms:.3f} ms/step = {n_h * 128 / ms / 1e3:.1f} M ray-samples/s")
 
 # ---- C4-style stage-3 chunk, forward only: background (128 proposal + 64 NeRF samples, 256 wide) + human branch (128 samples)

@@ -864,3 +864,44 @@ def test_s1_training_step_reduces_loss(golden):
         losses.append(float(loss))
     assert all(l == l for l in losses)
     assert losses[-1] < losses[0], losses
+
+
+# ----------------------------------------------------------------------------- flow side path / component-factory seam (a22)
+def _load_npz(name):
+    import numpy as np
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")) as z:
+        return {k: (z[k] if z[k].dtype.kind in "US" else torch.from_numpy(np.asarray(z[k]).copy())) for k in z.files}
+
+
+@pytest.mark.parametrize("tag", ["s3", "s2"])
+def test_human_flow_side_path_golden(tag):
+    """Train-mode call with time > 0.005 (S3 network.py:474-502, 609-631) against the unmodified reference's return dict:
+    same key set, deform_pts_prev_final [n, S, 3] from the previous frame's forward motion bases, cycle outputs next to it."""
+    g = _load_npz(f"human_{tag}_flow")
+    net = _human(stage2=(tag == "s2"))
+    b = synth.make_human_batch(24, time=0.5, is_train=True)
+    with torch.no_grad():
+        out = net(**{k: cu(v) for k, v in b.items()})
+    keys = sorted(k for k in out if not k.startswith("_") and k != "bgcolor")
+    assert keys == [str(k) for k in g["out_keys"]], (keys, list(g["out_keys"]))
+    assert out["deform_pts_prev_final"].shape == (24, 128, 3)
+    assert torch.equal(out["observe_pts"].cpu(), g["observe_pts"])
+    # same end-to-end gate as the eval path of this branch (sin(2^9 x) amplifies the warped point's last ulp)
+    assert max_abs(out["deform_pts_prev_final"].cpu(), g["deform_pts_prev_final"]) < 1e-3
+    assert max_abs(out["deform_pts_final"].cpu(), g["deform_pts_final"]) < 1e-3
+    if tag == "s3":
+        assert rel_err(out["human_rgb"].cpu(), g["human_rgb"]) < 5e-3
+    else:
+        assert rel_err(out["rgb"].cpu(), g["rgb"]) < 5e-3
+
+
+def test_component_factory_seam_rejects_foreign_modules():
+    """cfg.<component>.module (S3 component_factory.py:12-40): the reference's default strings are accepted, anything else
+    raises instead of silently running the built-in component."""
+    from hosnerf_b200.human import Cfg
+    cfg = default_cfg()
+    cfg.canonical_mlp = Cfg(dict(cfg.canonical_mlp), module="core.nets.human_nerf.canonical_mlps.mlp_rgb_sigma")
+    Network(cfg)
+    cfg.canonical_mlp = Cfg(dict(cfg.canonical_mlp), module="my_project.canonical_mlps.siren")
+    with pytest.raises(NotImplementedError, match="canonical_mlp"):
+        Network(cfg)

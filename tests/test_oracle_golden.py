@@ -205,6 +205,30 @@ def test_human_s3_jitter(golden):
         assert rel_err(out[k], g[k]) < HUMAN_TOL, (k, rel_err(out[k], g[k]))
 
 
+def _load_flow(tag):
+    import numpy as np
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"human_{tag}_flow.npz")) as z:
+        return {k: (z[k] if z[k].dtype.kind in "US" else torch.from_numpy(np.asarray(z[k]).copy())) for k in z.files}
+
+
+@pytest.mark.parametrize("tag", ["s3", "s2"])
+def test_human_flow_side_path(tag):
+    """Train mode with time > 0.005 (network.py:474-502, 609-631): previous-frame forward warp of all canonical points,
+    and the exact key set of the reference's return dict in that mode."""
+    g = _load_flow(tag)
+    sd = _human_state_dict()
+    b = _human_batch(g, 24, time=0.5, is_train=True)
+    with torch.no_grad():
+        out = HR.network_forward(sd, b, stage2=(tag == "s2"))
+    keys = sorted(k for k in out if not k.startswith("_") and k != "bgcolor")
+    assert keys == [str(k) for k in g["out_keys"]], (keys, list(g["out_keys"]))
+    for k in keys:
+        assert out[k].shape == g[k].shape, k
+        assert rel_err(out[k], g[k]) < HUMAN_TOL, (k, rel_err(out[k], g[k]))
+    assert out["deform_pts_prev_final"].shape == (24, 128, 3)
+
+
 def test_human_s2(golden):
     g = golden("human_s2_eval")
     sd = _human_state_dict()
