@@ -69,6 +69,8 @@ SIGNATURES = {
     "hos_fourier_embed": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f, c_i, c_i, c_f]),
     "hos_lbs_warp": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f]),
     "hos_lbs_forward": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f]),
+    "hos_lbs_warp_backward": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),
+    "hos_lbs_forward_backward": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f, c_f, c_f, c_f]),
     "hos_linear_f32": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_f, c_i, c_f]),
     "hos_linear_f32_ex": (c_i, [c_f, c_i, c_i, c_f, c_i, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_f, c_i, c_f]),
     "hos_head_f32": (c_i, [c_f, c_i, c_i, c_f, c_f, c_l, c_i, c_i, c_fl, c_f, c_f, c_i, c_f]),

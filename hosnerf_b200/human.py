@@ -501,14 +501,130 @@ class Network(nn.Module):
         Ts = torch.cat([dst_Ts[:, 0:1], dst_Ts[:, 1:] + dT], dim=1)
         return Rs, Ts
 
+    # ------------------------------------------------------------------ training forward (autograd)
+    @staticmethod
+    def _motion_bases_autograd(Rs, Ts, cnl_gtfms):
+        """MotionBasisComputer (network_util.py:106-174) with a graph: the 26-bone chain runs on the host (differentiable
+        device <-> host copies), so the pose decoder receives its gradient through the bone maps."""
+        dev = Rs.device
+        Rs, Ts, cg = Rs.cpu(), Ts.cpu(), cnl_gtfms.detach().cpu()
+        nb = Rs.shape[1]
+        local = torch.cat([torch.cat([Rs, Ts[..., None]], dim=-1),
+                           torch.tensor([0., 0., 0., 1.]).expand(1, nb, 1, 4)], dim=-2)            # [1, nb, 4, 4]
+        glob = [local[:, 0]]
+        for i in range(1, nb):
+            glob.append(torch.matmul(glob[SMPL_PARENT[i]], local[:, i]))
+        glob = torch.stack(glob, dim=1).view(-1, 4, 4)
+        cgf = cg.view(-1, 4, 4)
+        back = torch.matmul(cgf, torch.inverse(glob)).view(-1, nb, 4, 4)
+        fwd = torch.matmul(glob, torch.inverse(cgf)).view(-1, nb, 4, 4)
+        return (back[0, :, :3, :3].contiguous().to(dev), back[0, :, :3, 3].contiguous().to(dev),
+                fwd[0, :, :3, :3].contiguous().to(dev), fwd[0, :, :3, 3].contiguous().to(dev))
+
+    def _refined_pose(self, Rs, Ts, posevec, it):
+        """network.py:590-605 on the device, with a graph."""
+        if it < self.cfg.pose_decoder.get("kick_in_iter", 0):
+            return Rs, Ts
+        out = self.pose_decoder(posevec)
+        nb = self.cfg.total_bones - 1
+        Rn = torch.matmul(Rs[:, 1:].reshape(-1, 3, 3), out["Rs"].reshape(-1, 3, 3)).reshape(-1, nb, 3, 3)
+        return torch.cat([Rs[:, 0:1], Rn], dim=1), torch.cat([Ts[:, 0:1], Ts[:, 1:] + out["Ts"]], dim=1)
+
+    def _forward_train(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, near, far, iter_val, rand,
+                       **kwargs):
+        """``Network.forward`` under autograd (training, S3 network.py:574-698 / S2): every parameter receives its gradient.
+        The per-point work runs on the library's kernels through autograd Functions (``train.LbsWarpFn`` / ``LbsForwardFn``:
+        LBS forward + backward kernels; ``train.MlpFn``: tcgen05 layer GEMMs with dgrad / wgrad); encodings, the <= 4-wide
+        activations and the S2 composite are small elementwise torch ops; the per-frame prologue (pose decoder, kinematic
+        chain, volume decoder) is torch with a graph."""
+        from . import train
+        cfg = self.cfg
+        dev = rays.device
+        time = kwargs.get("time", 0.0)
+        flow = float(time) > 0.005
+        it = float(iter_val.reshape(-1)[0]) if isinstance(iter_val, torch.Tensor) else float(iter_val)
+        posevec = dst_posevec[None, ...].float()
+        Rs, Ts = self._refined_pose(dst_Rs[None, ...].float(), dst_Ts[None, ...].float(), posevec, it)
+        Rb, Tb, Rf, Tf = self._motion_bases_autograd(Rs, Ts, cnl_gtfms[None, ...])
+        vol = self.mweight_vol_decoder(motion_weights_priors=motion_weights_priors[None, ...])[0]
+        kick = cfg.non_rigid_motion_mlp.kick_in_iter
+        hann_w = hann_window_weights(self.nr_freqs, it, kick, cfg.non_rigid_motion_mlp.full_band_iter).to(dev)
+        cond = torch.zeros_like(posevec) if it < kick else posevec
+        state_idx = select_state_index(len(self.human_stateembeds), time, self.transitions_times)
+        bbox_min = kwargs["cnl_bbox_min_xyz"].detach().cpu().reshape(-1).tolist()
+        bbox_scale = kwargs["cnl_bbox_scale_xyz"].detach().cpu().reshape(-1).tolist()
+        rays_o, rays_d = rays
+        rays_shape = rays_d.shape
+        rays_o = torch.reshape(rays_o, [-1, 3]).float().contiguous()
+        rays_d = torch.reshape(rays_d, [-1, 3]).float().contiguous()
+        n, S = rays_o.shape[0], cfg.N_samples
+        t_lin = torch.linspace(0., 1., steps=S).to(dev)
+        jitter = None
+        if cfg.perturb > 0.:
+            jitter = (torch.rand(n, S) if rand is None else rand).to(dev, torch.float32).contiguous()
+        z, pts = ops.human_samples(rays_o, rays_d, near.reshape(-1).float().contiguous(), far.reshape(-1).float().contiguous(),
+                                   t_lin, jitter)
+        flat = pts.view(-1, 3)
+
+        def hann_pe(x):
+            f = 2.0 ** torch.arange(self.nr_freqs, device=dev, dtype=torch.float32)
+            ang = x[:, None, :] * f[None, :, None]                                        # [P, F, 3]
+            return (torch.stack([torch.sin(ang), torch.cos(ang)], dim=2) * hann_w[None, :, None, None]).reshape(x.shape[0], -1)
+
+        def fourier_pe(x):
+            f = 2.0 ** torch.arange(self.cnl_freqs, device=dev, dtype=torch.float32)
+            ang = x[:, None, :] * f[None, :, None]
+            return torch.cat([x, torch.stack([torch.sin(ang), torch.cos(ang)], dim=2).reshape(x.shape[0], -1)], dim=-1)
+
+        def nr(mlp, x, c):
+            return x if cfg.ignore_non_rigid_motions else train.non_rigid_mlp_train(mlp, hann_pe(x), c, x)
+
+        x_skel, mask = train.LbsWarpFn.apply(flat, Rb, Tb, vol, bbox_min, bbox_scale)
+        cnl = nr(self.non_rigid_mlp, x_skel, cond)
+        raw = train.canonical_mlp_train(self, fourier_pe(cnl), self.human_stateembeds[state_idx]).view(n, S, 4)
+        mask2 = mask.view(n, S)
+        ret = {}
+        sel = mask.detach() > 0.005
+        if bool(sel.any()):          # cycle side path (network.py:505-536)
+            xd = train.LbsForwardFn.apply(cnl[sel], Rf, Tf, vol, bbox_min, bbox_scale)
+            ret["deform_pts_final"], ret["observe_pts"] = nr(self.non_rigid_forward_mlp, xd, cond), flat[sel]
+        else:
+            ret["deform_pts_final"] = ret["observe_pts"] = pts[0, 0, :][None, :]
+        if flow:                     # previous frame (network.py:474-502, 609-637)
+            pv = kwargs["dst_posevec_prev"][None, ...].float()
+            Rp, Tp = self._refined_pose(kwargs["dst_Rs_prev"][None, ...].float(), kwargs["dst_Ts_prev"][None, ...].float(), pv, it)
+            _, _, Rfp, Tfp = self._motion_bases_autograd(Rp, Tp, cnl_gtfms[None, ...])
+            xp = train.LbsForwardFn.apply(cnl, Rfp, Tfp, vol, bbox_min, bbox_scale)
+            ret["deform_pts_prev_final"] = nr(self.non_rigid_forward_mlp, xp, torch.zeros_like(pv) if it < kick else pv).view(n, S, 3)
+        bgcolor = kwargs.get("bgcolor")
+        if self.stage2:              # S2 network.py:273-299
+            dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], dim=-1) * torch.norm(rays_d[..., None, :], dim=-1)
+            rgb = torch.sigmoid(raw[..., :3])
+            alpha = (1.0 - torch.exp(-F.relu(raw[..., 3]) * dists)) * mask2
+            T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], dim=-1), dim=-1)[:, :-1]
+            w = alpha * T
+            acc = torch.sum(w, -1)
+            ret.update(rgb=torch.sum(w[..., None] * rgb, -2) + (1. - acc[..., None]) * bgcolor.to(dev)[None, :] / 255.,
+                       alpha=acc, depth=torch.sum(w * z, -1), weights=w)
+        else:
+            ret.update(human_rgb=torch.sigmoid(raw[..., :3]), human_density=F.relu(raw[..., 3]), newsmpl_pts=pts, pts_mask=mask2)
+            if not flow:
+                ret.update(z_vals=z, rays_d=rays_d)
+        for k in ret:
+            if k not in ("deform_pts_prev_final", "deform_pts_final", "observe_pts"):
+                ret[k] = torch.reshape(ret[k], list(rays_shape[:-1]) + list(ret[k].shape[1:]))
+        ret["bgcolor"] = bgcolor
+        return ret
+
     def forward(self, rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec=None,
                 near=None, far=None, iter_val=1e7, rand=None, **kwargs):
         if not rays.is_cuda:
             raise RuntimeError("hosnerf_b200.Network: inputs must be CUDA tensors (no CPU fallback)")
         is_train = bool(kwargs.get("is_train", False))
         time = kwargs.get("time", 0.0)
-        if is_train and torch.is_grad_enabled():
-            raise NotImplementedError("hosnerf_b200 kernels are forward-only in this round; call under torch.no_grad()")
+        if is_train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(rays, dst_Rs, dst_Ts, cnl_gtfms, motion_weights_priors, dst_posevec, near, far,
+                                       iter_val, rand, **kwargs)
         flow = is_train and float(time) > 0.005           # flow side path: previous-frame forward warp (network.py:474-502)
         precision = self.precision or _m._DEFAULT_PRECISION
         cfg = self.cfg

@@ -166,6 +166,29 @@ def lbs_warp(pts, R, T, vol, bbox_min, bbox_scale):
     return x, m
 
 
+def lbs_warp_backward(pts, R, T, vol, bbox_min, bbox_scale, g_x, g_mask=None):
+    """-> (g_vol like vol, g_R [bones,3,3], g_T [bones,3]) for upstream g_x [P,3] (and g_mask [P])."""
+    for t, nm in ((pts, "pts"), (R, "R"), (T, "T"), (vol, "vol"), (g_x, "g_x"), (g_mask, "g_mask")):
+        _chk(t, nm)
+    p, bones, g = pts.numel() // 3, R.shape[0], vol.shape[-1]
+    g_vol, g_R, g_T = torch.zeros_like(vol), torch.zeros_like(R), torch.zeros_like(T)
+    _lib.call_unless_empty(p, "hos_lbs_warp_backward", _p(pts), _p(R), _p(T), _p(vol), _host3(bbox_min), _host3(bbox_scale), p, bones,
+                           g, _p(g_x), _p(g_mask), _p(g_vol), _p(g_R), _p(g_T), _stream())
+    return g_vol, g_R, g_T
+
+
+def lbs_forward_backward(cnl_pts, R_fwd, T_fwd, vol, bbox_min, bbox_scale, g_x):
+    """-> (g_vol, g_R, g_T, g_pts [P,3]) of the forward warp."""
+    for t, nm in ((cnl_pts, "cnl_pts"), (R_fwd, "R_fwd"), (T_fwd, "T_fwd"), (vol, "vol"), (g_x, "g_x")):
+        _chk(t, nm)
+    p, bones, g = cnl_pts.numel() // 3, R_fwd.shape[0], vol.shape[-1]
+    g_vol, g_R, g_T = torch.zeros_like(vol), torch.zeros_like(R_fwd), torch.zeros_like(T_fwd)
+    g_pts = torch.zeros(p, 3, device=cnl_pts.device, dtype=_F32)
+    _lib.call_unless_empty(p, "hos_lbs_forward_backward", _p(cnl_pts), _p(R_fwd), _p(T_fwd), _p(vol), _host3(bbox_min),
+                           _host3(bbox_scale), p, bones, g, _p(g_x), _p(g_vol), _p(g_R), _p(g_T), _p(g_pts), _stream())
+    return g_vol, g_R, g_T, g_pts
+
+
 def lbs_forward(cnl_pts, R_fwd, T_fwd, vol, bbox_min, bbox_scale):
     _chk(cnl_pts, "cnl_pts"), _chk(R_fwd, "R_fwd"), _chk(T_fwd, "T_fwd"), _chk(vol, "vol")
     p = cnl_pts.numel() // 3

@@ -267,3 +267,180 @@ def lossfun_distortion(t, w):
 
 def lossfun_outer_sum(t, w, t_env, w_env):
     return _OuterSumFn.apply(t, w, t_env, w_env)
+
+
+# ============================================================================ human-object branch (S2 / S3 network.py)
+class LbsWarpFn(torch.autograd.Function):
+    """``Network._sample_motion_fields`` (network.py:304-354): forward and backward on the library's kernels.  Gradient to
+    the motion-weight volume and the bone maps; the sample points are data."""
+
+    @staticmethod
+    def forward(ctx, pts, R, T, vol, bbox_min, bbox_scale):
+        pts, R, T, vol = pts.contiguous(), R.contiguous(), T.contiguous(), vol.contiguous()
+        ctx.save_for_backward(pts, R, T, vol)
+        ctx.bbox = (bbox_min, bbox_scale)
+        return ops.lbs_warp(pts, R, T, vol, bbox_min, bbox_scale)
+
+    @staticmethod
+    def backward(ctx, g_x, g_m):
+        pts, R, T, vol = ctx.saved_tensors
+        g_x = torch.zeros(pts.numel() // 3, 3, device=pts.device) if g_x is None else g_x.contiguous().float()
+        g_vol, g_R, g_T = ops.lbs_warp_backward(pts, R, T, vol, ctx.bbox[0], ctx.bbox[1], g_x,
+                                                None if g_m is None else g_m.contiguous().float())
+        return None, g_R, g_T, g_vol, None, None
+
+
+class LbsForwardFn(torch.autograd.Function):
+    """``Network._sample_motion_fields_forward`` (network.py:357-398) of the cycle / flow side paths: gradient to the volume, the
+    forward bone maps and the canonical points."""
+
+    @staticmethod
+    def forward(ctx, cnl_pts, R, T, vol, bbox_min, bbox_scale):
+        cnl_pts, R, T, vol = cnl_pts.contiguous(), R.contiguous(), T.contiguous(), vol.contiguous()
+        ctx.save_for_backward(cnl_pts, R, T, vol)
+        ctx.bbox = (bbox_min, bbox_scale)
+        return ops.lbs_forward(cnl_pts, R, T, vol, bbox_min, bbox_scale)[0]
+
+    @staticmethod
+    def backward(ctx, g_x):
+        pts, R, T, vol = ctx.saved_tensors
+        g_vol, g_R, g_T, g_pts = ops.lbs_forward_backward(pts, R, T, vol, ctx.bbox[0], ctx.bbox[1], g_x.contiguous().float())
+        return g_pts, g_R, g_T, g_vol, None, None
+
+
+def _pad8(t):
+    """fp16 copy of a matrix with its column count padded to a multiple of 8 (16-byte row pitch for the tensor maps)."""
+    k = t.shape[1]
+    kp = (k + 7) // 8 * 8
+    out = torch.zeros(t.shape[0], kp, device=t.device, dtype=_F16)
+    out[:, :k] = t
+    return out
+
+
+class MlpFn(torch.autograd.Function):
+    """A ReLU MLP with one skip concatenation and a <= 4-wide linear head, forward and backward on the tensor-core layer
+    kernels: the canonical MLP (mlp_rgb_sigma.py:16-58) and the non-rigid motion MLPs (mlp_offset.py:16-70).
+
+    ``x`` [P, kx] is the per-point encoded input (differentiable); per-call constants that the reference concatenates to
+    it (pose condition code, state embedding) ride in the bias of the layers that read them - ``const`` [kc] with its
+    column range in those layers' weights - and receive their gradient from the bias gradient.
+    spec: column ranges inside the weights:  first layer ``x_cols`` / ``c_cols``;  skip layer (index ``skip``) ``sh_cols``
+    (hidden part), ``sx_cols`` (encoded input), ``sc_cols`` (constant part or None).
+    Returns the head's pre-activation [P, n_out] (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, const, spec, *params):
+        nl = (len(params) - 2) // 2
+        Ws, bs = params[0:2 * nl:2], params[1:2 * nl:2]
+        Wo, bo = params[-2], params[-1]
+        width = Ws[0].shape[0]
+        kx = x.shape[1]
+        c = const.detach().reshape(-1).float()
+        x16 = _pad8(x.detach())
+        hs, h = [], None
+
+        def cbias(W, b, cols):
+            return (b if cols is None else b + W[:, cols[0]:cols[1]] @ c).contiguous()
+        for i in range(nl):
+            W, b = Ws[i].detach(), bs[i].detach()
+            if i == 0:
+                (xa, xb) = spec["x_cols"]
+                h = ops.gemm_tma(x16, _pad8(W[:, xa:xb]), width, bias=cbias(W, b, spec["c_cols"]), relu=True)[0]
+            elif i == spec["skip"]:
+                (ha, hb), (xa, xb) = spec["sh_cols"], spec["sx_cols"]
+                h = ops.gemm_tma(h, _h(W[:, ha:hb]), width, a1=x16, w1=_pad8(W[:, xa:xb]), bias=cbias(W, b, spec["sc_cols"]),
+                                 relu=True)[0]
+            else:
+                h = ops.gemm_tma(h, _h(W), width, bias=b.contiguous(), relu=True)[0]
+            hs.append(h)
+        # the head is <= 4 wide: evaluated from the fp16 activations in fp32 (SIMT kernel)
+        out = ops.head_f32(h.float(), Wo.detach().contiguous(), bo.detach().contiguous(), post=0)
+        ctx.spec, ctx.nl, ctx.kx = spec, nl, kx
+        ctx.hs, ctx.x16, ctx.c = hs, x16, c
+        ctx.params = params
+        ctx.need_x = x.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        spec, nl = ctx.spec, ctx.nl
+        params = ctx.params
+        Ws = params[0:2 * nl:2]
+        Wo = params[-2]
+        hs, x16, c = ctx.hs, ctx.x16, ctx.c
+        width = Ws[0].shape[0]
+        kx, kxp = ctx.kx, x16.shape[1]
+        dev = g_out.device
+        g_out = g_out.contiguous().float()
+        scale = _loss_scale(g_out)
+        inv = 1.0 / scale
+        g = (g_out * scale).contiguous()
+        gWo = torch.zeros(Wo.shape[0], width, device=dev)
+        ops.colsum_f16(hs[-1], gWo, g=g)
+        gbo = g.sum(0)
+        g_z = ops.head_dgrad(g, Wo.detach().contiguous(), width, mask=hs[-1])
+        gWs, gbs = [None] * nl, [None] * nl
+        g_c = torch.zeros_like(c)
+        g_x = torch.zeros(x16.shape[0], kxp, device=dev) if ctx.need_x else None
+
+        def input_part(W, gW, gb, x_cols, c_cols, want_colsum):
+            nonlocal g_c, g_x
+            xa, xb = x_cols
+            xg = torch.zeros(width, kxp, device=dev)
+            ops.wgrad_tma(g_z, x16, xg, colsum=gb if want_colsum else None)
+            gW[:, xa:xb] = xg[:, :kx]
+            if c_cols is not None:       # the constant rides in the bias: rank-1 weight gradient, and its own gradient
+                gW[:, c_cols[0]:c_cols[1]] = torch.outer(gb, c)
+                g_c += W[:, c_cols[0]:c_cols[1]].t() @ gb
+            if g_x is not None:
+                g_x += ops.gemm_tma(g_z, _pad8(W[:, xa:xb]), kxp, mode=1, out16=False, out32=True)[2]
+        for i in range(nl - 1, -1, -1):
+            W = Ws[i].detach()
+            gW = torch.zeros_like(W, dtype=torch.float32)
+            gb = torch.zeros(width, device=dev)
+            if i == 0:
+                input_part(W, gW, gb, spec["x_cols"], spec["c_cols"], True)
+            elif i == spec["skip"]:
+                ha, hb = spec["sh_cols"]
+                hg = torch.zeros(width, width, device=dev)
+                ops.wgrad_tma(g_z, hs[i - 1], hg, colsum=gb)
+                gW[:, ha:hb] = hg
+                input_part(W, gW, gb, spec["sx_cols"], spec["sc_cols"], False)
+                g_z = ops.gemm_tma(g_z, _h(W[:, ha:hb]), width, mode=1, mask=hs[i - 1])[0]
+            else:
+                ops.wgrad_tma(g_z, hs[i - 1], gW, colsum=gb)
+                g_z = ops.gemm_tma(g_z, _h(W), width, mode=1, mask=hs[i - 1])[0]
+            gWs[i], gbs[i] = gW * inv, gb * inv
+        out = [None if g_x is None else (g_x[:, :kx] * inv), g_c * inv, None]
+        for i in range(nl):
+            out += [gWs[i], gbs[i]]
+        out += [gWo * inv, gbo * inv]
+        ctx.hs = ctx.x16 = None
+        return tuple(out)
+
+
+def canonical_mlp_train(net, pe, emb):
+    """CanonicalMLP (mlp_rgb_sigma.py:16-58) on pe [P, 63] with the state embedding ``emb`` [64]: raw [P, 4]."""
+    m = net.cnl_mlp
+    lins = m.linears()
+    kpe, kin, w = pe.shape[1], m.input_ch, m.mlp_width
+    spec = dict(x_cols=(0, kpe), c_cols=(kpe, kin), skip=m.skip_layer_indices()[0], sx_cols=(0, kpe), sc_cols=(kpe, kin),
+                sh_cols=(kin, kin + w))
+    params = []
+    for lin in lins:
+        params += [lin.weight, lin.bias]
+    params += [m.output_linear[0].weight, m.output_linear[0].bias]
+    return MlpFn.apply(pe, emb, spec, *params)
+
+
+def non_rigid_mlp_train(mlp, pe, cond, xyz):
+    """NonRigidMotionMLP (mlp_offset.py:16-70): xyz + offset(pe, cond)."""
+    lins = mlp.linears()
+    cc, kpe, w = mlp.condition_code_size, mlp.pos_embed_size, mlp.mlp_width
+    spec = dict(x_cols=(cc, cc + kpe), c_cols=(0, cc), skip=mlp.skip_layer_indices()[0], sh_cols=(0, w), sx_cols=(w, w + kpe),
+                sc_cols=None)
+    params = []
+    for lin in lins[:-1]:
+        params += [lin.weight, lin.bias]
+    params += [lins[-1].weight, lins[-1].bias]
+    return xyz + MlpFn.apply(pe, cond.reshape(-1), spec, *params)

@@ -905,3 +905,34 @@ def test_component_factory_seam_rejects_foreign_modules():
     cfg.canonical_mlp = Cfg(dict(cfg.canonical_mlp), module="my_project.canonical_mlps.siren")
     with pytest.raises(NotImplementedError, match="canonical_mlp"):
         Network(cfg)
+
+
+def test_human_s2_training_gradients_golden():
+    """Backward of the human-object branch (train.LbsWarpFn / LbsForwardFn / MlpFn + torch prologue) against the gradients
+    autograd computes through the UNMODIFIED stage-2 reference (tests/golden/make_golden_backward_human.py): surrogate
+    objective mean(rgb) + 0.1 cycle, every parameter group - canonical / non-rigid / forward non-rigid MLPs, state
+    embedding, motion-weight volume decoder, pose decoder."""
+    g = _load_npz("human_s2_backward")
+    net = _human(stage2=True)
+    b = synth.make_human_batch(12)
+    b["is_train"] = True
+    res = net(**{k: cu(v) for k, v in b.items()})
+    assert res["rgb"].requires_grad and res["observe_pts"].shape[0] == int(g["n_cycle_pts"])
+    cyc = torch.mean(torch.sum((res["observe_pts"] - res["deform_pts_final"]) ** 2, 1) / 2.0)
+    loss = res["rgb"].mean() + 0.1 * cyc
+    assert abs(float(loss.detach()) - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))
+    loss.backward()
+    worst = {}
+    for name, p in net.named_parameters():
+        if f"gnone__{name}" in g:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, name
+        gn, ref = float(p.grad.double().norm()), float(g[f"gnorm__{name}"])
+        amax = max(float(g[f"gabsmax__{name}"]), 1e-20)
+        worst[name] = (abs(gn - ref) / max(ref, 1e-20), float((p.grad.reshape(-1)[:16].cpu() - g[f"ghead__{name}"]).abs().max()) / amax, ref)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_human_s2_backward.json", "w") as f:
+        json.dump(worst, f, indent=1)
+    bad = {k: v for k, v in worst.items() if not (v[0] < 5e-2 and v[1] < 1e-1)}      # norms 5 %, single leading entries 10 % of the largest (fp16 gradients)
+    assert not bad, bad
