@@ -42,3 +42,58 @@ def cycle_loss(net_output: dict):
     if a.shape != b.shape:
         raise RuntimeError("hosnerf_b200.cycle_loss: observe_pts and deform_pts_final differ in shape")
     return ops.reduce_scaled(a, 0.5 / max(a.shape[0], 1), y=b)
+
+
+def _composite_ray_set(samples, z, rays_d, mask):
+    """S3 ``_raw2outputs`` (model.py:73-99) on depth-ordered samples [m, S, 4] (rgb in [0,1], sigma >= 0): torch ops with a
+    graph - the [rays, 192] tensors of a training chunk are a few hundred kilobytes."""
+    dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], dim=-1) * torch.norm(rays_d[..., None, :], dim=-1)
+    alpha = (1.0 - torch.exp(-samples[..., 3] * dists)) * mask
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], dim=-1), dim=-1)[:, :-1]
+    w = alpha * T
+    return torch.sum(w[..., None] * samples[..., :3], -2), w
+
+
+def train_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dict, newsmpl_to_scale_world,
+                        near_bkg: float = 0.1, far_bkg: float = 1e6, train_frac: float = 1.0, randomized: bool = True,
+                        thre_fg: float = 5e-3, rands=None):
+    """The differentiable body of the stage-3 ``training_step`` (S3 model.py:1501-1596): background branch (one
+    ``train.RenderFn`` node: per-level weights and the final level's per-sample density / rgb carry the gradient), human-object
+    branch (``Network.forward`` under autograd), depth merge + composite.  The merge itself (sort of 64 + 128 depths per
+    foreground ray, gather, transmittance product) is a handful of torch ops on [rays, 192] tensors with autograd; the forward
+    kernel ``hos_composite_s3`` is the eval path.  Returns dict(rgb [n,3], idx_fg, human_weights [n_fg, S_h], ray_history,
+    net_output)."""
+    _, ray_history = bkg_model(batch_bkg, train_frac, randomized, True, near_bkg, far_bkg, rands=rands)
+    kw = dict(batch_human)
+    kw["is_train"] = True
+    net_output = human_net(**kw)
+    h = ray_history[-1]
+    n = h["density"].shape[0]
+    s_h = net_output["human_density"].shape[-1]
+    rays_o, rays_d = batch_bkg["rays_o"].float(), batch_bkg["rays_d"].float()
+    M = newsmpl_to_scale_world.to(rays_o.device).float()
+    pts = net_output["newsmpl_pts"].reshape(n, s_h, 3)
+    world = torch.einsum("ji,bni->bnj", M, torch.cat([pts, torch.ones_like(pts[..., :1])], -1))[..., :3]
+    if bool(torch.any(torch.abs(rays_d) < 1e-5)):
+        raise NotImplementedError("hosnerf_b200.train_hosnerf_chunk: axis-aligned ray directions (the reference's per-axis branch, "
+                                  "S3 model.py:1528-1543) are handled by the eval kernel only")
+    zh = torch.mean((world - rays_o[:, None, :]) / (rays_d[:, None, :] + 1e-10), dim=-1)            # depth along the bkg ray
+    mask = net_output["pts_mask"].reshape(n, s_h)
+    idx_fg = torch.sum(mask, dim=-1) > thre_fg
+    zb = h["tdist"][..., :-1]
+    bkg = torch.cat([h["rgb"], h["density"][..., None]], -1)
+    hum = torch.cat([net_output["human_rgb"].reshape(n, s_h, 3), net_output["human_density"].reshape(n, s_h, 1)], -1)
+    rgb = torch.zeros(n, 3, device=rays_o.device)
+    human_w = torch.zeros(0, s_h, device=rays_o.device)
+    if bool(idx_fg.any()):
+        z_sorted, order = torch.sort(torch.cat([zb[idx_fg], zh[idx_fg].detach()], -1), -1)
+        both = torch.gather(torch.cat([bkg[idx_fg], hum[idx_fg]], 1), 1, order[..., None].expand(-1, -1, 4))
+        m = torch.gather(torch.cat([torch.ones_like(zb[idx_fg]), mask[idx_fg]], -1), 1, order)
+        rgb_fg, w_fg = _composite_ray_set(both, z_sorted, rays_d[idx_fg], m)
+        rgb = rgb.index_put((torch.nonzero(idx_fg)[:, 0],), rgb_fg)
+        human_w = w_fg[order >= zb.shape[1]].reshape(-1, s_h)
+    if bool((~idx_fg).any()):
+        ib = ~idx_fg
+        rgb_bg, _ = _composite_ray_set(bkg[ib], zb[ib], rays_d[ib], torch.ones_like(zb[ib]))
+        rgb = rgb.index_put((torch.nonzero(ib)[:, 0],), rgb_bg)
+    return {"rgb": rgb, "idx_fg": idx_fg, "human_weights": human_w, "ray_history": ray_history, "net_output": net_output}

@@ -936,3 +936,55 @@ def test_human_s2_training_gradients_golden():
         json.dump(worst, f, indent=1)
     bad = {k: v for k, v in worst.items() if not (v[0] < 5e-2 and v[1] < 1e-1)}      # norms 5 %, single leading entries 10 % of the largest (fp16 gradients)
     assert not bad, bad
+
+
+def test_stage3_training_chunk_gradients_vs_oracle():
+    """Complete HOSNeRF training chunk (S3 model.py:1501-1596; C4's fwd + bwd with the mean(rgb) surrogate): background
+    RenderFn + human branch under autograd + depth-merge composite, against autograd through the oracle pipeline on the CPU
+    (itself pinned to the reference's gradients, tests/test_backward_contract_cpu.py).  Per-parameter gradient norms, both
+    branches; proposal MLPs receive no gradient from this objective (stop_level_grad)."""
+    from hosnerf_b200 import train_hosnerf_chunk
+    n = 96
+    hb = synth.make_human_batch(n)
+    Mw = synth.random_rigid()
+    ro, rd = hb["rays"][0], hb["rays"][1]
+    ro_w = (Mw[:3, :3] @ ro.T).T + Mw[:3, 3]
+    rd_w = (Mw[:3, :3] @ rd.T).T
+    bb = {"rays_o": ro_w, "rays_d": rd_w, "viewdirs": rd_w / rd_w.norm(dim=-1, keepdim=True),
+          "radii": torch.full((n, 1), 1e-3), "times": torch.tensor(0.0)}
+    bkg = MipNeRF360("/nonexistent", opaque_background=True, nerf_netwidth=256, stage3=True)
+    synth.fill_params_(bkg, 0)
+    human = _human()
+    pb, ph = dict(bkg.named_parameters()), dict(human.named_parameters())
+    sd_b = {k: v.detach().cpu().clone().requires_grad_(k in pb and v.is_floating_point()) for k, v in bkg.state_dict().items()}
+    sd_h = {k: v.detach().cpu().clone().requires_grad_(k in ph and v.is_floating_point()) for k, v in human.state_dict().items()}
+    _, hist = R.mip360_forward(sd_b, bb, 1.0, False, 0.1, 1e6, stage3=True)
+    ho = HR.network_forward(sd_h, hb)
+    ref_rgb, ref_fg, _, _ = HR.composite_s3(hist[-1]["rgb"], hist[-1]["density"], hist[-1]["tdist"], ho["human_rgb"],
+                                            ho["human_density"], ho["pts_mask"], ho["newsmpl_pts"], Mw, ro_w, rd_w)
+    ref_rgb.mean().backward()
+    bkg = bkg.to(DEV)
+    out = train_hosnerf_chunk(bkg, human, {k: cu(v) for k, v in bb.items()}, {k: cu(v) for k, v in hb.items()}, Mw, randomized=False)
+    assert torch.equal(out["idx_fg"].cpu(), ref_fg)
+    assert max_abs(out["rgb"].detach().cpu(), ref_rgb.detach()) < 5e-3
+    out["rgb"].mean().backward()
+    worst = {}
+    for tag, mod, sd in (("bkg", bkg, sd_b), ("human", human, sd_h)):
+        for name, p in mod.named_parameters():
+            rg = sd[name].grad
+            rn = 0.0 if rg is None else float(rg.double().norm())
+            gn = 0.0 if p.grad is None else float(p.grad.double().norm())
+            worst[f"{tag}.{name}"] = (gn, rn)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_s3_backward.json", "w") as f:
+        json.dump(worst, f, indent=1)
+    scale = max(r for _, r in worst.values())
+    assert scale > 0
+    n_live = 0
+    for k, (gn, rn) in worst.items():
+        if rn < 1e-6 * scale:                 # (numerically) no gradient in the reference graph either
+            assert gn < 1e-3 * scale, (k, gn, rn)
+            continue
+        n_live += 1
+        assert abs(gn - rn) < 5e-2 * rn + 1e-5 * scale, (k, gn, rn)
+    assert n_live > 60
