@@ -318,10 +318,31 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "fp32", "fp16x3"])
     ap.add_argument("--no-extras", action="store_true", help="skip the parity / accurate-mode / training-step sub-measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3", "C4", "C5"],
+                    help="C2 (default, the headline): stage-1 render_rays; C3 / C4 / C5: see bench_configs.py")
     ap.add_argument("--mlp-variant", type=int, default=0, help="A/B: 0 auto, 1 single-CTA MLP kernel, 2 cluster-pair kernel")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.config == "C3":
+            if int(os.environ.get("RANK", "0")) == 0:
+                import bench_configs
+                cb = bench_configs.c3_cpu(1024)
+                print(json.dumps({"impl": "reference", "metric": "ray_samples_per_s", "value": cb["value"], "unit": cb["unit"],
+                                  "n_gpus": args.gpus, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                                  "config": {"workload": "C3 (bounded sample)"}, "cpu_baseline": cb,
+                                  "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            return
         return run_reference(args)
+    if args.config != "C2":
+        import bench_configs
+        line = {"C3": bench_configs.run_c3, "C4": bench_configs.run_c4, "C5": bench_configs.run_c5}[args.config](args, peaks, ClockSampler)
+        if line is not None:
+            print(json.dumps(line))
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     import torch.distributed as dist
     from hosnerf_b200 import LitMipNeRF360, _lib, ops, synth
