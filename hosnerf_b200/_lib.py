@@ -61,6 +61,7 @@ SIGNATURES = {
     "hos_device_check": (c_i, [c_i]),
     "hos_max_dilate": (c_i, [c_f, c_f, c_i, c_i, c_fl, c_fl, c_fl, c_f, c_f, c_f]),
     "hos_sample_intervals": (c_i, [c_f, c_f, c_f, c_f, c_i, c_fl, c_i, c_i, c_i, c_fl, c_fl, c_f, c_f, c_f, c_f]),
+    "hos_invert_cdf": (c_i, [c_f, c_f, c_f, c_f, c_i, c_fl, c_i, c_i, c_i, c_fl, c_fl, c_f, c_f, c_f, c_f]),
     "hos_resample_level": (c_i, [c_f, c_f, c_i, c_i, c_i, c_fl, c_fl, c_fl, c_f, c_f, c_i, c_fl, c_i, c_fl,
                                  c_fl, c_fl, c_fl, c_f, c_f, c_f]),
     "hos_human_samples": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f]),

@@ -279,6 +279,24 @@ sample_intervals_kernel(const float* __restrict__ t, const float* __restrict__ l
              idx_out ? idx_out + (size_t)ray * S : nullptr);
 }
 
+// invert_cdf / sorted_interp alone (S1 helper.py:175-196) on a CDF given by the caller: the integer part of the sampler
+// (interval index per sample) separated from the floating-point softmax that produces the CDF.
+__global__ void __launch_bounds__(kSamplerThreads)
+invert_cdf_kernel(const float* __restrict__ t, const float* __restrict__ cw, const float* __restrict__ u_base,
+                  const float* __restrict__ jitter, int jitter_cols, float max_jitter, int M, int S, float lo, float hi,
+                  float* __restrict__ t_out, float* __restrict__ centers_out, int32_t* __restrict__ idx_out) {
+  __shared__ SamplerSmem sm;
+  const int ray = blockIdx.x;
+  for (int j = threadIdx.x; j <= M; j += blockDim.x) {
+    sm.knots[j] = t[(size_t)ray * (M + 1) + j];
+    sm.cw[j] = cw[(size_t)ray * (M + 1) + j];
+  }
+  __syncthreads();
+  invert_ray(sm, 0, M, u_base, jitter ? jitter + (size_t)ray * jitter_cols : nullptr, jitter_cols, max_jitter, S, lo, hi,
+             t_out + (size_t)ray * (S + 1), centers_out ? centers_out + (size_t)ray * S : nullptr,
+             idx_out ? idx_out + (size_t)ray * S : nullptr);
+}
+
 // One resampling step of MipNeRF360.forward (S1 model.py:362-408), fused.
 __global__ void __launch_bounds__(kSamplerThreads, 8)
 resample_level_kernel(const float* __restrict__ sdist, const float* __restrict__ weights, int M_in,
@@ -378,6 +396,19 @@ int hos_sample_intervals(const float* t, const float* logits, const float* u_bas
   if (N == 0) return HOS_OK;
   sample_intervals_kernel<<<N, kSamplerThreads, 0, (cudaStream_t)stream>>>(
       t, logits, u_base, jitter, jitter_cols, max_jitter, M, S, dom_lo, dom_hi, t_out, centers_out, idx_out);
+  HOS_LAUNCH_CHECK();
+  return HOS_OK;
+}
+
+int hos_invert_cdf(const float* t, const float* cw, const float* u_base, const float* jitter, int jitter_cols, float max_jitter,
+                   int N, int M, int S, float dom_lo, float dom_hi, float* t_out, float* centers_out, int32_t* idx_out, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(t && cw && u_base && t_out, "hos_invert_cdf: null pointer");
+  HOS_REQUIRE(N >= 0 && M >= 1 && M + 1 <= kMaxKnots && S >= 2 && S <= kMaxKnots, "hos_invert_cdf: bad M / S (M=%d S=%d)", M, S);
+  HOS_REQUIRE(!jitter || jitter_cols == 1 || jitter_cols == S, "hos_invert_cdf: jitter_cols must be 1 or S");
+  if (N == 0) return HOS_OK;
+  invert_cdf_kernel<<<N, kSamplerThreads, 0, (cudaStream_t)stream>>>(t, cw, u_base, jitter, jitter_cols, max_jitter, M, S, dom_lo,
+                                                                      dom_hi, t_out, centers_out, idx_out);
   HOS_LAUNCH_CHECK();
   return HOS_OK;
 }

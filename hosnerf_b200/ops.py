@@ -64,6 +64,20 @@ def sample_intervals(t, logits, u_base, jitter, max_jitter, lo, hi, want_aux=Fal
     return (out, centers, idx) if want_aux else out
 
 
+def invert_cdf(t, cw, u_base, jitter, max_jitter, lo, hi):
+    """helper.invert_cdf on a given CDF cw [N,M+1] -> (t_out [N,S+1], centers [N,S], idx int32 [N,S])."""
+    _chk(t, "t"), _chk(cw, "cw"), _chk(u_base, "u_base"), _chk(jitter, "jitter")
+    n, m1 = cw.shape
+    s = u_base.numel()
+    out = torch.empty(n, s + 1, device=t.device, dtype=_F32)
+    centers = torch.empty(n, s, device=t.device, dtype=_F32)
+    idx = torch.empty(n, s, device=t.device, dtype=torch.int32)
+    jc = 0 if jitter is None else jitter.shape[-1]
+    _lib.call_unless_empty(n, "hos_invert_cdf", _p(t), _p(cw), _p(u_base), _p(jitter), jc, max_jitter, n, m1 - 1, s, lo, hi,
+                           _p(out), _p(centers), _p(idx), _stream())
+    return out, centers, idx
+
+
 def resample_level(sdist, weights, dilate, dilation, anneal, padding, u_base, jitter, max_jitter,
                    lo, hi, s_near, s_far):
     _chk(sdist, "sdist"), _chk(weights, "weights"), _chk(u_base, "u_base"), _chk(jitter, "jitter")

@@ -103,6 +103,31 @@ def test_interval_indices_bit_exact():
     assert rel_err(out.cpu(), ref) < 1e-4
 
 
+def test_invert_cdf_bit_exact_on_the_reference_cdf():
+    """The integer gate of the north star ("bit-exact for sample indices"), on GENERAL distributions: given the reference's
+    own CDF (torch CPU softmax + cumsum of random, partly empty logits) hos_invert_cdf reproduces every interval index, every
+    centre and every output position bit for bit - deterministic and randomised (single / per-sample jitter) quantiles.
+    What hos_sample_intervals adds on top is only the fp32 softmax: ATen's CPU softmax uses a vectorised approximate exp whose
+    rounding depends on the host ISA (AVX2 / AVX-512 builds differ from each other and from a correctly rounded exp in up to
+    ~80 % of the entries at the 1e-6 level), so the end-to-end test above can only ask for > 99.95 % equal indices."""
+    gen = torch.Generator().manual_seed(11)
+    n, m, s = 1024, 190, 64
+    logits = torch.randn(n, m, generator=gen) * 3.0
+    logits[torch.rand(n, m, generator=gen) < 0.15] = -torch.inf         # empty bins (S1 model.py:390-394)
+    t = torch.sort(torch.rand(n, m + 1, generator=gen), -1).values
+    t[:, 0], t[:, -1] = 0.0, 1.0
+    cw = R.cdf_from_logits(logits)
+    ub, mj = u_base_rand(s)
+    cases = [(u_base_det(s), None, 0.0, {}), (ub, torch.rand(n, 1, generator=gen), mj, dict(randomized=True, single_jitter=True)),
+             (ub, torch.rand(n, s, generator=gen), mj, dict(randomized=True, single_jitter=False))]
+    for u_b, jit, mjit, kw in cases:
+        ref, aux = R.sample_intervals(t, logits, s, 0.0, 1.0, rand=jit, return_aux=True, **kw)
+        out, centers, idx = ops.invert_cdf(cu(t), cu(cw), cu(u_b), None if jit is None else cu(jit), mjit, 0.0, 1.0)
+        assert torch.equal(idx.cpu().long(), aux["idx"])
+        assert torch.equal(centers.cpu(), aux["centers"])
+        assert torch.equal(out.cpu(), ref)
+
+
 def test_sampler_search_bit_exact_given_cdf():
     """The search + interpolation arithmetic itself is bit-exact: feed a one-hot-free CDF through
     logits = log(p) where p are dyadic rationals that sum to exactly 1 (softmax reproduces them)."""
