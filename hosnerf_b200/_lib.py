@@ -66,6 +66,7 @@ SIGNATURES = {
                                  c_fl, c_fl, c_fl, c_f, c_f, c_f]),
     "hos_human_samples": (c_i, [c_f, c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_f, c_f, c_f]),
     "hos_ipe_features": (c_i, [c_f, c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_f, c_i, c_i, c_f, c_f, c_f]),
+    "hos_ipe_from_gaussians": (c_i, [c_f, c_f, c_f, c_l, c_i, c_i, c_i, c_f, c_i, c_f]),
     "hos_pos_enc": (c_i, [c_f, c_i, c_i, c_i, c_i, c_f, c_f]),
     "hos_fourier_embed": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f, c_i, c_i, c_f]),
     "hos_lbs_warp": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_hp, c_l, c_i, c_i, c_f, c_f, c_f]),
@@ -84,8 +85,8 @@ SIGNATURES = {
     "hos_mlp_forward": (c_i, [C.c_void_p, c_f, c_l, c_f, c_i, c_f, c_f, c_f, c_f]),
     "hos_mlp_set_ipe_input": (c_i, [C.c_void_p, c_i]),
     "hos_mlp_forward_ipe": (c_i, [C.c_void_p, c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_f, c_i, c_f, c_f, c_f]),
-    "hos_mlp_debug_timeline": (c_i, [c_f]),
-    "hos_mlp_set_variant": (c_i, [c_i]),
+    "hos_mlp_debug_timeline": (c_i, [C.c_void_p, c_f]),
+    "hos_mlp_set_variant": (c_i, [C.c_void_p, c_i]),
     "hos_pack_rows_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f]),
     "hos_gemm_create": (C.c_void_p, [c_i, c_i, c_i, c_i, c_i]),
     "hos_ipe_features_fast": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_f, c_f]),

@@ -1466,10 +1466,10 @@ struct hos_mlp {
   int pair_stages = 0;     // depth of its weight ring
   int max_clusters = 0;    // co-resident 2-CTA clusters (persistent grid of the pair kernel)
   int ipe_perm = 0;        // weights packed for the fused-IPE column order
+  int variant = 0;         // kernel selection of THIS handle: 0 automatic, 1 single-CTA kernel, 2 cluster-pair kernel
+  long long* timeline = nullptr;   // optional debug buffer of THIS handle (hos_mlp_debug_timeline)
 };
 
-// 0: pick automatically (pair kernel when the program supports it), 1: single-CTA kernel, 2: pair kernel (error if unsupported)
-static int g_mlp_variant = 0;
 
 extern "C" {
 
@@ -1638,8 +1638,6 @@ int hos_mlp_set_head(hos_mlp_t* m, int head, const float* W, const float* b, voi
 
 int hos_mlp_in_kblocks(const hos_mlp_t* m) { return m ? m->prog.kbx : 0; }
 
-static long long* g_timeline = nullptr;     // debug hook, see hos_mlp_debug_timeline
-
 static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int64_t rows, const float* rowbias,
                       int rowbias_div, const float* add, float* out0, float* out1, void* stream) {
   for (int l = 0; l < m->prog.n_layers; ++l)
@@ -1661,11 +1659,11 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   a.ntiles = (int)((rows + kTileM - 1) / kTileM);
   a.rowbias_div = rowbias_div < 1 ? 1 : rowbias_div;
   a.fused_ipe = ipe != nullptr;
-  a.timeline = g_timeline;
+  a.timeline = m->timeline;
   static const IpeArgs kNoIpe = {};
-  HOS_REQUIRE(g_mlp_variant != 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
+  HOS_REQUIRE(m->variant != 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
   // the pair kernel walks groups of 4 tiles; tiny batches keep more SMs busy on the single-CTA kernel
-  const bool pair = m->smem_pair && g_mlp_variant != 1 && (g_mlp_variant == 2 || a.ntiles >= 2);
+  const bool pair = m->smem_pair && m->variant != 1 && (m->variant == 2 || a.ntiles >= 2);
   if (pair) {
     const int n_groups = (a.ntiles + 1) / 2;
     const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
@@ -1687,14 +1685,15 @@ int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float
   return mlp_launch(m, x_tiled, nullptr, rows, rowbias, rowbias_div, add, out0, out1, stream);
 }
 
-int hos_mlp_set_variant(int variant) {
-  HOS_REQUIRE(variant >= 0 && variant <= 2, "hos_mlp_set_variant: 0 = auto, 1 = single-CTA kernel, 2 = cluster-pair kernel");
-  g_mlp_variant = variant;
+int hos_mlp_set_variant(hos_mlp_t* m, int variant) {
+  HOS_REQUIRE(m && variant >= 0 && variant <= 2, "hos_mlp_set_variant: handle + 0 = auto, 1 = single-CTA kernel, 2 = cluster-pair kernel");
+  m->variant = variant;
   return HOS_OK;
 }
 
-int hos_mlp_debug_timeline(long long* device_buf_1024) {
-  g_timeline = device_buf_1024;
+int hos_mlp_debug_timeline(hos_mlp_t* m, long long* device_buf_1024) {
+  HOS_REQUIRE(m, "hos_mlp_debug_timeline: null handle");
+  m->timeline = device_buf_1024;
   return HOS_OK;
 }
 

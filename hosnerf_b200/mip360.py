@@ -407,9 +407,31 @@ class MipNeRF360MLP(nn.Module):
         return density, rgb
 
     def forward(self, gaussians, viewdirs, randomized, is_train, time):
-        raise NotImplementedError(
-            "hosnerf_b200.MipNeRF360MLP evaluates samples straight from ray intervals "
-            "(eval_samples); the (means, covs) entry of the reference is subsumed by MipNeRF360.forward")
+        """The reference's own entry of the MLP (S1 model.py:223-264): ``gaussians = (means [N,S,3], covs [N,S,3,3])`` as
+        cast_rays produces them (un-contracted), ``viewdirs`` [N,3] -> ``{"density": [N,S], "rgb": [N,S,3]}``.  Runs the
+        un-fused fp32 kernels (encoder from the given Gaussians, FFMA layers); ``MipNeRF360.forward`` does not come through
+        here - it evaluates samples straight from ray intervals (``eval_samples``)."""
+        means, covs = gaussians
+        if not means.is_cuda:
+            raise RuntimeError("hosnerf_b200.MipNeRF360MLP: inputs must be CUDA tensors (no CPU fallback)")
+        if randomized and (self.density_noise > 0 or self.bottleneck_noise > 0):
+            raise NotImplementedError("hosnerf_b200: density_noise / bottleneck_noise > 0 with randomized=True is not built")
+        n, s = means.shape[0], means.shape[1]
+        st = self._state_index(time)
+        f = self._folded(st)
+        feat = ops.ipe_from_gaussians(means.contiguous().float(), covs.contiguous().float(), self.pos_basis_t,
+                                      self.min_deg_point, self.max_deg_point)
+        x = feat
+        for W, b, skip in f["layers"]:
+            x = ops.linear_f32(x, W, b, act=1, x2=feat if skip else None)
+        density = ops.head_f32(x, *f["density"], post=1, shift=float(self.density_bias)).view(n, s)
+        if self.disable_rgb:
+            return {"density": density, "rgb": torch.zeros_like(means)}
+        bott = ops.linear_f32(x, *f["bottleneck"], act=0)
+        de = ops.pos_enc(viewdirs.contiguous().float(), 0, self.deg_view, True)
+        v = ops.linear_f32(bott, f["views"][0], f["views"][1], act=1, x2=de, x2_row_div=s)
+        rgb = ops.head_f32(v, *f["rgb"], post=2, shift=float(self.rgb_padding)).view(n, s, 3)
+        return {"density": density, "rgb": rgb}
 
 
 @_configurable()

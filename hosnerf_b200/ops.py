@@ -134,6 +134,18 @@ def ipe_features(tdist, rays_o, rays_d, radii, basis, min_deg=0, max_deg=12, out
     return (feat, means, lvar) if want_aux else feat
 
 
+def ipe_from_gaussians(means, covs, basis, min_deg=0, max_deg=12):
+    """contract + lift + IPE of caller-supplied Gaussians: means [..., 3], covs [..., 3, 3] -> fp32 [rows, 2 * deg * B]."""
+    _chk(means, "means"), _chk(covs, "covs"), _chk(basis, "basis")
+    rows = means.numel() // 3
+    b = basis.shape[1]
+    width = 2 * (max_deg - min_deg) * b
+    feat = torch.empty(rows, width, device=means.device, dtype=_F32)
+    _lib.call_unless_empty(rows, "hos_ipe_from_gaussians", _p(means), _p(covs), _p(basis), rows, b, min_deg, max_deg, _p(feat), width,
+                           _stream())
+    return feat
+
+
 def ipe_features_fast(tdist, rays_o, rays_d, radii, basis_host):
     """504 IPE features per sample, tiled fp16, generation column order (for TiledLinear(ipe_inputs=...))."""
     for t, nm in ((tdist, "tdist"), (rays_o, "rays_o"), (rays_d, "rays_d"), (radii, "radii")):
@@ -262,6 +274,16 @@ class FusedMLP:
         assert tuple(w.shape) == (l["out_dim"], l["in_h"] + l["in_x"]), (i, w.shape, l)
         _lib.call("hos_mlp_set_layer", self._h, i, _p(w), _p(b), _stream())
 
+    def _apply_handle_options(self):
+        """Kernel variant / debug timeline are fields of the handle: push the host-side defaults when they changed."""
+        tl = MLP_TIMELINE
+        key = (MLP_VARIANT, None if tl is None else tl.data_ptr())
+        if getattr(self, "_opt_key", (0, None)) != key:
+            lib = _lib.load()
+            _lib.check(lib.hos_mlp_set_variant(self._h, MLP_VARIANT), "hos_mlp_set_variant")
+            _lib.check(lib.hos_mlp_debug_timeline(self._h, None if tl is None else tl.data_ptr()), "hos_mlp_debug_timeline")
+            self._opt_key = key
+
     def set_ipe_input(self, enable=True):
         """Select the fused-IPE weight-column order; call before set_layer()."""
         _lib.call("hos_mlp_set_ipe_input", self._h, int(enable))
@@ -279,6 +301,7 @@ class FusedMLP:
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        self._apply_handle_options()
         _lib.call_unless_empty(rows, "hos_mlp_forward_ipe", self._h, _p(tdist), _p(rays_o), _p(rays_d), _p(radii), basis_host, n, s,
                   _p(rowbias), rowbias_div, _p(outs[0]), _p(outs[1]), _stream())
         if PROFILE is not None:
@@ -304,6 +327,7 @@ class FusedMLP:
         if PROFILE is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        self._apply_handle_options()
         _lib.call_unless_empty(rows, "hos_mlp_forward", self._h, _p(x_tiled), rows, _p(rowbias), rowbias_div, _p(add),
                   _p(outs[0]), _p(outs[1]), _stream())
         if PROFILE is not None:
@@ -369,9 +393,16 @@ class TiledLinear:
             pass
 
 
+MLP_VARIANT = 0          # host-side default that FusedMLP applies to ITS handle before a launch (A/B measurements, tests)
+MLP_TIMELINE = None      # optional int64 CUDA tensor (>= 1024): debug stamps of the next FusedMLP launches
+
+
 def set_mlp_variant(variant: int):
-    """0 = automatic, 1 = single-CTA tcgen05 kernel, 2 = cluster-pair (cta_group::2, ping-pong) kernel."""
-    _lib.call("hos_mlp_set_variant", int(variant))
+    """0 = automatic, 1 = single-CTA tcgen05 kernel, 2 = cluster-pair (cta_group::2, ping-pong) kernel.  The choice is a
+    field of each ``hos_mlp_t`` handle (``hos_mlp_set_variant(mlp, v)``); this sets the value FusedMLP objects apply."""
+    global MLP_VARIANT
+    assert variant in (0, 1, 2)
+    MLP_VARIANT = int(variant)
 
 
 def pack_rows_f16(x, k=None):

@@ -20,17 +20,17 @@ with torch.no_grad():
         net(b, 1.0, False, False, 0.1, 1e6)
     buf = torch.zeros(1024, dtype=torch.int64, device=dev)
     if which == "nerf":
-        lib.hos_mlp_debug_timeline(buf.data_ptr())      # stamps of the last launch (NeRF MLP) remain
+        ops.MLP_TIMELINE = buf                           # every handle stamps its launches; the last one (NeRF MLP) remains
         net(b, 1.0, False, False, 0.1, 1e6)
     else:
         mlp = net.mlps[0]
         _, hist = net(b, 1.0, False, False, 0.1, 1e6)
-        lib.hos_mlp_debug_timeline(buf.data_ptr())
+        ops.MLP_TIMELINE = buf
         sd = hist[0]["sdist"]
         td = (1.0 / (sd / 1e6 + (1.0 - sd) / 0.1)).contiguous()
         mlp.eval_samples(td, b["rays_o"], b["rays_d"], b["radii"].reshape(-1).contiguous(), b["viewdirs"], 0.0, "fp16")
     torch.cuda.synchronize()
-    lib.hos_mlp_debug_timeline(None)
+    ops.MLP_TIMELINE = None
 if variant == 1:
     t = buf.cpu()[:256].view(64, 4)
     t0 = int(t[0, 0])
@@ -42,7 +42,7 @@ if variant == 1:
 else:
     t = buf.cpu()[:768].view(64, 12)
     t0 = int(t[0, 0])
-    nl = 4 if which == "prop" else len(net.mlps[-1]._cache["f16"].layers)
+    nl = 4 if which == "prop" else len(next(iter(net.mlps[-1]._cache["f16"].values()))[1].layers)
     print("unit(tile,layer): mma_enter issued | epi_enter acc_ready epi_done | feat_start feat_end | "
           "issue_span wait | epi_wait epi_span | feat_span | mma_enter->next")
     for i in range(63):

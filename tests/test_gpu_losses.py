@@ -75,8 +75,10 @@ def test_loss_terms_end_to_end_vs_oracle():
     got = lit.loss_terms({k: v.cuda() for k, v in b.items()}, randomized=True, rands=[r.cuda() for r in rands])
     for k in ("rgbloss", "interlevel", "distortion", "psnr", "loss"):
         assert np.allclose(float(got[k]), ref[k], rtol=1e-4), (k, float(got[k]), ref[k])
-    with pytest.raises(NotImplementedError):
-        lit.training_step(b, 0)
+    # the same objective with an autograd graph (fp16 tensor-core layers; LitMipNeRF360.training_step's body)
+    obj = lit.training_objective({k: v.cuda() for k, v in b.items()}, randomized=True, rands=[r.cuda() for r in rands])
+    assert obj["loss"].requires_grad
+    assert np.allclose(float(obj["loss"].detach()), ref["loss"], rtol=5e-3), (float(obj["loss"].detach()), ref["loss"])
 
 
 def test_loss_kernels_full_size_properties():
