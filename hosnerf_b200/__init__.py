@@ -11,8 +11,8 @@ from .mip360 import (LitMipNeRF360, MipNeRF360, MipNeRF360MLP, NeRFMLP, PropMLP,
 from .human import (BodyPoseRefiner, CanonicalMLP, MotionBasisComputer, MotionWeightVolumeDecoder, Network,
                     NonRigidForwardMLP, NonRigidMotionMLP, default_cfg)
 
-from .hosnerf import cycle_loss, render_hosnerf_chunk, train_hosnerf_chunk
+from .hosnerf import cycle_loss, flow_loss, render_hosnerf_chunk, train_hosnerf_chunk
 
-__all__ = ["render_hosnerf_chunk", "train_hosnerf_chunk", "cycle_loss", "LitMipNeRF360", "MipNeRF360", "MipNeRF360MLP", "NeRFMLP", "PropMLP", "Network", "CanonicalMLP",
+__all__ = ["render_hosnerf_chunk", "train_hosnerf_chunk", "flow_loss", "cycle_loss", "LitMipNeRF360", "MipNeRF360", "MipNeRF360MLP", "NeRFMLP", "PropMLP", "Network", "CanonicalMLP",
            "NonRigidMotionMLP", "NonRigidForwardMLP", "MotionWeightVolumeDecoder", "BodyPoseRefiner",
            "MotionBasisComputer", "default_cfg", "select_state_index", "set_precision"]

@@ -97,3 +97,19 @@ def train_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dict
         rgb_bg, _ = _composite_ray_set(bkg[ib], zb[ib], rays_d[ib], torch.ones_like(zb[ib]))
         rgb = rgb.index_put((torch.nonzero(ib)[:, 0],), rgb_bg)
     return {"rgb": rgb, "idx_fg": idx_fg, "human_weights": human_w, "ray_history": ray_history, "net_output": net_output}
+
+
+def flow_loss(ray_grid, newsmpl_to_camera_prev, intrinsics_prev, human_weights, deform_pts_prev_final):
+    """The flow term of the stage-3 objective (S3 src/model/mipnerf360/model.py:1680-1688 with img2mae :61-72): the
+    previous-frame points (``deform_pts_prev_final`` of the foreground rays, [n_fg, S, 3]) are projected into the previous
+    camera, and their weighted distance to the optical flow stored in ``ray_grid`` [n_fg, 5] = (x, y, flow_x, flow_y, valid)
+    is averaged.  A dozen elementwise torch ops on [n_fg, S, 2] tensors with a graph: gradient reaches the forward
+    non-rigid MLP, the previous frame's bone maps and the volume through ``deform_pts_prev_final`` (and the composite
+    through ``human_weights``)."""
+    hom = torch.cat([deform_pts_prev_final, torch.ones_like(deform_pts_prev_final[..., :1])], dim=-1)
+    cam = torch.einsum("ji,bni->bnj", newsmpl_to_camera_prev, hom)[..., :3]
+    p2 = torch.einsum("ji,bni->bnj", intrinsics_prev, cam)
+    p2 = p2[..., :-1] / p2[..., -1:]
+    grid = ray_grid.unsqueeze(1).repeat(1, p2.shape[1], 1)
+    x, y, M = p2 - grid[..., :2], grid[..., 2:4], grid[..., -1].unsqueeze(-1)
+    return torch.sum(torch.abs(x - y) * human_weights[..., None] * M) / (torch.sum(M) + 1e-8) / x.shape[-1]

@@ -971,3 +971,37 @@ class LitMipNeRF360(_LitBase):
 
     def configure_optimizers(self):
         return torch.optim.Adam(params=self.parameters(), lr=self.lr_init, betas=(0.9, 0.999))
+
+    # ------------------------------------------------------------------ eval tail (S1 src/model/interface.py:28-51)
+    def alter_gather_cat(self, outputs, key, image_sizes):
+        """Per-rank step outputs -> whole images: concatenate, all_gather over the ranks, undo the strided ray sharding
+        (ray i rendered by rank i mod W) and cut into [h, w, 3] images (interface.py:28-39).  One NCCL all_gather."""
+        from . import dist as hd
+        each = torch.cat([o[key] for o in outputs])
+        total = sum(h * w for h, w in image_sizes)
+        full = hd.gather_rays(each, total, "strided").detach()
+        ret, cur = [], 0
+        for h, w in image_sizes:
+            ret.append(full[cur:cur + h * w].reshape(h, w, 3))
+            cur += h * w
+        return ret
+
+    @torch.no_grad()
+    def psnr_each(self, preds, gts):
+        """interface.py:41-51."""
+        out = []
+        for pred, gt in zip(preds, gts):
+            mse = torch.mean((torch.clip(pred, 0, 1) - torch.clip(gt, 0, 1)) ** 2)
+            out.append(-10.0 * torch.log(mse) / math.log(10.0))
+        return torch.stack(out)
+
+    def validation_epoch_end(self, outputs):
+        """S1 model.py:571-581 without the metric packages this image lacks (SSIM / LPIPS need piqa + VGG weights): gathers the
+        rendered images of all ranks and returns / logs the mean PSNR."""
+        sizes = self.trainer.datamodule.val_image_sizes
+        rgbs = self.alter_gather_cat(outputs, "rgb", sizes)
+        targets = self.alter_gather_cat(outputs, "target", sizes)
+        psnr = self.psnr_each(rgbs, targets).mean()
+        if hasattr(self, "log"):
+            self.log("val/psnr", psnr.item(), on_epoch=True, sync_dist=True)
+        return psnr

@@ -43,3 +43,21 @@ for tag, sdir in (("s3", rh.S3), ("s2", rh.S2)):
                 arrays[f"in_{k}"] = v.numpy()
         np.savez_compressed(os.path.join(HERE, f"human_{tag}_flow.npz"), **arrays)
         print(tag, {k: v.shape for k, v in arrays.items() if not k.startswith("in_")})
+
+# ---- the flow term of the stage-3 objective on random inputs: LitMipNeRF360.flow_func (S3 model.py:1680-1688), unbound
+with rh.stage(rh.S3):
+    import src.model.mipnerf360.model as M3
+    g = torch.Generator().manual_seed(17)
+    n_fg, S = 37, 128
+    ray_grid = torch.cat([torch.rand(n_fg, 2, generator=g) * 500, torch.randn(n_fg, 2, generator=g) * 3,
+                          (torch.rand(n_fg, 1, generator=g) > 0.3).float()], dim=-1)
+    cam = torch.eye(4)
+    cam[:3, :3] = torch.linalg.qr(torch.randn(3, 3, generator=g))[0]
+    cam[:3, 3] = torch.tensor([0.1, -0.2, 3.0])
+    K = torch.tensor([[1500.0, 0.0, 250.0], [0.0, 1500.0, 250.0], [0.0, 0.0, 1.0]])
+    w = torch.rand(n_fg, S, generator=g) * 0.05
+    pts = torch.randn(n_fg, S, 3, generator=g) * 0.3
+    val = M3.LitMipNeRF360.flow_func(None, ray_grid, cam, K, w, pts)
+    np.savez_compressed(os.path.join(HERE, "flow_loss.npz"), ray_grid=ray_grid.numpy(), cam=cam.numpy(), K=K.numpy(), w=w.numpy(),
+                        pts=pts.numpy(), loss=np.float32(val.item()))
+    print("flow loss", float(val))

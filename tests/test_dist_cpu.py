@@ -65,6 +65,21 @@ def test_shard_gather_world2(n_rays, mode):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def test_eval_tail_gather_and_psnr_single_process():
+    """LitMipNeRF360.alter_gather_cat / psnr_each (S1 interface.py:28-51) on one process: images are cut out of the
+    concatenated per-step outputs in order; PSNR of a known error."""
+    from hosnerf_b200 import LitMipNeRF360
+    lit = LitMipNeRF360.__new__(LitMipNeRF360)
+    sizes = [(2, 3), (1, 4)]
+    flat = torch.arange(10 * 3, dtype=torch.float32).reshape(10, 3) / 30.0
+    outs = [{"rgb": flat[:4]}, {"rgb": flat[4:]}]
+    imgs = LitMipNeRF360.alter_gather_cat(lit, outs, "rgb", sizes)
+    assert [tuple(i.shape) for i in imgs] == [(2, 3, 3), (1, 4, 3)]
+    assert torch.equal(torch.cat([i.reshape(-1, 3) for i in imgs]), flat)
+    ps = LitMipNeRF360.psnr_each(lit, [torch.full((2, 2, 3), 0.5)], [torch.full((2, 2, 3), 0.6)])
+    assert abs(float(ps[0]) - 20.0) < 1e-4
+
+
 def test_single_process_passthrough():
     x = torch.arange(12.0).view(4, 3)
     assert torch.equal(hd.gather_rays(x, 4), x)
