@@ -677,18 +677,32 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
 __global__ void __launch_bounds__(256)
 colsum_f16_kernel(const __half* __restrict__ X, int64_t rows, int n, int ld, const float* __restrict__ g, int hn,
                   float* __restrict__ out, int ld_out, int rows_per_cta) {
+  // thread -> (column pair, row phase): the 256 threads cover n / 2 column pairs x `phases` interleaved row sets, four
+  // independent rows in flight per thread (the one-row-at-a-time version ran at 1 TB/s)
+  const int pairs = n >> 1;
+  const int phases = pairs >= 256 ? 1 : 256 / pairs;
+  const int cp = threadIdx.x % pairs, ph = threadIdx.x / pairs;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
-  for (int c = 2 * threadIdx.x; c < n; c += 2 * blockDim.x) {
+  if (ph >= phases) return;
+  for (int c = 2 * cp; c < n; c += 2 * 256) {
     float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = r0; r < r1; ++r) {
-      const __half2 h2 = *reinterpret_cast<const __half2*>(X + r * ld + c);
-      const float x0 = __low2float(h2), x1 = __high2float(h2);
-      if (!g) { a0[0] += x0; a1[0] += x1; }
-      else {
+    for (int64_t r = r0 + ph; r < r1; r += 4 * phases) {
+      __half2 h2[4];
+      float gv[4][4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h)
-          if (h < hn) { const float w = __ldg(g + r * hn + h); a0[h] = fmaf(w, x0, a0[h]); a1[h] = fmaf(w, x1, a1[h]); }
+      for (int u = 0; u < 4; ++u) {
+        const int64_t rr = r + (int64_t)u * phases;
+        const bool ok = rr < r1;
+        h2[u] = ok ? *reinterpret_cast<const __half2*>(X + rr * ld + c) : __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) gv[u][h] = !g ? (h == 0 ? 1.f : 0.f) : ((ok && h < hn) ? __ldg(g + rr * hn + h) : 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float x0 = __low2float(h2[u]), x1 = __high2float(h2[u]);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) { a0[h] = fmaf(gv[u][h], x0, a0[h]); a1[h] = fmaf(gv[u][h], x1, a1[h]); }
       }
     }
     for (int h = 0; h < (g ? hn : 1); ++h) {
@@ -939,9 +953,9 @@ int hos_colsum_f16(const void* x, int64_t rows, int n, int ld, const float* g, i
   HOS_REQUIRE(x && out && rows >= 0 && n >= 2 && (n % 2) == 0 && (ld % 2) == 0 && hn >= 0 && hn <= 4 && (g || hn <= 1),
               "hos_colsum_f16: X [rows, n even], hn <= 4");
   if (rows == 0) return HOS_OK;
-  const int rows_per_cta = 256;
+  const int rows_per_cta = 512;
   const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
-  const int threads = n / 2 < 256 ? ((n / 2 + 31) / 32) * 32 : 256;
+  const int threads = 256;
   colsum_f16_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)x, rows, n, ld, g, g ? hn : 1, out, ld_out, rows_per_cta);
   HOS_LAUNCH_CHECK();
   return HOS_OK;
