@@ -498,7 +498,7 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
 // [128 r, 128 r + 128) (its half of M) and the Q columns [nq/2 r, ...) of every 256-column accumulator block (its half of N) -
 // and issue 8 K = 16 steps; the fp32 accumulators stay in TMEM until the cluster has seen all of its tiles, then the
 // epilogue adds them to the global gradient with vector atomics.  Columns beyond the matrices are zero-filled by TMA.
-constexpr int kWgStages = 2;
+constexpr int kWgMaxStages = 3;           // ring depth: 3 stages of 64 KB (one accumulator block) or 2 of 96 KB (two)
 
 struct WgArgs {
   float* out;
@@ -509,6 +509,7 @@ struct WgArgs {
   int m, nq;          // valid P / Q columns
   int nacc;           // 256-column accumulator blocks (1 or 2)
   int transpose_out;  // 0: out[i * ld + j], 1: out[j * ld + i]
+  int stages;
 };
 struct WgMaps {
   CUtensorMap p, q;
@@ -523,10 +524,11 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
   const int q_bytes = nacc * 2 * kXChunkBytes;                // 128 Q columns per accumulator block
   const int stage_bytes = p_bytes + q_bytes;
   unsigned char* sRing = smem;
+  const uint32_t kWgStages = (uint32_t)args.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + (size_t)kWgStages * stage_bytes);
-  uint64_t* bar_full = bars;                                  // [kWgStages]
-  uint64_t* bar_empty = bar_full + kWgStages;                 // [kWgStages]
-  uint64_t* bar_done = bar_empty + kWgStages;                 // [1] all MMAs of this cluster retired
+  uint64_t* bar_full = bars;                                  // [kWgMaxStages]
+  uint64_t* bar_empty = bar_full + kWgMaxStages;              // [kWgMaxStages]
+  uint64_t* bar_done = bar_empty + kWgMaxStages;              // [1] all MMAs of this cluster retired
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -536,8 +538,8 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
   if (threadIdx.x == 0) {
     // a stage is free when its MMAs have retired (multicast commit) and, with column sums requested, when the 8 epilogue
     // warps of this CTA have read the P tile out of it
-    for (int s = 0; s < kWgStages; ++s) {
-      mbar_init(&bar_full[s], rank == 0 ? 4u : 2u);
+    for (int s = 0; s < kWgMaxStages; ++s) {
+      mbar_init(&bar_full[s], rank == 0 ? 3u : 2u);         // leader: own P + own Q + ONE relay from the peer's watcher warp
       mbar_init(&bar_empty[s], args.colsum ? 1u + kG2EpiWarps : 1u);
     }
     mbar_init(&bar_done[0], 1);
@@ -574,10 +576,19 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
               tma_load_2d(stage + p_bytes + (a * 2 + b) * kXChunkBytes, &maps.q, a * 256 + (int)rank * 128 + b * 64, t * kTileM,
                           &bar_full[st]);
         }
-        if (rank != 0) {
-          mbar_wait_guard<100>(&bar_full[st], use & 1);
-          mbar_arrive_remote(mapa_u32(smem_u32(&bar_full[st]), 0));
-        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== peer CTA: completion watcher =====================
+    // tells the leader "both of my operands of stage s have landed".  A separate warp, so that the producers above never wait
+    // for a copy to ARRIVE before issuing the next one (with the relay in the producer thread only one stage per CTA was in
+    // flight and the kernel ran at the latency of one HBM round trip per tile: 110-140 us per 0.54 GB).
+    if (rank != 0 && lane == 0) {
+      uint32_t st = 0, par = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait_guard<40>(&bar_full[st], par);
+        mbar_arrive_remote(mapa_u32(smem_u32(&bar_full[st]), 0));
+        if (++st == kWgStages) { st = 0; par ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -939,7 +950,8 @@ int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq,
     HOS_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     attr_dev = dev;
   }
-  const size_t smem = 1024 + (size_t)kWgStages * (2 + 2 * a.nacc) * kXChunkBytes + 8 * 8 + 64;
+  a.stages = a.nacc == 1 ? 3 : 2;
+  const size_t smem = 1024 + (size_t)a.stages * (2 + 2 * a.nacc) * kXChunkBytes + (2 * kWgMaxStages + 2) * 8 + 64;
   static thread_local int max_clusters = 0;
   if (!max_clusters) max_clusters = max_clusters_for((const void*)wgrad_tma_kernel, 227 * 1024 - 1024);
   const int clusters = a.ntiles < max_clusters ? a.ntiles : max_clusters;
