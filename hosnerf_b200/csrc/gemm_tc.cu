@@ -652,19 +652,31 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
     }
     mbar_wait_guard<200>(&bar_done[0], 0);
     tc_fence_after();
+    // Every MMA has retired, so the operand ring is free: each warp transposes its 32 x 32 accumulator blocks through a
+    // private 32 x 33 float patch of it and adds them to the global gradient with COALESCED atomics (a warp instruction
+    // covers 32 consecutive floats of one output row = one 128-byte line; thread-per-row atomics touched 32 lines each
+    // and made this epilogue - not the reduction over the rows - the cost of a small-batch launch).
+    asm volatile("bar.sync 1, %0;" ::"n"(kG2EpiWarps * 32) : "memory");     // every warp is done reading P tiles (column sums)
+    float* patch = reinterpret_cast<float*>(sRing) + (size_t)(warp - kG2EpiWarp0) * (32 * 33);
+    const int i_base = (int)rank * 128 + q * 32;              // first output row of this warp
     for (int a = 0; a < nacc; ++a) {
       for (int c = 0; c < 4; ++c) {
         const int j0 = a * 256 + c * 64 + ch * 32;
         uint32_t v[32];
         tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + c * 64 + ch * 32), v);
         tmem_wait_ld();
-        if (i >= args.m || j0 >= args.nq) continue;
+        if (i_base >= args.m || j0 >= args.nq) continue;       // warp-uniform
         if (!args.transpose_out) {
-          float* o = args.out + (size_t)i * args.ld_out + j0;
 #pragma unroll
-          for (int x = 0; x < 32; ++x)
-            if (j0 + x < args.nq) atomicAdd(o + x, __uint_as_float(v[x]));
-        } else {
+          for (int x = 0; x < 32; ++x) patch[lane * 33 + x] = __uint_as_float(v[x]);
+          __syncwarp();
+          const bool col_ok = j0 + lane < args.nq;
+          for (int rr = 0; rr < 32; ++rr) {
+            if (i_base + rr >= args.m) break;
+            if (col_ok) atomicAdd(args.out + (size_t)(i_base + rr) * args.ld_out + j0 + lane, patch[rr * 33 + lane]);
+          }
+          __syncwarp();
+        } else if (i < args.m) {                               // out[j][i]: lanes are consecutive i already
 #pragma unroll
           for (int x = 0; x < 32; ++x)
             if (j0 + x < args.nq) atomicAdd(args.out + (size_t)(j0 + x) * args.ld_out + i, __uint_as_float(v[x]));
@@ -954,7 +966,9 @@ int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq,
   const size_t smem = 1024 + (size_t)a.stages * (2 + 2 * a.nacc) * kXChunkBytes + (2 * kWgMaxStages + 2) * 8 + 64;
   static thread_local int max_clusters = 0;
   if (!max_clusters) max_clusters = max_clusters_for((const void*)wgrad_tma_kernel, 227 * 1024 - 1024);
-  const int clusters = a.ntiles < max_clusters ? a.ntiles : max_clusters;
+  int clusters = (a.ntiles + 15) / 16;          // >= 16 row tiles per cluster before it pays the atomic epilogue
+  if (clusters > max_clusters) clusters = max_clusters;
+  if (clusters < 1) clusters = 1;
   wgrad_tma_kernel<<<2 * clusters, kG2Threads, smem, (cudaStream_t)stream>>>(a, maps);
   HOS_LAUNCH_CHECK();
   return HOS_OK;

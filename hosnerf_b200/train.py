@@ -36,6 +36,7 @@ def mlp_forward_train(m, tdist, rays_o, rays_d, radii, viewdirs, state_idx: int)
     hs, x = [], feat
     dens = None
     nl = len(m.pts_linear)
+    w16 = []                     # fp16 copy of every layer's hidden-input weight block: reused by the data-gradient GEMMs
     for i, lin in enumerate(m.pts_linear):
         W, b = lin.weight.detach(), lin.bias.detach()
         last = i == nl - 1
@@ -44,28 +45,34 @@ def mlp_forward_train(m, tdist, rays_o, rays_d, radii, viewdirs, state_idx: int)
             kw["head"] = (m.density_layer.weight.detach().contiguous(), m.density_layer.bias.detach().contiguous(), 1,
                           float(m.density_bias))
         if i == 0:
-            res = ops.gemm_tma(x, _h(W[:, :F]), nw, bias=(b + W[:, F:] @ e).contiguous(), **kw)
+            wh = _h(W[:, :F])
+            res = ops.gemm_tma(x, wh, nw, bias=(b + W[:, F:] @ e).contiguous(), **kw)
         elif m._skip_inputs(i):
-            res = ops.gemm_tma(x, _h(W[:, :nw]), nw, a1=feat, w1=_h(W[:, nw:nw + F]), bias=(b + W[:, nw + F:] @ e).contiguous(), **kw)
+            wh = _h(W[:, :nw])
+            res = ops.gemm_tma(x, wh, nw, a1=feat, w1=_h(W[:, nw:nw + F]), bias=(b + W[:, nw + F:] @ e).contiguous(), **kw)
         else:
-            res = ops.gemm_tma(x, _h(W), nw, bias=b.contiguous(), **kw)
+            wh = _h(W)
+            res = ops.gemm_tma(x, wh, nw, bias=b.contiguous(), **kw)
+        w16.append(wh)
         x = res[0]
         hs.append(x)
         if last:
             dens = res[3]
-    ctx = {"m": m, "state": state_idx, "n": n, "s": s, "feat": feat, "hs": hs, "density": dens}
+    ctx = {"m": m, "state": state_idx, "n": n, "s": s, "feat": feat, "hs": hs, "density": dens, "w16": w16}
     if m.disable_rgb:
         return dens.view(n, s), None, ctx
     bw = m.bottleneck_width
-    bott = ops.gemm_tma(x, _h(m.bottleneck_layer.weight), bw, bias=m.bottleneck_layer.bias.detach().contiguous())[0]
+    wb16 = _h(m.bottleneck_layer.weight)
+    bott = ops.gemm_tma(x, wb16, bw, bias=m.bottleneck_layer.bias.detach().contiguous())[0]
     de = ops.pos_enc(viewdirs, 0, m.deg_view, True)
     Wv, bv = m.views_linear[0].weight.detach(), m.views_linear[0].bias.detach()
     rowterm = ops.linear_f32(de, Wv[:, bw:].contiguous(), bv.contiguous())
     Wr = (m.rgb_layer.weight.detach() * m.rgb_premultiplier).contiguous()
     br = (m.rgb_layer.bias.detach() * m.rgb_premultiplier + m.rgb_bias).contiguous()
-    v, _, _, rgb = ops.gemm_tma(bott, _h(Wv[:, :bw]), m.netwidth_condition, relu=True, rowbias=rowterm, rowbias_div=s,
+    wv16 = _h(Wv[:, :bw])
+    v, _, _, rgb = ops.gemm_tma(bott, wv16, m.netwidth_condition, relu=True, rowbias=rowterm, rowbias_div=s,
                                 head=(Wr, br, 2, float(m.rgb_padding)))
-    ctx.update(bott=bott, de=de, v=v, rgb=rgb)
+    ctx.update(bott=bott, de=de, v=v, rgb=rgb, wb16=wb16, wv16=wv16)
     return dens.view(n, s), rgb.view(n, s, 3), ctx
 
 
@@ -87,22 +94,22 @@ def mlp_backward(ctx, g_density, g_rgb, grads: dict):
     h_last = hs[-1]
     e = m.bkgd_stateembeds[ctx["state"]].detach()
 
-    def acc(name, shape):
-        if name not in grads:
-            grads[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
-        return grads[name]
-
     scale = _loss_scale(g_density, g_rgb)
     inv = 1.0 / scale
     # density = softplus(raw + bias): d/draw = sigmoid = 1 - exp(-density)
     g_raw = (g_density.reshape(rows, 1) * (1.0 - torch.exp(-ctx["density"])) * scale).contiguous()
     Wd = m.density_layer.weight.detach().contiguous()
-    # scaled gradient buffers of this MLP (unscaled into `grads` at the end)
-    sg = {}
+    # scaled gradients of this MLP: views of ONE zeroed buffer (one memset, one unscaling multiply at the end)
+    own = [(k, p) for k, p in m.named_parameters() if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for _, p in own), device=dev, dtype=torch.float32)
+    sg, off = {}, 0
+    for k, p in own:
+        sg[k] = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    touched = set()
 
     def sacc(name, shape):
-        if name not in sg:
-            sg[name] = torch.zeros(shape, device=dev, dtype=torch.float32)
+        touched.add(name)
         return sg[name]
 
     ops.colsum_f16(h_last, sacc("density_layer.weight", Wd.shape), g=g_raw)
@@ -126,10 +133,10 @@ def mlp_backward(ctx, g_density, g_rgb, grads: dict):
         g_row = g_zv.view(ctx["n"], ctx["s"], cw).sum(1, dtype=torch.float32)               # per-ray term
         gWv[:, bw:].add_(g_row.t() @ de)
         sacc("views_linear.0.bias", (cw,)).add_(g_row.sum(0))
-        g_bott = ops.gemm_tma(g_zv, _h(Wv[:, :bw]), bw, mode=1)[0]                           # [rows, bw]
+        g_bott = ops.gemm_tma(g_zv, ctx["wv16"], bw, mode=1)[0]                              # [rows, bw]
         Wb = m.bottleneck_layer.weight.detach()
         ops.wgrad_tma(g_bott, h_last, sacc("bottleneck_layer.weight", Wb.shape), colsum=sacc("bottleneck_layer.bias", (bw,)))
-        add = ops.gemm_tma(g_bott, _h(Wb), nw, mode=1)[0]                                    # d/dh_last through the bottleneck
+        add = ops.gemm_tma(g_bott, ctx["wb16"], nw, mode=1)[0]                               # d/dh_last through the bottleneck
     g_z = ops.head_dgrad(g_raw, Wd, nw, add=add, mask=h_last)                                # + density head, ReLU mask of the last layer
     g_e = sacc("bkgd_stateembeds.%d" % ctx["state"], e.shape)
     for i in range(len(m.pts_linear) - 1, -1, -1):
@@ -151,9 +158,13 @@ def mlp_backward(ctx, g_density, g_rgb, grads: dict):
             gW[:, emb0:].add_(torch.outer(gb, e))
             g_e.add_(W[:, emb0:].t() @ gb)
         if i > 0:
-            g_z = ops.gemm_tma(g_z, _h(W[:, :nw]), nw, mode=1, mask=hs[i - 1])[0]
-    for k, v_ in sg.items():
-        acc(k, v_.shape).add_(v_ * inv)
+            g_z = ops.gemm_tma(g_z, ctx["w16"][i], nw, mode=1, mask=hs[i - 1])[0]
+    flat.mul_(inv)
+    for k in touched:
+        if k in grads:
+            grads[k] = grads[k] + sg[k]
+        else:
+            grads[k] = sg[k]
     return grads
 
 
