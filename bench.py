@@ -40,11 +40,23 @@ MLP_KERNEL = {0: "mlp_pair_kernel", 1: "mlp_tc_kernel", 2: "mlp_pair_kernel"}
 WORKLOAD = "C2: stage-1 bkg render_rays, 4096 rays x (128 prop + 128 nerf) samples, PropMLP 4x256 + NeRFMLP 8x256"
 
 
+def workload_config(world, call="hos_render_bkg: one library call per batch"):
+    """The `config` object of the JSON line - identical in the product arm and the reference arm (same workload, same keys)."""
+    return {"workload": WORKLOAD, "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": SAMPLES_PER_RAY,
+            "parallelism": f"rays sharded over {world} GPU(s), no data-path collective",
+            "l2": "device-resident loop: a 256 MiB buffer is written between timed steps (untimed) to evict L2; e2e loop: no flush, "
+                  "every step's inputs arrive from pinned host memory",
+            "timing": "CUDA events per step on the launch stream, summed; max over ranks",
+            "call": call}
+
+
 def ncu_traffic():
-    """DRAM bytes of the dominant kernel (both MLP launches of a step) from the committed ncu capture."""
-    p = os.path.join(ROOT, "profiles", "r1_mlp_pair_ncu.json")
+    """DRAM bytes of the dominant kernel (both MLP launches of a step) from the committed `ncu --set full` capture
+    (profiles/r2_ncu_summary.json, made by scripts/ncu_r2.sh + scripts/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_summary.json")
     try:
-        return json.load(open(p))["dram_bytes_per_step"]
+        recs = json.load(open(p))["r2_full_mlp_pair"]
+        return int(sum((r.get("dram_read_MB", 0.0) + r.get("dram_write_MB", 0.0)) for r in recs) * 1e6)
     except Exception:
         return None
 
@@ -118,7 +130,7 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def cpu_reference_steps(n_rays, steps, warmup, threads, prefer_ref=True):
+def cpu_reference_steps(n_rays, steps, warmup, threads, prefer_ref=True, budget_s=None):
     """Time the reference's own CPU implementation of the path on `n_rays` rays of the workload: the UNMODIFIED reference
     modules from oracle/_ref (copied there by recipe, oracle/ref_loader.py) when present, else the oracle port.
     Returns (seconds per step, kind)."""
@@ -147,35 +159,42 @@ def cpu_reference_steps(n_rays, steps, warmup, threads, prefer_ref=True):
         fwd = lambda: R.mip360_forward(sd, batch, 1.0, False, NEAR, FAR, num_levels=2, num_prop_samples=S_PROP, num_nerf_samples=S_NERF)
     times = []
     import warnings
+    t_start = time.perf_counter()
     with torch.no_grad(), warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        for i in range(warmup + steps):
+        i = 0
+        while i < warmup + steps:
             t0 = time.perf_counter()
             fwd()
+            dt = time.perf_counter() - t0
             if i >= warmup:
-                times.append(time.perf_counter() - t0)
-    return sum(times) / len(times), kind
+                times.append(dt)
+            i += 1
+            # a step is seconds of CPU work: stop early (at least one timed step) when the whole run would exceed the budget
+            if budget_s is not None and times and time.perf_counter() - t_start + dt > budget_s:
+                break
+    return sum(times) / len(times), kind, len(times)
 
 
 def run_reference(args):
-    """Reference arm: LitMipNeRF360.render_rays's body (MipNeRF360.forward, eval mode) of the unmodified reference on the
-    host CPU, all cores, on the SAME 4096-ray batch shape as the product arm.  A step takes ~10 s, so the number of timed
-    steps is capped (stated in the line)."""
+    """Reference arm: LitMipNeRF360.render_rays's body (MipNeRF360.forward, eval mode) of the UNMODIFIED reference
+    (oracle/_ref, else the oracle port) on the host CPU, all cores, on the product arm's config: the same 4096-ray batch per
+    step, the requested steps / warm-ups (a step is seconds of CPU work; the run stops early once it would exceed ~4 minutes
+    and reports the steps it timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     n = N_RAYS
-    steps, warm = max(1, min(args.steps, 3)), 1
-    sec, kind = cpu_reference_steps(n, steps, warm, threads)
+    warm = max(0, args.warmup)
+    sec, kind, steps = cpu_reference_steps(n, max(1, args.steps), warm, threads, budget_s=240.0)
     value = n * SAMPLES_PER_RAY / sec
     line = {"impl": "reference", "metric": "ray_samples_per_s", "value": value, "unit": "ray-samples/s",
             "rays_per_s": n / sec, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step": n, "samples_per_ray": SAMPLES_PER_RAY,
-                       "note": f"full {n}-ray batch per step; {steps} timed step(s) after {warm} warm-up (a step is ~10 s of CPU work); "
-                               "one CPU process regardless of --gpus"},
+            "config": workload_config(args.gpus),
+            "reference_note": f"one CPU process regardless of --gpus; full {n}-ray batch per step; {steps} timed step(s) of the {args.steps} requested",
             "cpu_baseline": {"value": value, "unit": "ray-samples/s", "cores": threads, "kind": kind,
                              "sample": f"{n} rays x {SAMPLES_PER_RAY} samples per step, {steps} steps, torch CPU fp32, "
                                        + ("unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port")},
@@ -474,11 +493,7 @@ def main():
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f16" if args.precision == "fp16" else "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": N_RAYS, "samples_per_ray": SAMPLES_PER_RAY,
-                       "parallelism": f"rays sharded over {world} GPU(s), no data-path collective",
-                       "l2": "device-resident loop: a 256 MiB buffer is written between timed steps (untimed) to evict L2; e2e loop: no flush, every step's inputs arrive from pinned host memory",
-                       "timing": "CUDA events per step on the launch stream, summed; max over ranks",
-                       "call": "hos_render_bkg: one library call per batch" if one_call else "level loop in Python"},
+            "config": workload_config(world, "hos_render_bkg: one library call per batch" if one_call else "level loop in Python"),
             "e2e": {"value": samples / (e2e_ms_max * 1e-3), "unit": "ray-samples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms_max / K,
                     "api": "LitMipNeRF360.render_rays_stream(host batches): pinned host tensors in, rgb in pinned host memory out, "
@@ -490,7 +505,7 @@ def main():
             "roofline": {"bound": "tensor", "kernel": MLP_KERNEL[args.mlp_variant] + " (tcgen05 fused MLP, 2 launches/step)",
                          "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
                          "peak_source": f"{src} bf16_tflops (burst)", "traffic": ncu_traffic(),
-                         "traffic_note": "DRAM read+write bytes of the two MLP launches of one step, ncu --set full (profiles/r1_mlp_pair_ncu.json)",
+                         "traffic_note": "DRAM read+write bytes of the two MLP launches of one step, ncu --set full (profiles/r2_ncu_summary.json)",
                          "kernel_share_of_step": mlp_ms / dev_ms if dev_ms > 0 else None,
                          "flop_per_launch": [N_RAYS * S_PROP * FLOP_PROP, N_RAYS * S_NERF * FLOP_NERF]},
             "clocks": sampler.summary(),
@@ -502,7 +517,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             n = 2048
-            sec, kind = cpu_reference_steps(n, 2, 1, threads)          # about 15 s of host work on the box's cores
+            sec, kind, _ = cpu_reference_steps(n, 2, 1, threads)       # about 15 s of host work on the box's cores
             line["cpu_baseline"] = {"value": n * SAMPLES_PER_RAY / sec, "unit": "ray-samples/s", "cores": threads,
                                     "kind": kind, "sample": f"{n} of {N_RAYS} rays x {SAMPLES_PER_RAY} samples, 1 warm-up + 2 timed passes, torch CPU fp32, "
                                     + ("unmodified reference modules (oracle/_ref)" if kind == "reference" else "oracle port")}

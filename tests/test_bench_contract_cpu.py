@@ -24,7 +24,7 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "ray_samples_per_s" and d["unit"] == "ray-samples/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0
-    assert d["config"]["workload"].startswith("C2") and d["config"]["rays_per_step"] == 4096
+    assert d["config"]["workload"].startswith("C2") and d["config"]["rays_per_step_per_gpu"] == 4096
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
