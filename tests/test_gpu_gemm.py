@@ -106,3 +106,29 @@ def test_colsum_and_head_dgrad():
     y = ops.head_dgrad(gw, W, n, add=add, mask=x)
     ref = (gw @ W + add.float()) * (x > 0)
     assert _rel(y.float(), ref) < 2e-3
+
+
+def test_empty_and_argument_errors():
+    """Empty batches are no-ops; malformed descriptors come back as status codes with a message (no exceptions across the ABI)."""
+    import ctypes
+    from hosnerf_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    a = torch.zeros(0, 256, device="cuda", dtype=torch.float16)
+    w = torch.zeros(256, 256, device="cuda", dtype=torch.float16)
+    y, _, _ = ops.gemm_tma(a, w, 256)
+    assert y.shape == (0, 256)
+    out = torch.zeros(256, 256, device="cuda")
+    ops.wgrad_tma(a, a, out)
+    assert float(out.abs().max()) == 0.0
+    d = _lib.GemmTmaDesc()
+    stream = torch.cuda.current_stream().cuda_stream
+    assert lib.hos_gemm_tma(ctypes.byref(d), stream) != 0 and b"hos_gemm_tma" in lib.hos_last_error()       # nothing set
+    x = torch.randn(256, 100, device="cuda").half()                  # 200-byte pitch: not a multiple of 16
+    with pytest.raises(RuntimeError, match="16-byte"):
+        ops.gemm_tma(x, w[:, :100].contiguous(), 256)
+    g = torch.randn(64, 5, device="cuda")
+    with pytest.raises(AssertionError):
+        ops.head_dgrad(g, torch.randn(4, 256, device="cuda"), 256)   # head wider than its weight rows
+    assert lib.hos_wgrad_tma(None, 256, 256, None, 256, 256, 10, None, 256, 0, None, stream) != 0
+    assert lib.hos_lbs_warp_backward(None, None, None, None, None, None, 10, 26, 32, None, None, None, None, None, stream) != 0

@@ -1012,3 +1012,35 @@ def test_mip360_mlp_forward_gaussians_entry():
         assert max_abs(out["rgb"].cpu(), cref) < (1e-6 if disable_rgb else 5e-3)
         inside = mean.norm(dim=-1) <= 1.0
         assert rel_err(out["density"].cpu()[inside], dref[inside]) < TOL
+
+
+# ----------------------------------------------------------------------------- human branch at the BASELINE size + its fp32 floor
+def test_human_c3_size_vs_oracle_with_measured_floor():
+    """C3 of BASELINE.json: 6144 rays x 128 samples through Network.forward (S2 return dict), fp32 and fp16 modes, against the
+    CPU oracle on the same rays - and the oracle evaluated with torch ON THE GPU against itself on the CPU, which measures how far
+    two correct fp32 evaluations of this branch are apart (the canonical MLP sees sin(2^9 x): one ulp of the warped point is
+    amplified ~500x before the first layer).  Gates: rendered rgb 1e-4 wherever the reference is conditioned that well, i.e.
+    the worst ray must stay within max(1e-4, 2 x the measured floor); density per sample within max(5e-3, 2 x floor)."""
+    n = 6144
+    net = _human(stage2=True)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    b = synth.make_human_batch(n)
+    with torch.no_grad():
+        ref = HR.network_forward(sd, b, stage2=True)
+        with torch.device(DEV):
+            refg = HR.network_forward({k: cu(v) for k, v in sd.items()}, {k: cu(v) for k, v in b.items()}, stage2=True)
+        floor_rgb = rel_err(refg["rgb"].cpu(), ref["rgb"])
+        floor_raw = rel_err(refg["_raw"].cpu()[..., 3], ref["_raw"][..., 3])
+        rec = {"rays": n, "oracle_gpu_vs_cpu_rgb": floor_rgb, "oracle_gpu_vs_cpu_sigma_raw": floor_raw}
+        for prec in ("fp32", "fp16"):
+            net.precision = prec
+            out = net(**{k: cu(v) for k, v in b.items()}, cycle_outputs=False)
+            rec[f"{prec}_rgb_rel"] = rel_err(out["rgb"].cpu(), ref["rgb"])
+            rec[f"{prec}_rgb_abs"] = max_abs(out["rgb"].cpu(), ref["rgb"])
+            rec[f"{prec}_weights_rel"] = rel_err(out["weights"].cpu(), ref["weights"])
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/parity_baseline_C3.json", "w") as f:
+        json.dump(rec, f, indent=1)
+    assert rec["fp32_rgb_rel"] < max(TOL, 2 * floor_rgb), rec
+    assert rec["fp32_weights_rel"] < max(5e-3, 2 * floor_raw), rec
+    assert rec["fp16_rgb_abs"] < 1e-2, rec
