@@ -43,6 +43,12 @@ class BkgConfig(C.Structure):     # hos_bkg_config
                 ("mlp_events", C.POINTER(C.c_void_p))]
 
 
+class HumanConfig(C.Structure):       # hos_human_config
+    _fields_ = [("nr_mlp", C.c_void_p), ("cnl_mlp", C.c_void_p), ("n_samples", c_i), ("t_lin", c_f), ("jitter", c_f),
+                ("R", c_f), ("T", c_f), ("vol", c_f), ("bones", c_i), ("grid", c_i), ("bbox_min_host", c_hp), ("bbox_scale_host", c_hp),
+                ("nr_freqs", c_i), ("hann_w", c_f), ("cnl_freqs", c_i), ("stage2", c_i), ("bgcolor_host", c_hp)]
+
+
 class GemmTmaDesc(C.Structure):      # hos_gemm_tma_desc
     _fields_ = [("mode", c_i), ("rows", c_l),
                 ("a0_hi", c_f), ("a0_lo", c_f), ("k0", c_i), ("lda0", c_i),
@@ -108,6 +114,8 @@ SIGNATURES = {
                                c_f, c_f, c_f, c_f, c_f]),
     "hos_render_bkg_workspace": (c_i, [C.POINTER(BkgConfig), c_i, C.POINTER(C.c_size_t)]),
     "hos_render_bkg": (c_i, [C.POINTER(BkgConfig), c_f, c_f, c_f, c_f, c_i, c_f, C.c_size_t, c_f, c_f, c_f, c_f]),
+    "hos_render_human_workspace": (c_i, [C.POINTER(HumanConfig), c_i, C.POINTER(C.c_size_t)]),
+    "hos_render_human": (c_i, [C.POINTER(HumanConfig), c_f, c_f, c_f, c_f, c_i, c_f, C.c_size_t, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f]),
     "hos_lossfun_distortion": (c_i, [c_f, c_f, c_i, c_i, c_f, c_f]),
     "hos_lossfun_outer": (c_i, [c_f, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_f]),
     "hos_lossfun_distortion_backward": (c_i, [c_f, c_f, c_f, c_fl, c_i, c_i, c_f, c_f]),
@@ -119,7 +127,7 @@ _lib = None
 LAUNCHES = 0          # kernels of this library launched so far (bench.py reports it per timed region)
 _KERNELS_PER_CALL = {"hos_composite_s3": 2, "hos_mlp_set_layer": 2, "hos_mlp_set_bias": 1, "hos_mlp_set_head": 0,
                      "hos_mlp_set_ipe_input": 0, "hos_mlp_set_variant": 0, "hos_gemm_set_head": 0,
-                     "hos_render_bkg_workspace": 0, "hos_render_bkg": 0}      # hos_render_bkg: counted by its caller
+                     "hos_render_bkg_workspace": 0, "hos_render_bkg": 0, "hos_render_human_workspace": 0, "hos_render_human": 7}      # hos_render_bkg: counted by its caller
 
 
 def load():

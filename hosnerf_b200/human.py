@@ -31,6 +31,11 @@ from . import mip360 as _m
 from .synth import PARENT as SMPL_PARENT
 
 
+# eval chunks in fp16 mode go through ONE library call (hos_render_human) when the cycle / flow side paths are not asked for;
+# False keeps the kernel-by-kernel chain (same kernels, same order, same results - used by the A/B test)
+ONE_CALL = True
+
+
 class Cfg(dict):
     """Minimal attribute dict standing in for the reference's yacs CfgNode in tests / bench."""
     __getattr__ = dict.__getitem__
@@ -501,6 +506,55 @@ class Network(nn.Module):
         Ts = torch.cat([dst_Ts[:, 0:1], dst_Ts[:, 1:] + dT], dim=1)
         return Rs, Ts
 
+    # ------------------------------------------------------------------ one C call per chunk
+    def _render_chunk_fused(self, fr, rays_o, rays_d, near, far, t_lin, jitter, bgcolor):
+        """``hos_render_human``: samples -> LBS -> Hann PE -> non-rigid MLP -> Fourier PE -> canonical MLP (-> S2 composite) of one
+        ray chunk behind one library call, intermediates in a cached workspace.  Same kernels and order as the chain in
+        ``forward``; what is saved is the per-kernel Python / allocator work."""
+        import ctypes
+        from . import _lib
+        cfg = self.cfg
+        n, S, dev = rays_o.shape[0], cfg.N_samples, rays_o.device
+        hc = _lib.HumanConfig()
+        nr = None if cfg.ignore_non_rigid_motions else self._fused_nr("nr", self.non_rigid_mlp, fr["cond"])
+        cn = self._fused_cnl(fr["state_idx"])
+        hc.nr_mlp, hc.cnl_mlp = (None if nr is None else nr._h), cn._h
+        hc.n_samples, hc.t_lin, hc.jitter = S, t_lin.data_ptr(), (None if jitter is None else jitter.data_ptr())
+        R, T, vol = fr["Rb"][0].contiguous(), fr["Tb"][0].contiguous(), fr["vol"]
+        hc.R, hc.T, hc.vol, hc.bones, hc.grid = R.data_ptr(), T.data_ptr(), vol.data_ptr(), R.shape[0], vol.shape[-1]
+        bmin = (ctypes.c_float * 3)(*fr["bbox_min"])
+        bsc = (ctypes.c_float * 3)(*fr["bbox_scale"])
+        hc.bbox_min_host, hc.bbox_scale_host = bmin, bsc
+        hc.nr_freqs, hc.hann_w, hc.cnl_freqs, hc.stage2 = self.nr_freqs, fr["hann_w"].data_ptr(), self.cnl_freqs, int(self.stage2)
+        bg = None
+        if bgcolor is not None:
+            bg = (ctypes.c_float * 3)(*[float(x) for x in bgcolor.detach().cpu().reshape(-1).tolist()])
+            hc.bgcolor_host = bg
+        key = (n, S, str(dev), self.nr_freqs, self.cnl_freqs)
+        if self._cache.get("hws_key") != key:
+            nbytes = ctypes.c_size_t(0)
+            _lib.call("hos_render_human_workspace", ctypes.byref(hc), n, ctypes.byref(nbytes))
+            self._cache["hws_key"], self._cache["hws"] = key, torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        ws = self._cache["hws"]
+        f32 = dict(device=dev, dtype=torch.float32)
+        pts, z = torch.empty(n, S, 3, **f32), torch.empty(n, S, **f32)
+        ret = {}
+        if self.stage2:
+            rgb, acc, w, depth = torch.empty(n, 3, **f32), torch.empty(n, **f32), torch.empty(n, S, **f32), torch.empty(n, **f32)
+            outs = (rgb.data_ptr(), acc.data_ptr(), w.data_ptr(), depth.data_ptr(), None, None)
+            ret.update(rgb=rgb, alpha=acc, depth=depth, weights=w)
+        else:
+            raw, mask = torch.empty(n, S, 4, **f32), torch.empty(n, S, **f32)
+            outs = (None, None, None, None, raw.data_ptr(), mask.data_ptr())
+            ret.update(human_rgb=raw[..., :3], human_density=raw[..., 3], newsmpl_pts=pts, pts_mask=mask, z_vals=z, rays_d=rays_d)
+        _lib.call("hos_render_human", ctypes.byref(hc), rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr(), n,
+                  ws.data_ptr(), ws.numel(), *outs, pts.data_ptr(), z.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        if self.stage2:
+            _lib.LAUNCHES += 0       # hos_render_human counts its 7 launches (6 without the composite) in _KERNELS_PER_CALL
+        ret["deform_pts_final"] = pts[0, 0, :][None, :]
+        ret["observe_pts"] = pts[0, 0, :][None, :]
+        return ret
+
     # ------------------------------------------------------------------ training forward (autograd)
     @staticmethod
     def _motion_bases_autograd(Rs, Ts, cnl_gtfms):
@@ -694,8 +748,15 @@ class Network(nn.Module):
             outs = {}
             if n == 0:
                 raise RuntimeError("hosnerf_b200.Network: empty ray batch (the reference fails on it too: torch.cat of no chunks)")
+            one_call = ONE_CALL and precision == "fp16" and not flow and not kwargs.get("cycle_outputs", True)
             for c0 in range(0, n, cfg.chunk):
                 c1 = min(n, c0 + cfg.chunk)
+                if one_call:
+                    ret = self._render_chunk_fused(fr, rays_o[c0:c1], rays_d[c0:c1], near[c0:c1], far[c0:c1], t_lin,
+                                                   None if jitter is None else jitter[c0:c1], bgcolor)
+                    for k, v in ret.items():
+                        outs.setdefault(k, []).append(v)
+                    continue
                 z, pts = ops.human_samples(rays_o[c0:c1], rays_d[c0:c1], near[c0:c1], far[c0:c1], t_lin,
                                            None if jitter is None else jitter[c0:c1])
                 x_skel, mask = ops.lbs_warp(pts, Rb[0], Tb[0], vol, bbox_min, bbox_scale)

@@ -1044,3 +1044,25 @@ def test_human_c3_size_vs_oracle_with_measured_floor():
     assert rec["fp32_rgb_rel"] < max(TOL, 2 * floor_rgb), rec
     assert rec["fp32_weights_rel"] < max(5e-3, 2 * floor_raw), rec
     assert rec["fp16_rgb_abs"] < 1e-2, rec
+
+
+@pytest.mark.parametrize("stage2", [True, False])
+def test_render_human_one_call_matches_chain(stage2):
+    """hos_render_human (one C call per chunk: samples -> LBS -> PE -> non-rigid MLP -> PE -> canonical MLP (-> S2 composite))
+    against the kernel-by-kernel chain: same kernels, same order - identical results, ragged chunking included."""
+    import hosnerf_b200.human as H
+    net = _human(stage2=stage2, precision="fp16", chunk=200)
+    b = _hb(333)
+    outs = []
+    for flag in (True, False):
+        H.ONE_CALL = flag
+        try:
+            with torch.no_grad():
+                outs.append(net(**b, cycle_outputs=False))
+        finally:
+            H.ONE_CALL = True
+    keys = ("rgb", "alpha", "depth", "weights") if stage2 else ("human_rgb", "human_density", "pts_mask", "newsmpl_pts", "z_vals")
+    for k in keys:
+        assert outs[0][k].shape == outs[1][k].shape, k
+        assert torch.equal(outs[0][k], outs[1][k]), k
+    assert float(outs[0][keys[0]].abs().max()) > 0
