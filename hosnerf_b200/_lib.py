@@ -46,7 +46,7 @@ class BkgConfig(C.Structure):     # hos_bkg_config
 class HumanConfig(C.Structure):       # hos_human_config
     _fields_ = [("nr_mlp", C.c_void_p), ("cnl_mlp", C.c_void_p), ("n_samples", c_i), ("t_lin", c_f), ("jitter", c_f),
                 ("R", c_f), ("T", c_f), ("vol", c_f), ("bones", c_i), ("grid", c_i), ("bbox_min_host", c_hp), ("bbox_scale_host", c_hp),
-                ("nr_freqs", c_i), ("hann_w", c_f), ("cnl_freqs", c_i), ("stage2", c_i), ("bgcolor_host", c_hp)]
+                ("nr_freqs", c_i), ("hann_w", c_f), ("hann_w_host", c_hp), ("cnl_freqs", c_i), ("stage2", c_i), ("bgcolor_host", c_hp)]
 
 
 class GemmTmaDesc(C.Structure):      # hos_gemm_tma_desc
@@ -91,6 +91,8 @@ SIGNATURES = {
     "hos_mlp_forward": (c_i, [C.c_void_p, c_f, c_l, c_f, c_i, c_f, c_f, c_f, c_f]),
     "hos_mlp_set_ipe_input": (c_i, [C.c_void_p, c_i]),
     "hos_mlp_forward_ipe": (c_i, [C.c_void_p, c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_f, c_i, c_f, c_f, c_f]),
+    "hos_mlp_fourier_supported": (c_i, [C.c_void_p, c_l]),
+    "hos_mlp_forward_fourier": (c_i, [C.c_void_p, c_f, c_l, c_i, c_i, c_hp, c_f, c_f, c_f, c_f]),
     "hos_mlp_debug_timeline": (c_i, [C.c_void_p, c_f]),
     "hos_mlp_set_variant": (c_i, [C.c_void_p, c_i]),
     "hos_pack_rows_f16": (c_i, [c_f, c_l, c_i, c_i, c_f, c_f]),

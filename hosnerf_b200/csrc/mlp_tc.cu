@@ -99,7 +99,11 @@ struct MlpArgs {
   int64_t rows;
   int ntiles;
   int rowbias_div;
-  int fused_ipe;
+  int fused_ipe;                  // 0: features from x_tiled; 1: IPE prologue (IpeArgs); 2: Fourier prologue (pair kernel only):
+                                  // the feature warps encode fx [rows,3] straight into the A-operand ring, one 64-column chunk
+  const float* fx;                // mode 2: points [rows, 3]
+  int f_nfreq, f_ident;           // mode 2: octaves 2^0 .. 2^(f_nfreq-1); identity columns first (fourier.py) or not (hannw_fourier.py)
+  float f_hann[16];               // mode 2: per-octave window weights (all 1 for the plain embedder)
   long long* timeline;            // optional debug: per (tile iteration, layer) 4 clock64() stamps of CTA 0
 };
 
@@ -590,6 +594,35 @@ constexpr int kRowBiasVecs = 4;
 constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 2 + kPairMaxKbh + 2;
 static_assert(kPairBars % 2 == 0, "s_headx behind the barriers is read as float4");
 
+// One row of the Fourier / Hann-windowed embedding as 64 packed fp16 values (column order of the reference embedders; columns
+// beyond the embedding width are zero): one accurate sincos per coordinate, higher octaves by angle doubling.
+template <bool IDENT>
+__device__ __forceinline__ void fourier_row(const float (&p)[3], int nfreq, const float* hann, bool ok, uint32_t (&pk)[32]) {
+  float vals[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) vals[j] = 0.f;
+  float sn[3], cs[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) sincosf(p[a], &sn[a], &cs[a]);
+  constexpr int base = IDENT ? 3 : 0;
+  if (IDENT) { vals[0] = p[0]; vals[1] = p[1]; vals[2] = p[2]; }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {                               // 3 + 6 * 10 = 63 columns at most
+    if (k < nfreq) {
+      const float w = hann[k];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        vals[base + 6 * k + a] = w * sn[a];
+        vals[base + 6 * k + 3 + a] = w * cs[a];
+        const float s2 = 2.f * sn[a] * cs[a], c2 = 1.f - 2.f * sn[a] * sn[a];
+        sn[a] = s2; cs[a] = c2;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) pk[j] = cvt_f16x2(__float_as_uint(ok ? vals[2 * j] : 0.f), __float_as_uint(ok ? vals[2 * j + 1] : 0.f));
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
                 const __grid_constant__ IpeArgs ipe, const int stages_w) {
@@ -620,7 +653,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const bool fused = args.fused_ipe != 0;
+  const bool fused = args.fused_ipe != 0;                  // features written by the feature warps (IPE or Fourier prologue)
   const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int n_groups = (args.ntiles + 1) >> 1;             // 2 tiles per group: tile = 2 g + rank
   const int n_layers = prog.n_layers;
@@ -1061,7 +1094,40 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         if (tl) args.timeline[u * 12 + 5] = clock64();
       }
     }
-  } else if (fused && warp >= kFeatWarp0) {
+  } else if (args.fused_ipe == 2 && warp >= kFeatWarp0) {
+    // ===================== feature generators, Fourier prologue (human branch) =====================
+    // identity | per octave k: w_k sin(2^k p) (3), w_k cos(2^k p) (3)  (fourier.py:13-57, hannw_fourier.py:15-71): one sincos per
+    // coordinate, higher octaves by angle doubling (error 2^k x 1e-7, below the fp16 resolution of the operand); one 64-column
+    // chunk per reading layer, so the encoded points never exist outside shared memory.
+    const int r = (warp - kFeatWarp0) * 32 + lane;
+    const uint32_t xremote = rank != 0 ? mapa_u32(smem_u32(&bar_xfull[0]), 0) : 0u;
+    const uint32_t row_u32 = smem_u32(sRingX) + 128u * (uint32_t)r, r7 = (uint32_t)(r & 7);
+    uint32_t xi = 0;
+    for (int g = cluster; g < n_groups; g += n_clusters) {
+      const int64_t row = (int64_t)(2 * g + (int)rank) * kTileM + r;
+      const bool ok = row < args.rows;
+      float p[3] = {0.f, 0.f, 0.f};
+      if (ok) { p[0] = args.fx[row * 3 + 0]; p[1] = args.fx[row * 3 + 1]; p[2] = args.fx[row * 3 + 2]; }
+      uint32_t pk[32];                                         // the row's 64 fp16 features
+      if (args.f_ident) fourier_row<true>(p, args.f_nfreq, args.f_hann, ok, pk);
+      else fourier_row<false>(p, args.f_nfreq, args.f_hann, ok, pk);
+      for (int l = 0; l < n_layers; ++l) {
+        if (prog.layers[l].kb_x == 0) continue;
+        const int xs = xi % kPairStagesX;
+        mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kPairStagesX) & 1) ^ 1);
+        const uint32_t slot = row_u32 + (uint32_t)xs * kXChunkBytes;
+#pragma unroll
+        for (int gq = 0; gq < 8; ++gq) sts128(slot + (((uint32_t)gq ^ r7) << 4), pk[4 * gq], pk[4 * gq + 1], pk[4 * gq + 2], pk[4 * gq + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (xremote) mbar_arrive_remote(xremote + 8u * (uint32_t)xs);
+          else mbar_arrive(&bar_xfull[xs]);
+        }
+        ++xi;
+      }
+    }
+  } else if (args.fused_ipe == 1 && warp >= kFeatWarp0) {
     // ===================== feature generators (warps 12..15): fused IPE prologue =====================
     const int r = (warp - kFeatWarp0) * 32 + lane;
     const uint32_t xremote = rank != 0 ? mapa_u32(smem_u32(&bar_xfull[0]), 0) : 0u;
@@ -1638,8 +1704,14 @@ int hos_mlp_set_head(hos_mlp_t* m, int head, const float* W, const float* b, voi
 
 int hos_mlp_in_kblocks(const hos_mlp_t* m) { return m ? m->prog.kbx : 0; }
 
+struct FourierArgs {
+  const float* x;
+  int nfreq, ident;
+  float hann[16];
+};
+
 static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int64_t rows, const float* rowbias,
-                      int rowbias_div, const float* add, float* out0, float* out1, void* stream) {
+                      int rowbias_div, const float* add, float* out0, float* out1, void* stream, const FourierArgs* fe = nullptr) {
   for (int l = 0; l < m->prog.n_layers; ++l)
     HOS_REQUIRE(!m->prog.layers[l].rowbias || (rowbias && rowbias_div >= 1), "hos_mlp_forward: layer %d needs rowbias", l);
   for (int h = 0; h < m->prog.n_heads; ++h) {
@@ -1659,11 +1731,19 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   a.ntiles = (int)((rows + kTileM - 1) / kTileM);
   a.rowbias_div = rowbias_div < 1 ? 1 : rowbias_div;
   a.fused_ipe = ipe != nullptr;
+  a.fx = nullptr; a.f_nfreq = 0; a.f_ident = 0;
+  for (int i = 0; i < 16; ++i) a.f_hann[i] = 1.f;
+  if (fe) {
+    a.fused_ipe = 2;
+    a.fx = fe->x; a.f_nfreq = fe->nfreq; a.f_ident = fe->ident;
+    for (int i = 0; i < 16; ++i) a.f_hann[i] = fe->hann[i];
+  }
   a.timeline = m->timeline;
   static const IpeArgs kNoIpe = {};
   HOS_REQUIRE(m->variant != 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
   // the pair kernel walks groups of 4 tiles; tiny batches keep more SMs busy on the single-CTA kernel
   const bool pair = m->smem_pair && m->variant != 1 && (m->variant == 2 || a.ntiles >= 2);
+  HOS_REQUIRE(!fe || pair, "hos_mlp_forward_fourier: needs the cluster-pair kernel (uniform hidden width, >= 2 row tiles)");
   if (pair) {
     const int n_groups = (a.ntiles + 1) / 2;
     const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
@@ -1683,6 +1763,22 @@ int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float
   HOS_REQUIRE(m && x_tiled && rows >= 0, "hos_mlp_forward: bad handle/input");
   HOS_REQUIRE(!m->ipe_perm, "hos_mlp_forward: this MLP was created for the fused IPE prologue (use hos_mlp_forward_ipe)");
   return mlp_launch(m, x_tiled, nullptr, rows, rowbias, rowbias_div, add, out0, out1, stream);
+}
+
+int hos_mlp_fourier_supported(const hos_mlp_t* m, int64_t rows) {
+  return m && m->smem_pair && m->variant != 1 && !m->ipe_perm && m->prog.kbx == 1 && (m->variant == 2 || (rows + kTileM - 1) / kTileM >= 2);
+}
+
+int hos_mlp_forward_fourier(hos_mlp_t* m, const float* x, int64_t rows, int n_freqs, int include_input, const float* hann_host,
+                            const float* add, float* out0, float* out1, void* stream) {
+  HOS_ARCH_GUARD();
+  HOS_REQUIRE(m && x && rows >= 0 && n_freqs >= 1 && n_freqs <= 10, "hos_mlp_forward_fourier: bad arguments (1 <= n_freqs <= 10)");
+  HOS_REQUIRE(m->in_dim == (include_input ? 3 : 0) + 6 * n_freqs && m->prog.kbx == 1 && !m->ipe_perm,
+              "hos_mlp_forward_fourier: the MLP reads %d encoded columns, the prologue produces %d", m->in_dim, (include_input ? 3 : 0) + 6 * n_freqs);
+  FourierArgs fe;
+  fe.x = x; fe.nfreq = n_freqs; fe.ident = include_input != 0;
+  for (int i = 0; i < 16; ++i) fe.hann[i] = (hann_host && i < n_freqs) ? hann_host[i] : 1.f;
+  return mlp_launch(m, nullptr, nullptr, rows, nullptr, 1, add, out0, out1, stream, &fe);
 }
 
 int hos_mlp_set_variant(hos_mlp_t* m, int variant) {

@@ -86,14 +86,25 @@ int hos_render_human(const hos_human_config* cfg, const float* rays_o, const flo
   if ((st = hos_human_samples(rays_o, rays_d, near, far, cfg->t_lin, cfg->jitter, n, S, z, pts, stream)) != HOS_OK) return st;
   if ((st = hos_lbs_warp(pts, cfg->R, cfg->T, cfg->vol, cfg->bbox_min_host, cfg->bbox_scale_host, P, cfg->bones, cfg->grid, w.x_skel,
                          mask, stream)) != HOS_OK) return st;
+  // Encodings: generated inside the MLP kernel (Fourier prologue) when the handle / batch supports it, else materialised.
   const float* cnl = w.x_skel;
   if (cfg->nr_mlp) {          // x + offset(x)  (network.py:165-172)
-    if ((st = hos_fourier_embed(w.x_skel, P, cfg->nr_freqs, 0, cfg->hann_w, w.pe_nr, 0, 2, stream)) != HOS_OK) return st;
-    if ((st = hos_mlp_forward(cfg->nr_mlp, w.pe_nr, P, nullptr, 1, w.x_skel, w.cnl, nullptr, stream)) != HOS_OK) return st;
+    if (cfg->hann_w_host && hos_mlp_fourier_supported(cfg->nr_mlp, P) && cfg->nr_freqs <= 10) {
+      st = hos_mlp_forward_fourier(cfg->nr_mlp, w.x_skel, P, cfg->nr_freqs, 0, cfg->hann_w_host, w.x_skel, w.cnl, nullptr, stream);
+    } else {
+      if ((st = hos_fourier_embed(w.x_skel, P, cfg->nr_freqs, 0, cfg->hann_w, w.pe_nr, 0, 2, stream)) != HOS_OK) return st;
+      st = hos_mlp_forward(cfg->nr_mlp, w.pe_nr, P, nullptr, 1, w.x_skel, w.cnl, nullptr, stream);
+    }
+    if (st != HOS_OK) return st;
     cnl = w.cnl;
   }
-  if ((st = hos_fourier_embed(cnl, P, cfg->cnl_freqs, 1, nullptr, w.pe_cnl, 0, 2, stream)) != HOS_OK) return st;
-  if ((st = hos_mlp_forward(cfg->cnl_mlp, w.pe_cnl, P, nullptr, 1, nullptr, raw, nullptr, stream)) != HOS_OK) return st;
+  if (cfg->hann_w_host && hos_mlp_fourier_supported(cfg->cnl_mlp, P) && cfg->cnl_freqs <= 10) {
+    st = hos_mlp_forward_fourier(cfg->cnl_mlp, cnl, P, cfg->cnl_freqs, 1, nullptr, nullptr, raw, nullptr, stream);
+  } else {
+    if ((st = hos_fourier_embed(cnl, P, cfg->cnl_freqs, 1, nullptr, w.pe_cnl, 0, 2, stream)) != HOS_OK) return st;
+    st = hos_mlp_forward(cfg->cnl_mlp, w.pe_cnl, P, nullptr, 1, nullptr, raw, nullptr, stream);
+  }
+  if (st != HOS_OK) return st;
   if (cfg->stage2)
     return hos_composite_nerf(raw, mask, z, rays_d, cfg->bgcolor_host, n, S, 1, rgb_out, acc_out, weights_out, depth_out, stream);
   return HOS_OK;

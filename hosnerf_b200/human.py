@@ -34,6 +34,8 @@ from .synth import PARENT as SMPL_PARENT
 # eval chunks in fp16 mode go through ONE library call (hos_render_human) when the cycle / flow side paths are not asked for;
 # False keeps the kernel-by-kernel chain (same kernels, same order, same results - used by the A/B test)
 ONE_CALL = True
+# inside the one-call path: generate both positional encodings in the MLP kernels' prologue (False: materialise them in HBM first)
+FUSE_FOURIER = True
 
 
 class Cfg(dict):
@@ -526,6 +528,12 @@ class Network(nn.Module):
         bsc = (ctypes.c_float * 3)(*fr["bbox_scale"])
         hc.bbox_min_host, hc.bbox_scale_host = bmin, bsc
         hc.nr_freqs, hc.hann_w, hc.cnl_freqs, hc.stage2 = self.nr_freqs, fr["hann_w"].data_ptr(), self.cnl_freqs, int(self.stage2)
+        hann_host = None
+        if FUSE_FOURIER:           # encodings generated inside the MLP kernels (hos_mlp_forward_fourier)
+            if "hann_host" not in fr:
+                fr["hann_host"] = [float(v) for v in fr["hann_w"].detach().cpu().tolist()]
+            hann_host = (ctypes.c_float * len(fr["hann_host"]))(*fr["hann_host"])
+            hc.hann_w_host = hann_host
         bg = None
         if bgcolor is not None:
             bg = (ctypes.c_float * 3)(*[float(x) for x in bgcolor.detach().cpu().reshape(-1).tolist()])

@@ -1054,15 +1054,39 @@ def test_render_human_one_call_matches_chain(stage2):
     net = _human(stage2=stage2, precision="fp16", chunk=200)
     b = _hb(333)
     outs = []
-    for flag in (True, False):
-        H.ONE_CALL = flag
-        try:
+    H.FUSE_FOURIER = False            # same encoding kernels on both sides (the fused prologue has its own test below)
+    try:
+        for flag in (True, False):
+            H.ONE_CALL = flag
             with torch.no_grad():
                 outs.append(net(**b, cycle_outputs=False))
-        finally:
-            H.ONE_CALL = True
+    finally:
+        H.ONE_CALL, H.FUSE_FOURIER = True, True
     keys = ("rgb", "alpha", "depth", "weights") if stage2 else ("human_rgb", "human_density", "pts_mask", "newsmpl_pts", "z_vals")
     for k in keys:
         assert outs[0][k].shape == outs[1][k].shape, k
         assert torch.equal(outs[0][k], outs[1][k]), k
     assert float(outs[0][keys[0]].abs().max()) > 0
+
+
+@pytest.mark.parametrize("stage2", [True, False])
+def test_fused_fourier_prologue_matches_materialised_encoding(stage2):
+    """Encodings generated in the MLP kernel's prologue (hos_mlp_forward_fourier: sincos + angle doubling into the A-operand ring)
+    against the same MLPs fed with the materialised tiled encodings: both round to fp16 operands."""
+    import hosnerf_b200.human as H
+    net = _human(stage2=stage2, precision="fp16")
+    b = _hb(400)
+    outs = []
+    for flag in (True, False):
+        H.FUSE_FOURIER = flag
+        try:
+            with torch.no_grad():
+                outs.append(net(**b, cycle_outputs=False))
+        finally:
+            H.FUSE_FOURIER = True
+    if stage2:
+        assert max_abs(outs[0]["rgb"], outs[1]["rgb"]) < 2e-3
+        assert rel_err(outs[0]["weights"], outs[1]["weights"]) < 2e-2
+    else:
+        assert max_abs(outs[0]["human_rgb"], outs[1]["human_rgb"]) < 5e-3
+        assert rel_err(outs[0]["human_density"], outs[1]["human_density"]) < 3e-2
