@@ -69,3 +69,42 @@ def rays_intersect_3d_bbox(bounds, ray_o, ray_d):
                                torch.cuda.current_stream().cuda_stream)
     m = mask.bool()
     return near[m], far[m], m
+
+
+def batchified_get_rays(intrinsics, extrinsics, image_sizes, use_pixel_centers, get_radii, ndc_coord=False, ndc_coeffs=None,
+                        multlosses=None, device="cuda"):
+    """Stage-1 dataset ray generator (S1 src/data/ray_utils.py:34-139), non-NDC branch (the 360 scenes): for every image
+    pixel-centre directions through the intrinsics, rotated by the camera-to-world extrinsic, origins = camera centres,
+    ``viewdirs`` = normalised directions - and, like the reference (``viewdirs = rays_d; viewdirs /= norm`` aliases the array),
+    ``rays_d`` comes back normalised too - radii from the distance between vertically neighbouring un-normalised directions
+    (x 2 / sqrt(12)), per-image loss multipliers expanded per ray.  Runs once per dataset, as float32 torch ops on the device
+    (the reference pins NumPy 1.23, whose value-based casting keeps this arithmetic in float32); returns CUDA tensors
+    (rays_o, rays_d, viewdirs [N,3], radii [N,1] or None, multloss_expand [N,1] or None)."""
+    if ndc_coord:
+        raise NotImplementedError("hosnerf_b200.camera.batchified_get_rays: the NDC branch (forward-facing scenes) is not built")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("hosnerf_b200.camera: rays are generated on a CUDA device (this package has no CPU path)")
+    center = 0.5 if use_pixel_centers else 0.0
+    f32 = dict(device=dev, dtype=torch.float32)
+    ros, rds, radii, mults = [], [], [], []
+    for idx, ((h, w), K, E) in enumerate(zip(image_sizes, intrinsics, extrinsics)):
+        K = torch.as_tensor(np.asarray(K), **f32)
+        E = torch.as_tensor(np.asarray(E), **f32)
+        i = (torch.arange(w, **f32) + center)[None, :].expand(h, w)
+        j = (torch.arange(h, **f32) + center)[:, None].expand(h, w)
+        dirs = torch.stack([(i - K[0, 2]) / K[0, 0], (j - K[1, 2]) / K[1, 1], torch.ones_like(i)], -1)       # [h, w, 3]
+        d = torch.einsum("hwc,rc->hwr", dirs, E[:3, :3])
+        ros.append(E[:3, 3].expand(h * w, 3))
+        if get_radii:
+            dx = torch.sqrt(torch.sum((d[:-1] - d[1:]) ** 2, -1))
+            dx = torch.cat([dx, dx[-2:-1]], 0)
+            radii.append((dx[..., None] * 2 / np.sqrt(12)).reshape(-1))
+        rds.append(d.reshape(-1, 3))
+        if multlosses is not None:
+            mults.append(torch.full((h * w,), float(multlosses[idx]), **f32))
+    rays_o = torch.cat(ros).contiguous()
+    rays_d = torch.cat(rds)
+    rays_d = (rays_d / torch.linalg.norm(rays_d, dim=-1, keepdim=True)).contiguous()
+    return (rays_o, rays_d, rays_d, torch.cat(radii)[:, None] if get_radii else None,
+            torch.cat(mults)[:, None] if multlosses is not None else None)

@@ -69,3 +69,19 @@ def test_rays_intersect_bbox_large_vs_oracle_and_edges():
     assert n0.numel() == 0 and m0.numel() == 0
     with pytest.raises(RuntimeError, match="CUDA"):
         camera.rays_intersect_3d_bbox(bounds, torch.zeros(4, 3), torch.ones(4, 3))
+
+
+def test_batchified_get_rays_golden():
+    """Stage-1 dataset ray generator (S1 src/data/ray_utils.py:34-139) against the reference's own output on three small cameras:
+    origins exact, directions / radii within 2 float32 ulps (NumPy-version dependent promotion in the reference, see the
+    generator), rays_d returned normalised like the reference's aliased array."""
+    import numpy as np
+    from hosnerf_b200 import camera
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "batchified_rays.npz"))
+    sizes = [tuple(int(v) for v in s) for s in z["sizes"]]
+    ro, rd, vd, radii, ml = camera.batchified_get_rays(list(z["intr"]), list(z["extr"]), sizes, True, True, False, None, [1.0, 0.5, 2.0])
+    assert torch.equal(ro.cpu(), torch.from_numpy(z["rays_o"]))
+    assert rd.data_ptr() == vd.data_ptr()
+    assert float((rd.cpu() - torch.from_numpy(z["rays_d"])).abs().max()) < 3e-7
+    assert float(((radii.cpu() - torch.from_numpy(z["radii"]).float()).abs() / torch.from_numpy(z["radii"]).float()).max()) < 2e-5
+    assert torch.equal(ml.cpu(), torch.from_numpy(z["multloss"]).float())
