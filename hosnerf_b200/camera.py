@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops
 
 _D = C.c_double
 
@@ -33,7 +33,7 @@ def _rays(H, W, K, R, T, bkg, dtype, device):
     with torch.cuda.device(dev):
         _lib.call("hos_rays_from_krt", int(H), int(W), _host(kinv, 9), _host(R, 9), _host(T, 3), int(bkg),
                   int(dtype == torch.float64), o.data_ptr(), d.data_ptr(), None if v is None else v.data_ptr(),
-                  None if r is None else r.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                  None if r is None else r.data_ptr(), ops._stream())
     return (o, d, v, r) if bkg else (o, d)
 
 
@@ -66,7 +66,7 @@ def rays_intersect_3d_bbox(bounds, ray_o, ray_d):
     with torch.cuda.device(dev):
         _lib.call_unless_empty(n, "hos_rays_intersect_bbox", _host(b[0], 3), _host(b[1], 3), ray_o.data_ptr(), ray_d.data_ptr(), n,
                                int(ray_o.dtype == torch.float64), near.data_ptr(), far.data_ptr(), mask.data_ptr(),
-                               torch.cuda.current_stream().cuda_stream)
+                               ops._stream())
     m = mask.bool()
     return near[m], far[m], m
 

@@ -135,5 +135,6 @@ class FlatGrads:
         for wk in self.works:
             wk.wait()
         self.works = []
+        self.reduced = set()                   # ready for the next step even when zero_() is replayed from a CUDA graph
         if w > 1 and average:
             self.flat.div_(w)

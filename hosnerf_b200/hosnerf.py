@@ -44,25 +44,34 @@ def cycle_loss(net_output: dict):
     return ops.reduce_scaled(a, 0.5 / max(a.shape[0], 1), y=b)
 
 
-def _composite_ray_set(samples, z, rays_d, mask):
+def _composite_ray_set(samples, z, rays_d, mask, graph_safe: bool = False):
     """S3 ``_raw2outputs`` (model.py:73-99) on depth-ordered samples [m, S, 4] (rgb in [0,1], sigma >= 0): torch ops with a
-    graph - the [rays, 192] tensors of a training chunk are a few hundred kilobytes."""
+    graph - the [rays, 192] tensors of a training chunk are a few hundred kilobytes.  ``graph_safe``: the transmittance as
+    exp(cumsum(log)) - torch's cumprod backward reads ``(x == 0).any()`` back to the host, which a CUDA-graph capture cannot do
+    (the factors are >= 1e-10, so the logarithm is finite)."""
     dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], dim=-1) * torch.norm(rays_d[..., None, :], dim=-1)
     alpha = (1.0 - torch.exp(-samples[..., 3] * dists)) * mask
-    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], dim=-1), dim=-1)[:, :-1]
+    if graph_safe:
+        T = torch.exp(torch.cumsum(torch.log(1. - alpha + 1e-10), dim=-1) - torch.log(1. - alpha + 1e-10))
+    else:
+        T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], dim=-1), dim=-1)[:, :-1]
     w = alpha * T
     return torch.sum(w[..., None] * samples[..., :3], -2), w
 
 
 def train_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dict, newsmpl_to_scale_world,
                         near_bkg: float = 0.1, far_bkg: float = 1e6, train_frac: float = 1.0, randomized: bool = True,
-                        thre_fg: float = 5e-3, rands=None):
+                        thre_fg: float = 5e-3, rands=None, dense: bool = False):
     """The differentiable body of the stage-3 ``training_step`` (S3 model.py:1501-1596): background branch (one
     ``train.RenderFn`` node: per-level weights and the final level's per-sample density / rgb carry the gradient), human-object
     branch (``Network.forward`` under autograd), depth merge + composite.  The merge itself (sort of 64 + 128 depths per
     foreground ray, gather, transmittance product) is a handful of torch ops on [rays, 192] tensors with autograd; the forward
     kernel ``hos_composite_s3`` is the eval path.  Returns dict(rgb [n,3], idx_fg, human_weights [n_fg, S_h], ray_history,
-    net_output)."""
+    net_output).
+
+    ``dense=True`` is the static-shape variant for CUDA-graph capture (``train.GraphedStep``): both composites run on every
+    ray and ``idx_fg`` selects between them, ``human_weights`` is [n, S_h] with zero rows on background rays, and nothing is
+    read back to the host.  Same rgb and gradients as the indexed form."""
     _, ray_history = bkg_model(batch_bkg, train_frac, randomized, True, near_bkg, far_bkg, rands=rands)
     kw = dict(batch_human)
     kw["is_train"] = True
@@ -74,7 +83,7 @@ def train_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dict
     M = newsmpl_to_scale_world.to(rays_o.device).float()
     pts = net_output["newsmpl_pts"].reshape(n, s_h, 3)
     world = torch.einsum("ji,bni->bnj", M, torch.cat([pts, torch.ones_like(pts[..., :1])], -1))[..., :3]
-    if bool(torch.any(torch.abs(rays_d) < 1e-5)):
+    if not dense and bool(torch.any(torch.abs(rays_d) < 1e-5)):
         raise NotImplementedError("hosnerf_b200.train_hosnerf_chunk: axis-aligned ray directions (the reference's per-axis branch, "
                                   "S3 model.py:1528-1543) are handled by the eval kernel only")
     zh = torch.mean((world - rays_o[:, None, :]) / (rays_d[:, None, :] + 1e-10), dim=-1)            # depth along the bkg ray
@@ -83,6 +92,18 @@ def train_hosnerf_chunk(bkg_model, human_net, batch_bkg: dict, batch_human: dict
     zb = h["tdist"][..., :-1]
     bkg = torch.cat([h["rgb"], h["density"][..., None]], -1)
     hum = torch.cat([net_output["human_rgb"].reshape(n, s_h, 3), net_output["human_density"].reshape(n, s_h, 1)], -1)
+    if dense:
+        nb = zb.shape[1]
+        z_sorted, order = torch.sort(torch.cat([zb, zh.detach()], -1), -1)
+        both = torch.gather(torch.cat([bkg, hum], 1), 1, order[..., None].expand(-1, -1, 4))
+        m = torch.gather(torch.cat([torch.ones_like(zb), mask], -1), 1, order)
+        rgb_fg, w_fg = _composite_ray_set(both, z_sorted, rays_d, m, graph_safe=True)
+        rgb_bg, _ = _composite_ray_set(bkg, zb, rays_d, torch.ones_like(zb), graph_safe=True)
+        rgb = torch.where(idx_fg[:, None], rgb_fg, rgb_bg)
+        # the human samples of a ray are already depth-ordered, so un-sorting puts their weights in the reference's order
+        w_orig = torch.zeros_like(w_fg).scatter(1, order, w_fg)
+        human_w = torch.where(idx_fg[:, None], w_orig[:, nb:], torch.zeros_like(w_orig[:, nb:]))
+        return {"rgb": rgb, "idx_fg": idx_fg, "human_weights": human_w, "ray_history": ray_history, "net_output": net_output}
     rgb = torch.zeros(n, 3, device=rays_o.device)
     human_w = torch.zeros(0, s_h, device=rays_o.device)
     if bool(idx_fg.any()):

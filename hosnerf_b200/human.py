@@ -321,6 +321,9 @@ class Network(nn.Module):
         self.cfg = cfg
         self.stage2 = stage2
         self.precision = precision
+        # True: the training forward keeps every shape static and reads nothing back to the host (device-side bone chain, dense
+        # cycle side path with ``cycle_mask``, device jitter) so a whole step can be captured in a CUDA graph (train.GraphedStep)
+        self.static_shapes = False
         nb = cfg.total_bones
         self.motion_basis_computer = MotionBasisComputer(total_bones=nb)
         self.mweight_vol_decoder = MotionWeightVolumeDecoder(
@@ -556,7 +559,7 @@ class Network(nn.Module):
             outs = (None, None, None, None, raw.data_ptr(), mask.data_ptr())
             ret.update(human_rgb=raw[..., :3], human_density=raw[..., 3], newsmpl_pts=pts, pts_mask=mask, z_vals=z, rays_d=rays_d)
         _lib.call("hos_render_human", ctypes.byref(hc), rays_o.data_ptr(), rays_d.data_ptr(), near.data_ptr(), far.data_ptr(), n,
-                  ws.data_ptr(), ws.numel(), *outs, pts.data_ptr(), z.data_ptr(), torch.cuda.current_stream().cuda_stream)
+                  ws.data_ptr(), ws.numel(), *outs, pts.data_ptr(), z.data_ptr(), ops._stream())
         if self.stage2:
             _lib.LAUNCHES += 0       # hos_render_human counts its 7 launches (6 without the composite) in _KERNELS_PER_CALL
         ret["deform_pts_final"] = pts[0, 0, :][None, :]
@@ -583,6 +586,45 @@ class Network(nn.Module):
         return (back[0, :, :3, :3].contiguous().to(dev), back[0, :, :3, 3].contiguous().to(dev),
                 fwd[0, :, :3, :3].contiguous().to(dev), fwd[0, :, :3, 3].contiguous().to(dev))
 
+    @staticmethod
+    def _affine_inverse(M):
+        """Inverse of [B, 4, 4] affine maps ([A t; 0 1]) from cross products - no LU, no pivots read on the host."""
+        A, t = M[:, :3, :3], M[:, :3, 3]
+        a, b, c = A[:, :, 0], A[:, :, 1], A[:, :, 2]
+        r0, r1, r2 = torch.linalg.cross(b, c), torch.linalg.cross(c, a), torch.linalg.cross(a, b)
+        det = (a * r0).sum(-1)
+        Ai = torch.stack([r0, r1, r2], dim=1) / det[:, None, None]
+        ti = -torch.matmul(Ai, t[:, :, None])
+        return torch.cat([torch.cat([Ai, ti], dim=-1), M[:, 3:4, :]], dim=-2)
+
+    @classmethod
+    def _motion_bases_device(cls, Rs, Ts, cnl_gtfms):
+        """MotionBasisComputer (network_util.py:106-174) with a graph, entirely on the device and free of host reads (the
+        ``static_shapes`` training mode: CUDA-graph capturable).  Same chain as ``_motion_bases_autograd``; the two inverses
+        use the closed form for affine maps."""
+        nb = Rs.shape[1]
+        cg = cnl_gtfms.detach().to(Rs.dtype)
+        local = torch.cat([torch.cat([Rs, Ts[..., None]], dim=-1), cg[:, :, 3:4, :]], dim=-2)      # last row [0 0 0 1] of the inputs
+        glob = [local[:, 0]]
+        for i in range(1, nb):
+            glob.append(torch.matmul(glob[SMPL_PARENT[i]], local[:, i]))
+        glob = torch.stack(glob, dim=1).view(-1, 4, 4)
+        cgf = cg.view(-1, 4, 4)
+        back = torch.matmul(cgf, cls._affine_inverse(glob)).view(-1, nb, 4, 4)
+        fwd = torch.matmul(glob, cls._affine_inverse(cgf)).view(-1, nb, 4, 4)
+        return (back[0, :, :3, :3].contiguous(), back[0, :, :3, 3].contiguous(),
+                fwd[0, :, :3, :3].contiguous(), fwd[0, :, :3, 3].contiguous())
+
+    def _train_const(self, key, make):
+        """Per-module constants of the training forward that start on the host (Hann window, linspace, bounding box): made
+        once per key, so a step that has been run before touches no host memory (and can be captured in a CUDA graph)."""
+        d = self._cache.setdefault("train_const", {})
+        if key not in d:
+            if len(d) > 64:
+                d.clear()
+            d[key] = make()
+        return d[key]
+
     def _refined_pose(self, Rs, Ts, posevec, it):
         """network.py:590-605 on the device, with a graph."""
         if it < self.cfg.pose_decoder.get("kick_in_iter", 0):
@@ -607,23 +649,31 @@ class Network(nn.Module):
         it = float(iter_val.reshape(-1)[0]) if isinstance(iter_val, torch.Tensor) else float(iter_val)
         posevec = dst_posevec[None, ...].float()
         Rs, Ts = self._refined_pose(dst_Rs[None, ...].float(), dst_Ts[None, ...].float(), posevec, it)
-        Rb, Tb, Rf, Tf = self._motion_bases_autograd(Rs, Ts, cnl_gtfms[None, ...])
+        static = bool(getattr(self, "static_shapes", False))       # CUDA-graph capturable variant, see train.GraphedStep
+        bases = self._motion_bases_device if static else self._motion_bases_autograd
+        Rb, Tb, Rf, Tf = bases(Rs, Ts, cnl_gtfms[None, ...])
         vol = self.mweight_vol_decoder(motion_weights_priors=motion_weights_priors[None, ...])[0]
         kick = cfg.non_rigid_motion_mlp.kick_in_iter
-        hann_w = hann_window_weights(self.nr_freqs, it, kick, cfg.non_rigid_motion_mlp.full_band_iter).to(dev)
+        hann_w = self._train_const(("hann", it, str(dev)), lambda: hann_window_weights(
+            self.nr_freqs, it, kick, cfg.non_rigid_motion_mlp.full_band_iter).to(dev))
         cond = torch.zeros_like(posevec) if it < kick else posevec
         state_idx = select_state_index(len(self.human_stateembeds), time, self.transitions_times)
-        bbox_min = kwargs["cnl_bbox_min_xyz"].detach().cpu().reshape(-1).tolist()
-        bbox_scale = kwargs["cnl_bbox_scale_xyz"].detach().cpu().reshape(-1).tolist()
+        bmin_t, bscale_t = kwargs["cnl_bbox_min_xyz"], kwargs["cnl_bbox_scale_xyz"]
+        bbox_min, bbox_scale, _, _ = self._train_const(
+            ("bbox", id(bmin_t), bmin_t._version, id(bscale_t), bscale_t._version),
+            lambda: (bmin_t.detach().cpu().reshape(-1).tolist(), bscale_t.detach().cpu().reshape(-1).tolist(), bmin_t, bscale_t))
         rays_o, rays_d = rays
         rays_shape = rays_d.shape
         rays_o = torch.reshape(rays_o, [-1, 3]).float().contiguous()
         rays_d = torch.reshape(rays_d, [-1, 3]).float().contiguous()
         n, S = rays_o.shape[0], cfg.N_samples
-        t_lin = torch.linspace(0., 1., steps=S).to(dev)
+        t_lin = self._train_const(("t_lin", S, str(dev)), lambda: torch.linspace(0., 1., steps=S).to(dev))
         jitter = None
         if cfg.perturb > 0.:
-            jitter = (torch.rand(n, S) if rand is None else rand).to(dev, torch.float32).contiguous()
+            if rand is None and static:
+                jitter = torch.rand(n, S, device=dev)           # device generator: its state advances with every graph replay
+            else:
+                jitter = (torch.rand(n, S) if rand is None else rand).to(dev, torch.float32).contiguous()
         z, pts = ops.human_samples(rays_o, rays_d, near.reshape(-1).float().contiguous(), far.reshape(-1).float().contiguous(),
                                    t_lin, jitter)
         flat = pts.view(-1, 3)
@@ -647,7 +697,10 @@ class Network(nn.Module):
         mask2 = mask.view(n, S)
         ret = {}
         sel = mask.detach() > 0.005
-        if bool(sel.any()):          # cycle side path (network.py:505-536)
+        if static:                   # dense cycle side path: every point goes through it, ``cycle_mask`` marks the reference's subset
+            xd = train.LbsForwardFn.apply(cnl, Rf, Tf, vol, bbox_min, bbox_scale)
+            ret["deform_pts_final"], ret["observe_pts"], ret["cycle_mask"] = nr(self.non_rigid_forward_mlp, xd, cond), flat, sel
+        elif bool(sel.any()):        # cycle side path (network.py:505-536)
             xd = train.LbsForwardFn.apply(cnl[sel], Rf, Tf, vol, bbox_min, bbox_scale)
             ret["deform_pts_final"], ret["observe_pts"] = nr(self.non_rigid_forward_mlp, xd, cond), flat[sel]
         else:
@@ -673,7 +726,7 @@ class Network(nn.Module):
             if not flow:
                 ret.update(z_vals=z, rays_d=rays_d)
         for k in ret:
-            if k not in ("deform_pts_prev_final", "deform_pts_final", "observe_pts"):
+            if k not in ("deform_pts_prev_final", "deform_pts_final", "observe_pts", "cycle_mask"):
                 ret[k] = torch.reshape(ret[k], list(rays_shape[:-1]) + list(ret[k].shape[1:]))
         ret["bgcolor"] = bgcolor
         return ret

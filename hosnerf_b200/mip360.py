@@ -714,7 +714,7 @@ class MipNeRF360(nn.Module):
             _lib.call("hos_render_bkg", ctypes.byref(cfg), rays_o.data_ptr(), rays_d.data_ptr(), viewdirs.data_ptr(),
                       radii.data_ptr(), n, ws.data_ptr(), ws.numel(), rgb.data_ptr(),
                       sd.data_ptr() if want_hist else None, wt.data_ptr() if want_hist else None,
-                      torch.cuda.current_stream().cuda_stream)
+                      ops._stream())
             _lib.LAUNCHES += 1 + 3 * self.num_levels + 2      # level-0 histogram; resample + MLP + composite per level; view term
         return (rgb, sd, wt) if want_hist else rgb
 

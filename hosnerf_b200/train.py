@@ -455,3 +455,43 @@ def non_rigid_mlp_train(mlp, pe, cond, xyz):
         params += [lin.weight, lin.bias]
     params += [lins[-1].weight, lins[-1].bias]
     return xyz + MlpFn.apply(pe, cond.reshape(-1), spec, *params)
+
+
+# ============================================================================ whole-step CUDA graph
+class GraphedStep:
+    """``fn()`` - zero the gradient buffers, forward, objective, ``backward()`` - captured ONCE in a CUDA graph and replayed.
+
+    A training chunk is ~1400 small launches; at a few thousand rays per GPU the host cannot enqueue them as fast as the
+    GPU retires them (23 ms of enqueue for ~8 ms of kernels at 1024 rays), which is what caps strong scaling.  A replay is
+    one launch.  Requirements on ``fn`` (checked by CUDA itself: a violation aborts the capture with an error):
+      * static shapes and no host reads: ``Network.static_shapes = True``, ``train_hosnerf_chunk(dense=True)``, ray batches
+        written in place into the same device tensors (``copy_``), ``times`` / ``iter_val`` as host scalars (their value is
+        frozen into the graph: re-capture when the Hann window or the state index changes);
+      * gradients accumulate into persistent buffers (``dist.FlatGrads`` or ``zero_grad(set_to_none=False)``);
+      * collectives and the optimiser step stay outside (``fn`` ends with ``backward()``).
+    The first ``warmup`` calls run eagerly (lazy initialisation, weight-cache fills, allocator warm-up), the next one captures.
+    Returns whatever ``fn`` returns; after capture these are the graph's static output tensors, overwritten by every replay."""
+
+    def __init__(self, fn, warmup: int = 3):
+        self.fn, self.warmup = fn, warmup
+        self.calls, self.graph, self.out = 0, None, None
+        self.launches_per_step = 0
+
+    def __call__(self):
+        from . import _lib
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.LAUNCHES += self.launches_per_step
+            return self.out
+        self.calls += 1
+        if self.calls <= self.warmup:
+            return self.fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = _lib.LAUNCHES
+        with torch.cuda.graph(g):
+            self.out = self.fn()
+        self.launches_per_step = _lib.LAUNCHES - l0
+        _lib.LAUNCHES = l0
+        self.graph = g
+        return self()

@@ -1090,3 +1090,29 @@ def test_fused_fourier_prologue_matches_materialised_encoding(stage2):
     else:
         assert max_abs(outs[0]["human_rgb"], outs[1]["human_rgb"]) < 5e-3
         assert rel_err(outs[0]["human_density"], outs[1]["human_density"]) < 3e-2
+
+
+def test_flat_grad_sink_matches_autograd_accumulation(golden):
+    """dist.FlatGrads as the gradient sink of RenderFn (the multi-GPU training path: gradients added straight into one flat fp32
+    buffer, buckets all-reduced per level) leaves the same gradients as plain autograd accumulation (world size 1: no collective)."""
+    from hosnerf_b200.dist import FlatGrads
+    g, lit, batch, rands = _s1_train_setup(golden)
+    lit.training_objective(batch, randomized=True, rands=rands)["loss"].backward()
+    want = {k: p.grad.clone() for k, p in lit.model.named_parameters() if p.grad is not None}
+    for p in lit.model.parameters():
+        p.grad = None
+    sink = FlatGrads(lit.model, bucket_of=lambda name: int(name.split(".")[1]))
+    lit.model._grad_sink = sink
+    try:
+        sink.zero_()
+        lit.training_objective(batch, randomized=True, rands=rands)["loss"].backward()
+        sink.finish()
+    finally:
+        lit.model._grad_sink = None
+    assert sorted(sink.ranges) == [0, 1, 2]
+    for k, p in lit.model.named_parameters():
+        assert p.grad.data_ptr() == sink.views[k].data_ptr()
+        if k in want:
+            assert torch.allclose(p.grad, want[k], rtol=1e-5, atol=1e-7 * float(want[k].abs().max()) + 1e-12), k
+        else:
+            assert float(p.grad.abs().max()) == 0.0, k
