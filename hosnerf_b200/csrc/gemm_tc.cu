@@ -506,10 +506,9 @@ struct WgArgs {
   int64_t rows;
   int ld_out;
   int ntiles;
-  int m, nq;          // valid P / Q columns
-  int nacc;           // 256-column accumulator blocks (1 or 2)
+  int m, nq;          // valid P / Q columns of the whole product; blockIdx.y walks its 256 x 512 output blocks
+  int nqblocks;       // 512-column blocks of Q (blockIdx.y = mblock * nqblocks + qblock)
   int transpose_out;  // 0: out[i * ld + j], 1: out[j * ld + i]
-  int stages;
 };
 struct WgMaps {
   CUtensorMap p, q;
@@ -519,12 +518,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ WgMaps maps) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int nacc = args.nacc;
+  // this cluster's output block: P columns [m0, m0 + 256) x Q columns [q0, q0 + 512)
+  const int m0 = ((int)blockIdx.y / args.nqblocks) * 256, q0 = ((int)blockIdx.y % args.nqblocks) * 512;
+  const int m_here = args.m - m0 < 256 ? args.m - m0 : 256, nq_here = args.nq - q0 < 512 ? args.nq - q0 : 512;
+  const int nacc = nq_here > 256 ? 2 : 1;                     // 256-column accumulator blocks
+  float* const out = args.out + (args.transpose_out ? (size_t)q0 * args.ld_out + m0 : (size_t)m0 * args.ld_out + q0);
+  float* const colsum = (args.colsum && q0 == 0) ? args.colsum + m0 : nullptr;
   const int p_bytes = 2 * kXChunkBytes;                       // this CTA's 128 P columns = two [128 x 64] boxes
   const int q_bytes = nacc * 2 * kXChunkBytes;                // 128 Q columns per accumulator block
   const int stage_bytes = p_bytes + q_bytes;
   unsigned char* sRing = smem;
-  const uint32_t kWgStages = (uint32_t)args.stages;
+  const uint32_t kWgStages = nacc == 1 ? 3u : 2u;             // 3 x 64 KB or 2 x 96 KB: the same 192 KB either way
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRing + (size_t)kWgStages * stage_bytes);
   uint64_t* bar_full = bars;                                  // [kWgMaxStages]
   uint64_t* bar_empty = bar_full + kWgMaxStages;              // [kWgMaxStages]
@@ -540,7 +544,7 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
     // warps of this CTA have read the P tile out of it
     for (int s = 0; s < kWgMaxStages; ++s) {
       mbar_init(&bar_full[s], rank == 0 ? 3u : 2u);         // leader: own P + own Q + ONE relay from the peer's watcher warp
-      mbar_init(&bar_empty[s], args.colsum ? 1u + kG2EpiWarps : 1u);
+      mbar_init(&bar_empty[s], colsum ? 1u + kG2EpiWarps : 1u);
     }
     mbar_init(&bar_done[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -568,12 +572,12 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
         if (warp == 0) {
           mbar_expect_tx(&bar_full[st], (uint32_t)p_bytes);
           for (int b = 0; b < 2; ++b)
-            tma_load_2d(stage + b * kXChunkBytes, &maps.p, (int)rank * 128 + b * 64, t * kTileM, &bar_full[st]);
+            tma_load_2d(stage + b * kXChunkBytes, &maps.p, m0 + (int)rank * 128 + b * 64, t * kTileM, &bar_full[st]);
         } else {
           mbar_expect_tx(&bar_full[st], (uint32_t)q_bytes);
           for (int a = 0; a < nacc; ++a)
             for (int b = 0; b < 2; ++b)
-              tma_load_2d(stage + p_bytes + (a * 2 + b) * kXChunkBytes, &maps.q, a * 256 + (int)rank * 128 + b * 64, t * kTileM,
+              tma_load_2d(stage + p_bytes + (a * 2 + b) * kXChunkBytes, &maps.q, q0 + a * 256 + (int)rank * 128 + b * 64, t * kTileM,
                           &bar_full[st]);
         }
       }
@@ -624,7 +628,7 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
     const int q = warp & 3;
     const int ch = (warp - kG2EpiWarp0) >> 2;
     const int i = (int)rank * 128 + q * 32 + lane;            // P column = output row
-    if (args.colsum) {
+    if (colsum) {
       // While the tensor core works, these warps add up the columns of every P tile straight from the staged (swizzled)
       // boxes: thread -> column e & 127 of this CTA's 128, rows [64 (e >> 7), +64).  The bias gradient costs no extra pass.
       const int e = threadIdx.x - kG2EpiWarp0 * 32;
@@ -648,7 +652,7 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
         if (++st == kWgStages) { st = 0; par ^= 1; }
       }
       const int pc = (int)rank * 128 + col;
-      if (pc < args.m) atomicAdd(args.colsum + pc, acc);
+      if (pc < m_here) atomicAdd(colsum + pc, acc);
     }
     mbar_wait_guard<200>(&bar_done[0], 0);
     tc_fence_after();
@@ -665,21 +669,21 @@ wgrad_tma_kernel(const __grid_constant__ WgArgs args, const __grid_constant__ Wg
         uint32_t v[32];
         tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + c * 64 + ch * 32), v);
         tmem_wait_ld();
-        if (i_base >= args.m || j0 >= args.nq) continue;       // warp-uniform
+        if (i_base >= m_here || j0 >= nq_here) continue;       // warp-uniform
         if (!args.transpose_out) {
 #pragma unroll
           for (int x = 0; x < 32; ++x) patch[lane * 33 + x] = __uint_as_float(v[x]);
           __syncwarp();
-          const bool col_ok = j0 + lane < args.nq;
+          const bool col_ok = j0 + lane < nq_here;
           for (int rr = 0; rr < 32; ++rr) {
-            if (i_base + rr >= args.m) break;
-            if (col_ok) atomicAdd(args.out + (size_t)(i_base + rr) * args.ld_out + j0 + lane, patch[rr * 33 + lane]);
+            if (i_base + rr >= m_here) break;
+            if (col_ok) atomicAdd(out + (size_t)(i_base + rr) * args.ld_out + j0 + lane, patch[rr * 33 + lane]);
           }
           __syncwarp();
-        } else if (i < args.m) {                               // out[j][i]: lanes are consecutive i already
+        } else if (i < m_here) {                               // out[j][i]: lanes are consecutive i already
 #pragma unroll
           for (int x = 0; x < 32; ++x)
-            if (j0 + x < args.nq) atomicAdd(args.out + (size_t)(j0 + x) * args.ld_out + i, __uint_as_float(v[x]));
+            if (j0 + x < nq_here) atomicAdd(out + (size_t)(j0 + x) * args.ld_out + i, __uint_as_float(v[x]));
         }
       }
     }
@@ -942,8 +946,7 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
 int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq, int64_t rows, float* out, int ld_out,
                   int transpose_out, float* colsum_p, void* stream) {
   HOS_ARCH_GUARD();
-  HOS_REQUIRE(p && q && out && m >= 1 && m <= 256 && nq >= 1 && nq <= 512 && rows >= 0 && ld_out >= 1,
-              "hos_wgrad_tma: need P [rows, m <= 256], Q [rows, nq <= 512] and out");
+  HOS_REQUIRE(p && q && out && m >= 1 && nq >= 1 && rows >= 0 && ld_out >= 1, "hos_wgrad_tma: need P [rows, m], Q [rows, nq] and out");
   if (rows == 0) return HOS_OK;
   WgArgs a;
   memset(&a, 0, sizeof(a));
@@ -951,7 +954,9 @@ int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq,
   memset(&maps, 0, sizeof(maps));
   a.out = out; a.rows = rows; a.ld_out = ld_out; a.colsum = colsum_p;
   a.ntiles = (int)((rows + kTileM - 1) / kTileM);
-  a.m = m; a.nq = nq; a.nacc = nq > 256 ? 2 : 1; a.transpose_out = transpose_out;
+  a.m = m; a.nq = nq; a.nqblocks = (nq + 511) / 512; a.transpose_out = transpose_out;
+  const int nblocks = ((m + 255) / 256) * a.nqblocks;        // 256 x 512 output blocks, one grid row each
+  HOS_REQUIRE(nblocks <= 65535, "hos_wgrad_tma: product too large (%d output blocks)", nblocks);
   int rc;
   if ((rc = make_map(&maps.p, p, rows, m, ldp, kTileM)) != HOS_OK) return rc;
   if ((rc = make_map(&maps.q, q, rows, nq, ldq, kTileM)) != HOS_OK) return rc;
@@ -962,14 +967,16 @@ int hos_wgrad_tma(const void* p, int m, int ldp, const void* q, int nq, int ldq,
     HOS_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     attr_dev = dev;
   }
-  a.stages = a.nacc == 1 ? 3 : 2;
-  const size_t smem = 1024 + (size_t)a.stages * (2 + 2 * a.nacc) * kXChunkBytes + (2 * kWgMaxStages + 2) * 8 + 64;
+  const size_t smem = 1024 + (size_t)12 * kXChunkBytes + (2 * kWgMaxStages + 2) * 8 + 64;       // 3 x 64 KB = 2 x 96 KB of ring
   static thread_local int max_clusters = 0;
   if (!max_clusters) max_clusters = max_clusters_for((const void*)wgrad_tma_kernel, 227 * 1024 - 1024);
-  int clusters = (a.ntiles + 15) / 16;          // >= 16 row tiles per cluster before it pays the atomic epilogue
-  if (clusters > max_clusters) clusters = max_clusters;
+  // clusters per output block: >= 16 row tiles each before a cluster pays the atomic epilogue, and about one wave of the
+  // machine over all the blocks (a 1024 x 1024 layer is 8 blocks: 9 clusters each instead of 8 launches of 32)
+  int clusters = (a.ntiles + 15) / 16;
+  const int cap = max_clusters / nblocks > 1 ? max_clusters / nblocks : 1;
+  if (clusters > cap) clusters = cap;
   if (clusters < 1) clusters = 1;
-  wgrad_tma_kernel<<<2 * clusters, kG2Threads, smem, (cudaStream_t)stream>>>(a, maps);
+  wgrad_tma_kernel<<<dim3(2 * clusters, nblocks, 1), kG2Threads, smem, (cudaStream_t)stream>>>(a, maps);
   HOS_LAUNCH_CHECK();
   return HOS_OK;
 }

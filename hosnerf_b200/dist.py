@@ -109,6 +109,9 @@ class FlatGrads:
             off += n
         self.works, self.reduced = [], set()
         self.nbytes = total * 4
+        # True: reduce_bucket() calls made from inside backward are ignored and finish() reduces everything - for a backward
+        # that is replayed from a CUDA graph (train.GraphedStep), where the collective has to stay outside the capture
+        self.defer = False
 
     def zero_(self):
         self.flat.zero_()
@@ -117,9 +120,9 @@ class FlatGrads:
     def add_(self, name, g):
         self.views[name].add_(g)
 
-    def reduce_bucket(self, b):
+    def reduce_bucket(self, b, _from_finish: bool = False):
         _, w = world()
-        if w == 1 or b not in self.ranges or b in self.reduced:
+        if w == 1 or b not in self.ranges or b in self.reduced or (self.defer and not _from_finish):
             return
         self.reduced.add(b)
         lo, hi = self.ranges[b]
@@ -127,7 +130,7 @@ class FlatGrads:
 
     def reduce_all(self):
         for b in sorted(self.ranges):
-            self.reduce_bucket(b)
+            self.reduce_bucket(b, _from_finish=True)
 
     def finish(self, average: bool = True):
         _, w = world()

@@ -474,6 +474,9 @@ class MipNeRF360(nn.Module):
         self.mlps = nn.ModuleList([PropMLP(basedir, **prop_kw) for _ in range(num_levels - 1)]
                                   + [NeRFMLP(basedir, **nerf_kw)])
         self._u_cache = {}
+        # True: the stratified-sampling jitter is drawn by the device generator (the reference draws it on the host and copies
+        # it over, helper.py:325-328) - no host work per step, and the step can be captured in a CUDA graph (train.GraphedStep)
+        self.device_rng = False
 
     # quantiles of helper.sample (deterministic_center=True): generated on the HOST with the same
     # torch.linspace call as the reference so both sides invert the CDF at bit-identical u.
@@ -588,7 +591,10 @@ class MipNeRF360(nn.Module):
             if randomized:
                 d = 1 if self.single_jitter else s
                 # the reference draws on the host: torch.rand(t.shape[:-1] + (d,))  (helper.py:325-328)
-                r = torch.rand(n, d) if rands is None else rands[lvl]
+                if rands is None and getattr(self, "device_rng", False):
+                    r = torch.rand(n, d, device=dev)         # device generator: no host draw / copy (CUDA-graph capturable)
+                else:
+                    r = torch.rand(n, d) if rands is None else rands[lvl]
                 jitter = r.to(dev, torch.float32).contiguous()
             sdist, tdist = ops.resample_level(sdist, weights, dilate, dilation, float(anneal),
                                               float(self.resample_padding), u_base, jitter, max_jitter,

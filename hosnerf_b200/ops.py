@@ -628,17 +628,9 @@ def wgrad_tma(p, q, out, transpose_out=False, colsum=None):
     assert colsum is None or (colsum.dtype == _F32 and colsum.is_cuda and colsum.numel() == m and colsum.is_contiguous())
     if rows == 0:
         return out
-    # blocks of <= 256 x 512 outputs per launch, addressed by pointer arithmetic (no view tensors on this path: a 1024-wide
-    # layer is 8 launches)
-    pp, qp, op, ldo = p.data_ptr(), q.data_ptr(), out.data_ptr(), out.stride(0)
-    csp = None if colsum is None else colsum.data_ptr()
-    ldp, ldq, st, tr = p.stride(0), q.stride(0), _stream(), int(transpose_out)
-    for i0 in range(0, m, 256):
-        for j0 in range(0, nq, 512):
-            mi, nj = min(256, m - i0), min(512, nq - j0)
-            o = op + 4 * ((j0 * ldo + i0) if transpose_out else (i0 * ldo + j0))
-            cs = csp + 4 * i0 if (csp is not None and j0 == 0) else None
-            _lib.call("hos_wgrad_tma", pp + 2 * i0, mi, ldp, qp + 2 * j0, nj, ldq, rows, o, ldo, tr, cs, st)
+    # one launch: blockIdx.y of the kernel walks the 256 x 512 output blocks
+    _lib.call("hos_wgrad_tma", p.data_ptr(), m, p.stride(0), q.data_ptr(), nq, q.stride(0), rows, out.data_ptr(), out.stride(0),
+              int(transpose_out), None if colsum is None else colsum.data_ptr(), _stream())
     return out
 
 

@@ -182,8 +182,12 @@ class RenderFn(torch.autograd.Function):
         ctx.rays_d = batch["rays_d"].contiguous().float()
         ctx.bg = model._background(randomized)
         ctx.levels = len(hist)
-        ctx.tdists = [h.pop("_tdist") for h in hist]
-        ctx.hist = hist
+        tdists = [h.pop("_tdist") for h in hist]
+        # the context keeps detached aliases: the tensors returned below become outputs of this node, and a context that
+        # holds its own outputs is a reference cycle - the node (and the parameters' AccumulateGrad nodes, with the stream
+        # they were created on) would outlive the step until the garbage collector runs
+        ctx.tdists = [t.detach() for t in tdists]
+        ctx.hist = [{k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in h.items()} for h in hist]
         ctx.stage3 = model.stage3
         L = len(hist)
         aux = []
@@ -192,11 +196,11 @@ class RenderFn(torch.autograd.Function):
         rgb_final = rend[-1]["rgb"] if not model.stage3 else torch.zeros(0, device=ctx.rays_d.device)
         # stage 3 composites outside (together with the human samples): there the final level's per-sample density / rgb
         # carry the gradient instead of the composited colour
-        nondiff = [a for i, a in enumerate(aux) if not (model.stage3 and i in (3 * (L - 1), 3 * (L - 1) + 1))] + ctx.tdists
+        nondiff = [a for i, a in enumerate(aux) if not (model.stage3 and i in (3 * (L - 1), 3 * (L - 1) + 1))] + tdists
         if model.stage3:
             nondiff.append(rgb_final)
         ctx.mark_non_differentiable(*nondiff)
-        return tuple([rgb_final] + [h["weights"] for h in hist] + aux + ctx.tdists)
+        return tuple([rgb_final] + [h["weights"] for h in hist] + aux + tdists)
 
     @staticmethod
     def backward(ctx, *gouts):
@@ -486,10 +490,14 @@ class GraphedStep:
         self.calls += 1
         if self.calls <= self.warmup:
             return self.fn()
-        torch.cuda.synchronize()
+        import gc
+        gc.collect()               # autograd graphs of earlier eager steps still alive in reference cycles would hand their
+        torch.cuda.synchronize()   # AccumulateGrad nodes (bound to the eager stream) to the captured backward
         g = torch.cuda.CUDAGraph()
         l0 = _lib.LAUNCHES
-        with torch.cuda.graph(g):
+        # thread_local: only this thread is held to the capture rules (the NCCL watchdog thread polls its events meanwhile);
+        # the autograd worker's launches still land in the graph because they go to the capturing stream
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self.out = self.fn()
         self.launches_per_step = _lib.LAUNCHES - l0
         _lib.LAUNCHES = l0

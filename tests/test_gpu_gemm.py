@@ -72,7 +72,8 @@ def test_gemm_dgrad(rows, kred, n):
 
 
 @pytest.mark.parametrize("rows,m,nq,tr", [(1000, 256, 256, False), (128 * 300 + 17, 256, 504, False), (5000, 128, 256, True),
-                                          (3000, 128, 128, False), (2000, 1024, 768, False), (777, 256, 64, False)])
+                                          (3000, 128, 128, False), (2000, 1024, 768, False), (777, 256, 64, False),
+                                          (128 * 40 + 5, 1024, 1528, False), (4100, 640, 1024, True), (300, 520, 520, False)])
 def test_wgrad(rows, m, nq, tr):
     """dW += P^T Q over all rows (split over clusters, fp32 atomics)."""
     ops = _ops()

@@ -1116,3 +1116,105 @@ def test_flat_grad_sink_matches_autograd_accumulation(golden):
             assert torch.allclose(p.grad, want[k], rtol=1e-5, atol=1e-7 * float(want[k].abs().max()) + 1e-12), k
         else:
             assert float(p.grad.abs().max()) == 0.0, k
+
+
+def _s3_chunk_setup(n=96, width=256):
+    hb = synth.make_human_batch(n)
+    hb["is_train"] = True
+    Mw = synth.random_rigid()
+    ro, rd = hb["rays"][0], hb["rays"][1]
+    ro_w = (Mw[:3, :3] @ ro.T).T + Mw[:3, 3]
+    rd_w = (Mw[:3, :3] @ rd.T).T
+    bb = {"rays_o": ro_w, "rays_d": rd_w, "viewdirs": rd_w / rd_w.norm(dim=-1, keepdim=True), "radii": torch.full((n, 1), 1e-3)}
+    bb = {k: cu(v) for k, v in bb.items()}
+    bb["times"] = torch.tensor(0.0)                           # host scalar
+    bkg = MipNeRF360("/nonexistent", opaque_background=True, nerf_netwidth=width, stage3=True)
+    synth.fill_params_(bkg, 0)
+    bkg = bkg.to(DEV)
+    human = _human()
+    hb = {k: cu(v) for k, v in hb.items()}
+    for k in ("time", "iter_val"):
+        if isinstance(hb.get(k), torch.Tensor):
+            hb[k] = float(hb[k].reshape(-1)[0])
+    hb["rand"] = torch.rand(n, human.cfg.N_samples, generator=torch.Generator().manual_seed(5)).to(DEV)
+    return bkg, human, bb, hb, Mw.to(DEV)
+
+
+def test_static_shape_training_chunk_matches_indexed_form():
+    """``Network.static_shapes`` + ``train_hosnerf_chunk(dense=True)`` (the CUDA-graph capturable form: device-side bone chain,
+    dense cycle side path with ``cycle_mask``, both composites on every ray selected by ``idx_fg``, exp-cumsum-log transmittance)
+    give the rgb, foreground split, human weights, cycle points and parameter gradients of the indexed form."""
+    from hosnerf_b200 import train_hosnerf_chunk
+    bkg, human, bb, hb, Mw = _s3_chunk_setup()
+
+    def run(dense):
+        human.static_shapes = dense
+        for p in list(bkg.parameters()) + list(human.parameters()):
+            p.grad = None
+        out = train_hosnerf_chunk(bkg, human, bb, hb, Mw, randomized=False, dense=dense)
+        no = out["net_output"]
+        cyc = (no["deform_pts_final"] - no["observe_pts"]).pow(2)
+        if dense:
+            cyc = cyc[no["cycle_mask"]]
+        (out["rgb"].mean() + cyc.mean()).backward()
+        grads = {f"{t}.{k}": (None if p.grad is None else p.grad.clone()) for t, m in (("bkg", bkg), ("human", human))
+                 for k, p in m.named_parameters()}
+        return out, grads
+    ref, g_ref = run(False)
+    out, g_out = run(True)
+    human.static_shapes = False
+    assert torch.equal(out["idx_fg"], ref["idx_fg"]) and bool(ref["idx_fg"].any()) and not bool(ref["idx_fg"].all())
+    assert max_abs(out["rgb"], ref["rgb"]) < 5e-5          # transmittance as exp(cumsum(log)) instead of cumprod, closed-form inverses
+    fg = ref["idx_fg"]
+    assert out["human_weights"].shape == (fg.numel(), ref["human_weights"].shape[1])
+    assert max_abs(out["human_weights"][fg], ref["human_weights"]) < 5e-5
+    assert float(out["human_weights"][~fg].abs().max()) == 0.0
+    m = out["net_output"]["cycle_mask"]
+    assert int(m.sum()) == ref["net_output"]["observe_pts"].shape[0]
+    assert torch.equal(out["net_output"]["observe_pts"][m], ref["net_output"]["observe_pts"])
+    assert max_abs(out["net_output"]["deform_pts_final"][m], ref["net_output"]["deform_pts_final"]) < 1e-4
+    scale = max(float(g.norm()) for g in g_ref.values() if g is not None)
+    for k, g in g_ref.items():
+        if g is None or float(g.norm()) < 1e-6 * scale:
+            assert g_out[k] is None or float(g_out[k].norm()) < 1e-4 * scale, k
+        else:
+            assert float((g_out[k] - g).norm()) < 2e-2 * float(g.norm()) + 1e-5 * scale, (k, float((g_out[k] - g).norm()), float(g.norm()))
+
+
+def test_graphed_step_replays_the_training_chunk():
+    """``train.GraphedStep``: zero + forward + objective + backward of a complete HOSNeRF chunk captured in ONE CUDA graph.  The
+    replay leaves the eager step's loss and gradients, and it reads the CURRENT parameters (an optimiser step between two
+    replays changes the result exactly as it changes the eager one)."""
+    from hosnerf_b200 import train_hosnerf_chunk
+    from hosnerf_b200.dist import FlatGrads
+    from hosnerf_b200.train import GraphedStep
+    bkg, human, bb, hb, Mw = _s3_chunk_setup(n=64)
+    human.static_shapes = True
+
+    class Both(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model, self.human = bkg, human
+    both = Both()
+    sink = FlatGrads(both)
+    opt = torch.optim.SGD(both.parameters(), lr=1e-2)
+
+    def fwd_bwd():
+        sink.zero_()
+        out = train_hosnerf_chunk(bkg, human, bb, hb, Mw, randomized=False, dense=True)
+        loss = out["rgb"].mean()
+        loss.backward()
+        return loss.detach()
+    l0 = float(fwd_bwd())
+    g0 = sink.flat.clone()
+    gs = GraphedStep(fwd_bwd, warmup=0)
+    l1 = float(gs())
+    assert gs.graph is not None and gs.launches_per_step > 50
+    assert abs(l1 - l0) < 1e-6 and float((sink.flat - g0).norm()) < 1e-5 * float(g0.norm())
+    opt.step()                                      # parameters move: the replay must see them
+    l2 = float(gs())
+    g2 = sink.flat.clone()
+    l3 = float(fwd_bwd())
+    assert abs(l2 - l0) > 1e-7, "the step did not change the loss - test is vacuous"
+    assert abs(l2 - l3) < 1e-6 and float((sink.flat - g2).norm()) < 1e-5 * float(g2.norm())
+    human.static_shapes = False
