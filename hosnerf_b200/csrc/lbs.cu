@@ -17,34 +17,71 @@ struct LbsParams {
   float bbox_scale[3];
 };
 
-// trilinear sample with zeros padding, align_corners=True; term order follows ATen's
-// grid_sampler_3d CPU kernel (tnw, tne, tsw, tse, bnw, bne, bsw, bse).
-__device__ __forceinline__ float trilinear_zeros(const float* __restrict__ v, int G, float gx, float gy, float gz) {
+// Trilinear sample with zeros padding, align_corners=True; term order follows ATen's grid_sampler_3d CPU kernel (tnw, tne,
+// tsw, tse, bnw, bne, bsw, bse).  Split in two so the forward warp - all bones sampled at ONE position - sets the cell up once:
+// tri_setup() finds the cell and the eight corner weights, tri_sample() gathers one channel.  32-bit index arithmetic, one base
+// offset plus constant corner strides, and an interior fast path without per-corner predicates (the common case); the
+// arithmetic of each term (three un-fused multiplies and one add, -fmad=false) is unchanged.
+struct TriCell {
+  int base;          // (z0 * G + y0) * G + x0 - may point outside when a corner is outside; such corners are never read
+  unsigned valid;    // bit c: corner c inside the volume; 0xff = interior cell; 0 = sample completely outside
+  float w[8];
+};
+
+__device__ __forceinline__ void tri_setup(int G, float gx, float gy, float gz, TriCell& c) {
   float s = (float)(G - 1);
   float ix = ((gx + 1.f) / 2.f) * s;
   float iy = ((gy + 1.f) / 2.f) * s;
   float iz = ((gz + 1.f) / 2.f) * s;
-  float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  c.valid = 0u;
   // completely outside (or NaN): every corner is out of range
-  if (!(ix > -1.f && ix < (float)G && iy > -1.f && iy < (float)G && iz > -1.f && iz < (float)G)) return 0.f;
+  if (!(ix > -1.f && ix < (float)G && iy > -1.f && iy < (float)G && iz > -1.f && iz < (float)G)) return;
+  float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
   int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
   int x1 = x0 + 1, y1 = y0 + 1, z1 = z0 + 1;
   float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;     // weight of the +1 corner
   float wx0 = (float)x1 - ix, wy0 = (float)y1 - iy, wz0 = (float)z1 - iz;
-  bool bx0 = x0 >= 0 && x0 < G, bx1 = x1 >= 0 && x1 < G;
-  bool by0 = y0 >= 0 && y0 < G, by1 = y1 >= 0 && y1 < G;
-  bool bz0 = z0 >= 0 && z0 < G, bz1 = z1 >= 0 && z1 < G;
-  auto at = [&](int z, int y, int x) { return __ldg(v + ((size_t)z * G + y) * G + x); };
+  c.base = (z0 * G + y0) * G + x0;
+  c.w[0] = wx0 * wy0 * wz0; c.w[1] = wx1 * wy0 * wz0; c.w[2] = wx0 * wy1 * wz0; c.w[3] = wx1 * wy1 * wz0;
+  c.w[4] = wx0 * wy0 * wz1; c.w[5] = wx1 * wy0 * wz1; c.w[6] = wx0 * wy1 * wz1; c.w[7] = wx1 * wy1 * wz1;
+  const unsigned bx0 = x0 >= 0 && x0 < G, bx1 = x1 >= 0 && x1 < G;
+  const unsigned by0 = y0 >= 0 && y0 < G, by1 = y1 >= 0 && y1 < G;
+  const unsigned bz0 = z0 >= 0 && z0 < G, bz1 = z1 >= 0 && z1 < G;
+  c.valid = ((bz0 & by0 & bx0) << 0) | ((bz0 & by0 & bx1) << 1) | ((bz0 & by1 & bx0) << 2) | ((bz0 & by1 & bx1) << 3) |
+            ((bz1 & by0 & bx0) << 4) | ((bz1 & by0 & bx1) << 5) | ((bz1 & by1 & bx0) << 6) | ((bz1 & by1 & bx1) << 7);
+}
+
+__device__ __forceinline__ float tri_sample(const float* __restrict__ v, int G, const TriCell& c) {
+  if (c.valid == 0u) return 0.f;
+  const float* p = v + c.base;
+  const int sy = G, sz = G * G;
   float acc = 0.f;
-  if (bz0 && by0 && bx0) acc += at(z0, y0, x0) * (wx0 * wy0 * wz0);
-  if (bz0 && by0 && bx1) acc += at(z0, y0, x1) * (wx1 * wy0 * wz0);
-  if (bz0 && by1 && bx0) acc += at(z0, y1, x0) * (wx0 * wy1 * wz0);
-  if (bz0 && by1 && bx1) acc += at(z0, y1, x1) * (wx1 * wy1 * wz0);
-  if (bz1 && by0 && bx0) acc += at(z1, y0, x0) * (wx0 * wy0 * wz1);
-  if (bz1 && by0 && bx1) acc += at(z1, y0, x1) * (wx1 * wy0 * wz1);
-  if (bz1 && by1 && bx0) acc += at(z1, y1, x0) * (wx0 * wy1 * wz1);
-  if (bz1 && by1 && bx1) acc += at(z1, y1, x1) * (wx1 * wy1 * wz1);
+  if (c.valid == 0xffu) {
+    acc += __ldg(p) * c.w[0];
+    acc += __ldg(p + 1) * c.w[1];
+    acc += __ldg(p + sy) * c.w[2];
+    acc += __ldg(p + sy + 1) * c.w[3];
+    acc += __ldg(p + sz) * c.w[4];
+    acc += __ldg(p + sz + 1) * c.w[5];
+    acc += __ldg(p + sz + sy) * c.w[6];
+    acc += __ldg(p + sz + sy + 1) * c.w[7];
+    return acc;
+  }
+  if (c.valid & 1u) acc += __ldg(p) * c.w[0];
+  if (c.valid & 2u) acc += __ldg(p + 1) * c.w[1];
+  if (c.valid & 4u) acc += __ldg(p + sy) * c.w[2];
+  if (c.valid & 8u) acc += __ldg(p + sy + 1) * c.w[3];
+  if (c.valid & 16u) acc += __ldg(p + sz) * c.w[4];
+  if (c.valid & 32u) acc += __ldg(p + sz + 1) * c.w[5];
+  if (c.valid & 64u) acc += __ldg(p + sz + sy) * c.w[6];
+  if (c.valid & 128u) acc += __ldg(p + sz + sy + 1) * c.w[7];
   return acc;
+}
+
+__device__ __forceinline__ float trilinear_zeros(const float* __restrict__ v, int G, float gx, float gy, float gz) {
+  TriCell c;
+  tri_setup(G, gx, gy, gz, c);
+  return tri_sample(v, G, c);
 }
 
 __global__ void __launch_bounds__(256)
@@ -102,9 +139,11 @@ lbs_forward_kernel(const float* __restrict__ pts, const float* __restrict__ R, c
     float gy = (py - prm.bbox_min[1]) * prm.bbox_scale[1] - 1.0f;
     float gz = (pz - prm.bbox_min[2]) * prm.bbox_scale[2] - 1.0f;
     float ax = 0.f, ay = 0.f, az = 0.f, wsum = 0.f;
+    TriCell cell;
+    tri_setup(G, gx, gy, gz, cell);                       // every bone channel is sampled at the same position
     for (int b = 0; b < bones; ++b) {
       const float* r = sR + b * 9;
-      float w = trilinear_zeros(vol + b * vstride, G, gx, gy, gz);
+      float w = tri_sample(vol + b * vstride, G, cell);
       float qx = fmaf(r[2], pz, fmaf(r[1], py, r[0] * px)) + sT[b * 3 + 0];
       float qy = fmaf(r[5], pz, fmaf(r[4], py, r[3] * px)) + sT[b * 3 + 1];
       float qz = fmaf(r[8], pz, fmaf(r[7], py, r[6] * px)) + sT[b * 3 + 2];

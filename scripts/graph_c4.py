@@ -73,3 +73,9 @@ print("loss eager/graph", l_e, l_g, "grad rel diff", float((g_g - g_e).norm() / 
 ms, enq = timed(graphed)
 print(f"n={n} graphed: {ms:.2f} ms/step (enqueue {enq:.2f})")
 l_g2 = float(graphed()); print("replay loss", l_g2, "grad rel diff", float((sink.flat - g_e).norm() / g_e.norm()))
+if os.environ.get("PROFILE"):
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as p:
+        for _ in range(3): graphed()
+        torch.cuda.synchronize()
+    print(p.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
