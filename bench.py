@@ -519,7 +519,9 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": MLP_KERNEL[args.mlp_variant] + " (tcgen05 fused MLP, 2 launches/step)",
                          "achieved": achieved, "peak": tf_burst, "unit": "TFLOP/s", "frac": achieved / tf_burst,
-                         "peak_source": f"{src} bf16_tflops (burst)", "traffic": ncu_traffic(),
+                         "peak_source": f"{src} bf16_tflops (burst: the kernel is timed alone between L2 flushes)",
+                         "peak_sustained": tf_sus, "frac_of_sustained": achieved / tf_sus,
+                         "traffic": ncu_traffic(),
                          "traffic_note": "DRAM read+write bytes of the two MLP launches of one step, ncu --set full (profiles/r2_ncu_summary.json)",
                          "kernel_share_of_step": mlp_ms / dev_ms if dev_ms > 0 else None,
                          "flop_per_launch": [N_RAYS * S_PROP * FLOP_PROP, N_RAYS * S_NERF * FLOP_NERF]},

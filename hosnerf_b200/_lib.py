@@ -99,6 +99,7 @@ SIGNATURES = {
     "hos_gemm_create": (C.c_void_p, [c_i, c_i, c_i, c_i, c_i]),
     "hos_ipe_features_fast": (c_i, [c_f, c_f, c_f, c_f, c_hp, c_i, c_i, c_f, c_f]),
     "hos_gemm_destroy": (None, [C.c_void_p]),
+    "hos_gemm_set_cluster": (c_i, [C.c_void_p, c_i]),
     "hos_gemm_set_weight": (c_i, [C.c_void_p, c_f, c_f, c_f]),
     "hos_gemm_set_head": (c_i, [C.c_void_p, c_i, c_f, c_f, c_f]),
     "hos_gemm_forward": (c_i, [C.c_void_p, c_f, c_f, c_l, c_i, c_f, c_f, c_i, c_fl, c_f]),

@@ -104,6 +104,7 @@ struct G2Args {
   int kb0, kb1;     // 64-wide K chunks read from A0 / A1
   int relu, split, b_mn;
   int stages;
+  int group;          // operand chunks per MMA issue group (non-split): the ring keeps stages - group chunks of prefetch
   int nbuf_out;     // output staging buffers (TMA stores in flight + 1)
   int bias_smem;    // bias of the current 256-column block staged in shared memory
   int dbg;
@@ -231,7 +232,7 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
           int kb = 0;
           while (kb < KB) {
             // up to four chunks per poll (one parallel try_wait costs ~220 cycles; a non-split chunk is 512 cycles of tensor work)
-            const int lim = args.split ? 1 : (S >= 4 ? 4 : 1);
+            const int lim = args.split ? 1 : args.group;
             const int cnt = KB - kb < lim ? KB - kb : lim;
             uint32_t fb[4], fp[4];
             {
@@ -897,6 +898,10 @@ int hos_gemm_tma(const hos_gemm_tma_desc* d, void* stream) {
   HOS_REQUIRE(stages >= 2, "hos_gemm_tma: shared memory budget leaves %d pipeline stages", stages);
   { const char* e = getenv("HOS_G2_STAGES"); if (e) stages = atoi(e); }
   a.stages = stages;
+  { const char* e = getenv("HOS_G2_GROUP"); a.group = e ? atoi(e) : 2; }
+  if (a.group < 1) a.group = 1;
+  if (a.group > 4) a.group = 4;
+  if (a.group > stages - 1) a.group = stages - 1;
   { const char* e = getenv("HOS_G2_DBG"); a.dbg = e ? atoi(e) : 0; }
   const size_t smem = fixed + (size_t)stages * stage_bytes;
   const int half_n = a.n_blk / 2;

@@ -1257,10 +1257,17 @@ struct GemmArgs {
   int ntiles, kb0, kb1, n, relu;
   int hn, head_post;
   float head_shift;
+  int group;                   // operand chunks per MMA issue group (1 .. 4)
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
-gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
+// CS = 4 (gemm_quad_kernel, opt-in): two CTA pairs per cluster work on different row tiles and the SAME weight block.  At
+// 256 x 256 tiles a pair pulls 64 B per clock and SM of operands out of L2; in the quad kernel every CTA fetches only HALF of
+// its weight stage and multicasts it to its sibling in the other pair (which fetches the other half): 48 B per clock and SM.
+// A stage is refilled once BOTH pairs have consumed it (their commits are multicast to all four CTAs).  Bit-identical
+// results; measured slower than the pair kernel (see hos_gemm_forward), so it is kept as an A/B switch only.
+template <int CS>
+__device__ __forceinline__ void gemm_cluster_body(const GemmArgs& args) {
+  constexpr bool QUAD = CS == 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kWStage = kGemmNB * 64;                     // 16 KB: this CTA's half of a [256 x 64] weight chunk
@@ -1278,15 +1285,17 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
   float* s_headx = reinterpret_cast<float*>(s_tmem + 4);    // [128][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int n_groups = (args.ntiles + 1) >> 1;              // 2 tiles per group: tile = 2 g + rank
+  const uint32_t crank = cluster_ctarank();                 // 0 .. CS - 1
+  const uint32_t rank = crank & 1u, pair = crank >> 1;      // rank inside the CTA pair (0 = leader: issues the MMAs); pair index
+  const uint32_t leader = crank & ~1u;                      // cluster rank of this pair's leader
+  const int cluster = blockIdx.x / CS, n_clusters = gridDim.x / CS;
+  const int n_groups = (args.ntiles + CS - 1) / CS;         // CS tiles per group: tile = CS g + crank
   const int KB = args.kb0 + args.kb1;
   const int nblk = args.n / kGemmNB;
 
   for (int i = threadIdx.x; i < param_floats; i += kMlpThreads) sParams[i] = args.params[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], CS / 2); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1312,7 +1321,7 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
       unsigned char* ring = w_producer ? sRingW : sRingA;
       uint32_t ci = 0;
       for (int g = cluster; g < n_groups; g += n_clusters) {
-        int tile = 2 * g + (int)rank;
+        int tile = CS * g + (int)crank;
         if (tile >= args.ntiles) tile = args.ntiles - 1;           // padding tile: any valid rows, nothing is stored
         for (int j = 0; j < nblk; ++j) {
           for (int kb = 0; kb < KB; ++kb, ++ci) {
@@ -1320,17 +1329,23 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
             const uint32_t st = ci % kGemmStages, use = ci / kGemmStages;
             mbar_wait_guard<100>(&empty[st], (use & 1) ^ 1);
             mbar_expect_tx(&full[st], kXChunkBytes);
-            const unsigned char* src;
             if (w_producer) {
-              src = args.w + ((size_t)j * KB + kb) * (2u * kWStage) + rank * kWStage;
+              const unsigned char* src = args.w + ((size_t)j * KB + kb) * (2u * kWStage) + rank * kWStage;
+              if (QUAD) {       // this CTA's half of the stage: rows [64 pair, +64) of its 128, delivered to both pairs
+                const uint32_t off = pair * (uint32_t)(kWStage / 2);
+                bulk_g2s_mcast(ring + st * kXChunkBytes + off, src + off, kWStage / 2, &full[st],
+                               (uint16_t)((1u << rank) | (1u << (rank + 2))));
+              } else {
+                bulk_g2s(ring + st * kXChunkBytes, src, kXChunkBytes, &full[st]);
+              }
             } else {
-              src = kb < args.kb0 ? args.a0 + ((size_t)tile * args.kb0 + kb) * kXChunkBytes
-                                  : args.a1 + ((size_t)tile * args.kb1 + (kb - args.kb0)) * kXChunkBytes;
+              const unsigned char* src = kb < args.kb0 ? args.a0 + ((size_t)tile * args.kb0 + kb) * kXChunkBytes
+                                                       : args.a1 + ((size_t)tile * args.kb1 + (kb - args.kb0)) * kXChunkBytes;
+              bulk_g2s(ring + st * kXChunkBytes, src, kXChunkBytes, &full[st]);
             }
-            bulk_g2s(ring + st * kXChunkBytes, src, kXChunkBytes, &full[st]);
             if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
               mbar_wait_guard<100>(&full[st], use & 1);
-              mbar_arrive_remote(mapa_u32(smem_u32(&full[st]), 0));
+              mbar_arrive_remote(mapa_u32(smem_u32(&full[st]), leader));
             }
           }
         }
@@ -1353,7 +1368,7 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
           while (kb < KB) {
             // up to four chunks per group: one parallel poll (~220 cycles) and the issue overhead amortised over 2048
             // cycles of tensor work
-            const int cnt = KB - kb < 4 ? KB - kb : 4;
+            const int cnt = KB - kb < args.group ? KB - kb : args.group;
             uint32_t fb[4], fp[4];
             {
               uint32_t s_ = st, p_ = par;
@@ -1374,8 +1389,8 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
 #pragma unroll
                 for (int k = 0; k < kKB / 16; ++k)
                   tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb + i) != 0 || k != 0 ? 1u : 0u);
-                tc_commit_pair_addr(empty0 + 8u * st);
-                if (kb + i == KB - 1) tc_commit_pair_addr(tfull0 + 8u * (u & 1));
+                tc_commit_mask_addr(empty0 + 8u * st, QUAD ? (uint16_t)0xF : (uint16_t)0x3);
+                if (kb + i == KB - 1) tc_commit_mask_addr(tfull0 + 8u * (u & 1), (uint16_t)(3u << (2 * pair)));
               }
               if (++st == kGemmStages) { st = 0; par ^= 1; }
             }
@@ -1390,13 +1405,13 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
     const int q = warp & 3;
     const int ch = (warp - kEpiWarp0) >> 2;
     const int r = q * 32 + lane;
-    const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), 0);
+    const uint32_t tempty0 = mapa_u32(smem_u32(&bar_tempty[0]), leader);
     const uint32_t sparams_u32 = smem_u32(sParams);
     const uint32_t headx_u32 = smem_u32(s_headx) + 16u * r;
     const bool has_head = args.hn > 0 && args.head_out != nullptr;
     uint32_t u = 0;
     for (int g = cluster; g < n_groups; g += n_clusters) {
-      const int tile = 2 * g + (int)rank;
+      const int tile = CS * g + (int)crank;
       const int64_t row = (int64_t)tile * kTileM + r;
       const bool row_ok = row < args.rows, tile_ok = tile < args.ntiles;
       float hacc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1489,6 +1504,11 @@ gemm_pair_kernel(const __grid_constant__ GemmArgs args) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
   }
 }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+gemm_pair_kernel(const __grid_constant__ GemmArgs args) { gemm_cluster_body<2>(args); }
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kMlpThreads, 1)
+gemm_quad_kernel(const __grid_constant__ GemmArgs args) { gemm_cluster_body<4>(args); }
 
 
 // Generated IPE features to HBM in the tiled fp16 layout (kernel column order, see ipe_generate_pass): the wide-layer
@@ -1855,7 +1875,9 @@ struct hos_gemm {
   unsigned char* d_w = nullptr;     // packed fp16 [n / 256][kb0 + kb1][256 x 128 B]
   float* d_params = nullptr;        // [n] bias | [4][n] head weights | [4] head bias
   size_t smem_bytes = 0;
-  int max_clusters = 0;
+  int max_clusters = 0;        // co-resident CTA pairs (gemm_pair_kernel)
+  int max_quads = 0;           // co-resident 4-CTA clusters (gemm_quad_kernel); 0: not available
+  int cluster = 0;             // kernel selection of THIS handle: 0 automatic, 2 pair kernel, 4 quad kernel
 };
 
 hos_gemm_t* hos_gemm_create(int n_out, int k0, int k1, int x_first, int ipe_inputs) {
@@ -1885,7 +1907,8 @@ hos_gemm_t* hos_gemm_create(int n_out, int k0, int k1, int x_first, int ipe_inpu
   }
   if (cudaMalloc(&m->d_w, wbytes) != cudaSuccess || cudaMalloc(&m->d_params, pfloats * 4) != cudaSuccess ||
       cudaMemset(m->d_params, 0, pfloats * 4) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
+      cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
     hos::set_error("hos_gemm_create: CUDA allocation/attribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     hos_gemm_destroy(m);
     return nullptr;
@@ -1900,6 +1923,12 @@ hos_gemm_t* hos_gemm_create(int n_out, int k0, int k1, int x_first, int ipe_inpu
     nc = kNumSMs / 2;
   }
   m->max_clusters = nc < kNumSMs / 2 ? nc : kNumSMs / 2;
+  int nq = 0;
+  if (cudaOccupancyMaxActiveClusters(&nq, gemm_quad_kernel, &cfg) != cudaSuccess || nq < 1) {
+    cudaGetLastError();
+    nq = 0;
+  }
+  m->max_quads = nq < kNumSMs / 4 ? nq : kNumSMs / 4;
   return m;
 }
 
@@ -1908,6 +1937,13 @@ void hos_gemm_destroy(hos_gemm_t* m) {
   if (m->d_w) cudaFree(m->d_w);
   if (m->d_params) cudaFree(m->d_params);
   delete m;
+}
+
+int hos_gemm_set_cluster(hos_gemm_t* m, int cluster_size) {
+  HOS_REQUIRE(m && (cluster_size == 0 || cluster_size == 2 || cluster_size == 4), "hos_gemm_set_cluster: 0 (automatic), 2 or 4");
+  HOS_REQUIRE(cluster_size != 4 || m->max_quads > 0, "hos_gemm_set_cluster: no 4-CTA cluster of this kernel fits on the device");
+  m->cluster = cluster_size;
+  return HOS_OK;
 }
 
 int hos_gemm_set_weight(hos_gemm_t* m, const float* W, const float* b, void* stream) {
@@ -1962,10 +1998,25 @@ int hos_gemm_forward(hos_gemm_t* m, const void* a0_tiled, const void* a1_tiled, 
   a.hn = head_out ? m->hn : 0;
   a.head_post = head_post;
   a.head_shift = head_shift;
-  const int n_groups = (a.ntiles + 1) / 2;
-  const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
-  // parameter block in shared memory: bias + the heads actually used
-  gemm_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(a);
+  static const int group_env = getenv("HOS_GEMM_GROUP") ? atoi(getenv("HOS_GEMM_GROUP")) : 0;
+  // two chunks per issue group: with the 6-stage ring that leaves four stages of prefetch (groups of four left two, and the
+  // tensor pipe waited for the refill after every group: 1144 -> 1209 TFLOP/s on a 1024 x 1024 layer at 4.2 M rows)
+  a.group = group_env >= 1 && group_env <= 4 ? group_env : 2;
+  const int force = m->cluster;                             // A/B switch (hos_gemm_set_cluster): 2 or 4
+  const int quads_needed = (a.ntiles + 3) / 4;
+  // the quad kernel is opt-in (hos_gemm_set_cluster): measured on a 1024 x 1024 layer at 4.2 M rows it runs at 1029 TFLOP/s
+  // against the pair kernel's 1209 - the halved weight traffic buys nothing (the pair kernel is not L2-bound at the clocks the
+  // power cap allows) and fewer 4-CTA clusters than CTA pairs are co-resident
+  const bool quad = force == 4;
+  if (quad && m->max_quads > 0) {
+    const int clusters = quads_needed < m->max_quads ? quads_needed : m->max_quads;
+    gemm_quad_kernel<<<4 * clusters, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(a);
+  } else {
+    const int n_groups = (a.ntiles + 1) / 2;
+    const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
+    // parameter block in shared memory: bias + the heads actually used
+    gemm_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(a);
+  }
   HOS_LAUNCH_CHECK();
   return HOS_OK;
 }

@@ -40,6 +40,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// the same copy delivered to the same CTA-relative address (and mbarrier) of every CTA in `cta_mask` of the cluster
+__device__ __forceinline__ void bulk_g2s_mcast(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -144,6 +152,11 @@ __device__ __forceinline__ bool elect_one() {      // one lane of the (converged
 __device__ __forceinline__ void tc_commit_pair_addr(uint32_t bar_saddr) {     // arrives on the barrier in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_saddr),
                "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_commit_mask_addr(uint32_t bar_saddr, uint16_t cta_mask) {   // arrives in every CTA of `cta_mask`
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_saddr),
+               "h"(cta_mask)
                : "memory");
 }
 // wait until up to three phases have all completed: the polls overlap instead of paying three latencies in a row

@@ -352,6 +352,9 @@ class FusedMLP:
             pass
 
 
+GEMM_CLUSTER = 0      # A/B switch for new TiledLinear handles: 0 automatic, 2 / 4 force the pair / quad kernel
+
+
 class TiledLinear:
     """One wide nn.Linear (n_out a multiple of 256) on the tensor cores: tiled fp16 in, tiled fp16 out
     (``hos_gemm_*``).  ``x2`` is the skip-connection input whose columns follow (or, ``x_first``, precede) x1's in W."""
@@ -363,6 +366,12 @@ class TiledLinear:
         if not self._h:
             raise RuntimeError("hos_gemm_create failed: " + lib.hos_last_error().decode())
         self.head_dim = 0
+        if GEMM_CLUSTER:
+            self.set_cluster(GEMM_CLUSTER)
+
+    def set_cluster(self, cluster_size: int):
+        """0 automatic, 2 CTA-pair kernel, 4 quad kernel (weight stages multicast between two pairs)."""
+        _lib.check(_lib.load().hos_gemm_set_cluster(self._h, int(cluster_size)), "hos_gemm_set_cluster")
 
     def set_weight(self, w, b):
         _chk(w, "w"), _chk(b, "b")

@@ -29,6 +29,16 @@ cases = {
     "wgrad 256x256": (lambda: ops.wgrad_tma(a, h, out, colsum=cs), 2 * rows * k * 2, 2 * rows * k * n),
     "wgrad 256x504": (lambda: ops.wgrad_tma(a, feat, out504), rows * (256 + 504) * 2, 2 * rows * 504 * n),
 }
+r2 = 65536
+a1k = torch.randn(r2, 1024, device="cuda", generator=g).half()
+h1k = torch.randn(r2, 1024, device="cuda", generator=g).half()
+w1k = (torch.randn(1024, 1024, device="cuda", generator=g) / 32).half()
+b1k = torch.randn(1024, device="cuda", generator=g)
+y1k = torch.empty(r2, 1024, device="cuda", dtype=torch.float16)
+o1k = torch.zeros(1024, 1024, device="cuda")
+cases["fwd 1024 (65k rows)"] = (lambda: ops.gemm_tma(a1k, w1k, 1024, bias=b1k, relu=True, y16=y1k), 2 * r2 * 1024 * 2, 2 * r2 * 1024 * 1024)
+cases["dgrad 1024 (65k rows)"] = (lambda: ops.gemm_tma(a1k, w1k, 1024, mode=1, mask=h1k, y16=y1k), 3 * r2 * 1024 * 2, 2 * r2 * 1024 * 1024)
+cases["wgrad 1024 (65k rows)"] = (lambda: ops.wgrad_tma(a1k, h1k, o1k), 2 * r2 * 1024 * 2, 2 * r2 * 1024 * 1024)
 for name, (fn, nbytes, flops) in cases.items():
     for _ in range(3):
         fn()

@@ -451,10 +451,12 @@ def _untile_f16(buf, rows, k):
     return out[:rows, :k].float()
 
 
+@pytest.mark.parametrize("cluster", [2, 4])
 @pytest.mark.parametrize("rows,n_out,k1,k2", [(128 * 3 + 50, 256, 504, 0), (2000, 1024, 1024, 504), (128 * 151, 512, 512, 0),
-                                               (77, 1024, 1024, 0)])
-def test_wide_layer_gemm_vs_emulation(rows, n_out, k1, k2):
-    """hos_gemm_*: one wide nn.Linear on the tensor cores (tiled fp16 in / out, optional skip input and fp32 head)."""
+                                               (77, 1024, 1024, 0), (128 * 613 + 9, 1024, 1024, 0)])
+def test_wide_layer_gemm_vs_emulation(rows, n_out, k1, k2, cluster):
+    """hos_gemm_*: one wide nn.Linear on the tensor cores (tiled fp16 in / out, optional skip input and fp32 head), on the
+    CTA-pair kernel and on the quad kernel (two pairs per cluster, weight stages multicast between them)."""
     gen = torch.Generator().manual_seed(rows + n_out)
     x1 = torch.randn(rows, k1, generator=gen)
     x2 = torch.randn(rows, k2, generator=gen) if k2 else None
@@ -463,6 +465,7 @@ def test_wide_layer_gemm_vs_emulation(rows, n_out, k1, k2):
     hw = torch.randn(1, n_out, generator=gen) / n_out ** 0.5
     hb = torch.randn(1, generator=gen) * 0.1
     lin = ops.TiledLinear(n_out, k1, k2)
+    lin.set_cluster(cluster)
     lin.set_weight(cu(W), cu(b))
     lin.set_head(cu(hw), cu(hb))
     y, head = lin.forward(ops.pack_rows_f16(cu(x1)), rows, x2_tiled=ops.pack_rows_f16(cu(x2)) if k2 else None,
