@@ -740,6 +740,67 @@ colsum_f16_kernel(const __half* __restrict__ X, int64_t rows, int n, int ld, con
   }
 }
 
+// The same reduction with 16-byte loads: thread -> (8-column group, row phase), a warp reads 512 contiguous bytes of a row,
+// two rows in flight per thread; the CTA's partial sums meet in shared memory (atomics between the row phases only) and leave
+// as one global atomic per output element.  Needs n % 8 == 0, n <= 2048, 16-byte aligned rows.  (The 4-byte-per-thread kernel
+// above ran at 1.0 - 1.4 TB/s: 190 us per 524 288 x 256 head gradient.)
+__global__ void __launch_bounds__(256)
+colsum_f16_v8_kernel(const __half* __restrict__ X, int64_t rows, int n, int ld, const float* __restrict__ g, int hn,
+                     float* __restrict__ out, int ld_out, int rows_per_cta) {
+  extern __shared__ float s_sum[];                       // [hn][n]
+  const int groups = n >> 3;
+  const int phases = 256 / groups;
+  const int cgp = threadIdx.x % groups, ph = threadIdx.x / groups;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  for (int i = threadIdx.x; i < hn * n; i += 256) s_sum[i] = 0.f;
+  __syncthreads();
+  if (ph < phases) {
+    float acc[4][8];
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[h][c] = 0.f;
+    const __half* col = X + 8 * cgp;
+    for (int64_t r = r0 + ph; r < r1; r += 2 * phases) {
+      const int64_t rb = r + phases;
+      const bool okb = rb < r1;
+      const uint4 va = __ldg(reinterpret_cast<const uint4*>(col + r * ld));
+      const uint4 vb = okb ? __ldg(reinterpret_cast<const uint4*>(col + rb * ld)) : make_uint4(0u, 0u, 0u, 0u);
+      float ga[4], gb[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        ga[h] = !g ? (h == 0 ? 1.f : 0.f) : (h < hn ? __ldg(g + r * hn + h) : 0.f);
+        gb[h] = !g ? (h == 0 ? 1.f : 0.f) : ((okb && h < hn) ? __ldg(g + rb * hn + h) : 0.f);
+      }
+      const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2 a2 = *reinterpret_cast<const __half2*>(&wa[k]), b2 = *reinterpret_cast<const __half2*>(&wb[k]);
+        const float a0 = __low2float(a2), a1 = __high2float(a2), b0 = __low2float(b2), b1 = __high2float(b2);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          acc[h][2 * k] = fmaf(ga[h], a0, acc[h][2 * k]);
+          acc[h][2 * k + 1] = fmaf(ga[h], a1, acc[h][2 * k + 1]);
+          acc[h][2 * k] = fmaf(gb[h], b0, acc[h][2 * k]);
+          acc[h][2 * k + 1] = fmaf(gb[h], b1, acc[h][2 * k + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      if (h < hn) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) atomicAdd(&s_sum[h * n + 8 * cgp + c], acc[h][c]);
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hn * n; i += 256) {
+    const int h = i / n, c = i - h * n;
+    atomicAdd(out + (size_t)h * ld_out + c, s_sum[i]);
+  }
+}
+
 // Y[row, c] = (sum_h g[row, h] W[h, c] (+ Y_add[row, c])) .* (mask[row, c] > 0)   as fp16: the data gradient of a head with
 // <= 4 outputs (density / rgb / raw4 / offset heads), fused with the ReLU mask of the layer it reads.
 __global__ void __launch_bounds__(256)
@@ -991,10 +1052,21 @@ int hos_colsum_f16(const void* x, int64_t rows, int n, int ld, const float* g, i
   HOS_REQUIRE(x && out && rows >= 0 && n >= 2 && (n % 2) == 0 && (ld % 2) == 0 && hn >= 0 && hn <= 4 && (g || hn <= 1),
               "hos_colsum_f16: X [rows, n even], hn <= 4");
   if (rows == 0) return HOS_OK;
+  const int hn_eff = g ? hn : 1;
+  if ((n % 8) == 0 && n <= 2048 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // about four CTAs per SM in one wave, at least 256 rows each
+    int64_t per = (rows + 148 * 4 - 1) / (148 * 4);
+    if (per < 256) per = 256;
+    const unsigned grid = (unsigned)((rows + per - 1) / per);
+    colsum_f16_v8_kernel<<<grid, 256, (size_t)hn_eff * n * sizeof(float), (cudaStream_t)stream>>>((const __half*)x, rows, n, ld, g, hn_eff,
+                                                                                               out, ld_out, (int)per);
+    HOS_LAUNCH_CHECK();
+    return HOS_OK;
+  }
   const int rows_per_cta = 512;
   const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
   const int threads = 256;
-  colsum_f16_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)x, rows, n, ld, g, g ? hn : 1, out, ld_out, rows_per_cta);
+  colsum_f16_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>((const __half*)x, rows, n, ld, g, hn_eff, out, ld_out, rows_per_cta);
   HOS_LAUNCH_CHECK();
   return HOS_OK;
 }

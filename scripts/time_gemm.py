@@ -39,6 +39,12 @@ o1k = torch.zeros(1024, 1024, device="cuda")
 cases["fwd 1024 (65k rows)"] = (lambda: ops.gemm_tma(a1k, w1k, 1024, bias=b1k, relu=True, y16=y1k), 2 * r2 * 1024 * 2, 2 * r2 * 1024 * 1024)
 cases["dgrad 1024 (65k rows)"] = (lambda: ops.gemm_tma(a1k, w1k, 1024, mode=1, mask=h1k, y16=y1k), 3 * r2 * 1024 * 2, 2 * r2 * 1024 * 1024)
 cases["wgrad 1024 (65k rows)"] = (lambda: ops.wgrad_tma(a1k, h1k, o1k), 2 * r2 * 1024 * 2, 2 * r2 * 1024 * 1024)
+gw = torch.randn(rows, 1, device="cuda", generator=g)
+gw3 = torch.randn(rows, 3, device="cuda", generator=g)
+o1 = torch.zeros(1, n, device="cuda"); o3 = torch.zeros(3, n, device="cuda")
+cases["colsum head 1x256"] = (lambda: ops.colsum_f16(a, o1, g=gw), rows * k * 2, 2 * rows * k)
+cases["colsum head 3x256"] = (lambda: ops.colsum_f16(a, o3, g=gw3), rows * k * 2, 6 * rows * k)
+cases["colsum bias 256"] = (lambda: ops.colsum_f16(a, cs), rows * k * 2, rows * k)
 for name, (fn, nbytes, flops) in cases.items():
     for _ in range(3):
         fn()
