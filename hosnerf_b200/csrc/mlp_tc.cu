@@ -105,6 +105,7 @@ struct MlpArgs {
   int f_nfreq, f_ident;           // mode 2: octaves 2^0 .. 2^(f_nfreq-1); identity columns first (fourier.py) or not (hannw_fourier.py)
   float f_hann[16];               // mode 2: per-octave window weights (all 1 for the plain embedder)
   long long* timeline;            // optional debug: per (tile iteration, layer) 4 clock64() stamps of CTA 0
+  int duo;                        // pair kernel: two tile pairs in flight per cluster, units interleaved layer by layer (narrow programs)
 };
 
 // ----------------------------------------------------------------------------- fused IPE prologue
@@ -591,7 +592,7 @@ constexpr int kOnesBytes = kTileM * 32;               // constant ones operand: 
 constexpr int kPairProducers = 3;
 constexpr int kPairMaxKbh = 4;
 constexpr int kRowBiasVecs = 4;
-constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 2 + kPairMaxKbh + 2;
+constexpr int kPairBars = 2 * kPairMaxStagesW + 2 * kPairStagesX + 4 + 2 * kPairMaxKbh + 4;
 static_assert(kPairBars % 2 == 0, "s_headx behind the barriers is read as float4");
 
 // One row of the Fourier / Hann-windowed embedding as 64 packed fp16 values (column order of the reference embedders; columns
@@ -629,8 +630,14 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_stage_bytes = prog.n_max * 64;               // this CTA's half of an [n_max x 64] fp16 chunk
-  unsigned char* sH = smem;                                // [kbh][16 KB] activations (A operand of the next layer)
-  unsigned char* sOnes = sH + prog.kbh * kXChunkBytes;     // [4 KB] constant A operand of the bias MMA: [128 x 16], columns 0, 1 = 1.0
+  // "duo" mode (narrow programs: n_max <= 128, so four 128-column accumulators fit in TMEM): a cluster keeps TWO tile pairs in
+  // flight and walks the units (layer l, tile pair t) as l0t0 l0t1 l1t0 l1t1 ...: while one tile pair is in the layer-to-layer
+  // hand-off (commit -> epilogue -> first operand chunk: 1.5 - 2.8 k cycles against 0.5 k cycles of tensor work for a 128-wide
+  // layer) the other one's MMAs run.  Each tile pair has its own activation buffer, accumulator pair and hready barriers.
+  const int T = args.duo ? 2 : 1;
+  const uint32_t h_tile_bytes = (uint32_t)prog.kbh * kXChunkBytes;
+  unsigned char* sH = smem;                                // [T][kbh][16 KB] activations (A operand of the next layer)
+  unsigned char* sOnes = sH + T * h_tile_bytes;            // [4 KB] constant A operand of the bias MMA: [128 x 16], columns 0, 1 = 1.0
   unsigned char* sRingW = sOnes + kOnesBytes;              // [stages_w][w_stage_bytes]
   unsigned char* sRingX = sRingW + stages_w * w_stage_bytes;       // [kPairStagesX][16 KB]
   float* sParams = reinterpret_cast<float*>(sRingX + kPairStagesX * kXChunkBytes);   // head weights / biases only: the layer
@@ -642,11 +649,13 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   uint64_t* bar_xfull = bar_wempty + kPairMaxStagesW;      // [2] leader: feature chunk complete in BOTH CTAs (fused: one arrive
                                                            //     per feature warp of the pair; else own tx bytes + relay)
   uint64_t* bar_xempty = bar_xfull + kPairStagesX;         // [2] multicast commit
-  uint64_t* bar_tfull = bar_xempty + kPairStagesX;         // [2 accumulator buffers] multicast commit
-  uint64_t* bar_hready = bar_tfull + 2;                    // [kbh] leader only: K-chunk c of the next A operand written by
-                                                           //       the 16 epilogue warps of the pair
-  uint64_t* bar_tfree = bar_hready + kPairMaxKbh;          // [1] leader only: a head layer's epilogue has finished its deferred
+  uint64_t* bar_tfull = bar_xempty + kPairStagesX;         // [2 accumulator buffers; duo: 4 = (tile pair, layer parity)] multicast commit
+  uint64_t* bar_hready = bar_tfull + 4;                    // [T][kPairMaxKbh] leader only: K-chunk c of the next A operand written
+                                                           //       by the 16 epilogue warps of the pair
+  uint64_t* bar_tfree = bar_hready + 2 * kPairMaxKbh;      // [1] leader only: a head layer's epilogue has finished its deferred
                                                            //     second pass over the accumulator (16 warp arrivals)
+  uint64_t* bar_tlast = bar_tfree + 2;                     // [2] leader only, duo: the LAST layer's epilogue of tile pair t has read
+                                                           //     its accumulator (nothing else orders the next iteration's layer 0 after it)
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kPairBars);       // kPairBars is even: 16-byte aligned
   float* s_headx = reinterpret_cast<float*>(s_tmem + 4);   // [128][4], read as float4
   float* s_rowbias = s_headx + kTileM * 4;                 // [kRowBiasVecs][128] per-ray bias vectors of the current tile
@@ -674,9 +683,11 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       mbar_init(&bar_xfull[s], fused ? 8 : both);
       mbar_init(&bar_xempty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) mbar_init(&bar_tfull[s], 1);
-    for (int s = 0; s < kPairMaxKbh; ++s) mbar_init(&bar_hready[s], 2 * kEpiWarps);
+    for (int s = 0; s < 4; ++s) mbar_init(&bar_tfull[s], 1);
+    const uint32_t epi_arrivals = args.duo ? (uint32_t)kEpiWarps : 2u * kEpiWarps;       // duo: four epilogue warps per CTA and tile pair
+    for (int s = 0; s < 2 * kPairMaxKbh; ++s) mbar_init(&bar_hready[s], epi_arrivals);
     mbar_init(&bar_tfree[0], 2 * kEpiWarps);
+    for (int s = 0; s < 2; ++s) mbar_init(&bar_tlast[s], epi_arrivals);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -689,15 +700,19 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0 || warp == 2 || warp == 3) {
-    // ===================== weight producers: chunk i -> producer i % 3, ring stage i % S =====================
+  if (warp == 0 || warp == 2 || (warp == 3 && !args.duo)) {
+    // ===================== weight producers: chunk i -> producer i % P, ring stage i % S =====================
+    // (duo: two producers - warp 3 of the leader is the second MMA issuer; with the relay in the watcher warp a producer only
+    // issues copies and never waits for one to land)
     if (lane == 0) {
+      const uint32_t n_prod = args.duo ? 2u : (uint32_t)kPairProducers;
       const uint32_t p = warp == 0 ? 0u : (uint32_t)(warp - 1);
       uint32_t wi = 0, xi = 0;
-      for (int g = cluster; g < n_groups; g += n_clusters) {
-        int tile = 2 * g + (int)rank;
-        if (tile >= args.ntiles) tile = args.ntiles - 1;            // padding tile: any valid rows, outputs masked
+      for (int g0 = cluster; g0 < n_groups; g0 += T * n_clusters) {
         for (int l = 0; l < n_layers; ++l) {
+         for (int t = 0; t < T; ++t) {
+          int tile = 2 * (g0 + t * n_clusters) + (int)rank;
+          if (tile >= args.ntiles) tile = args.ntiles - 1;          // padding tile: any valid rows, outputs masked
           const LayerDev L = prog.layers[l];
           const uint32_t half_bytes = (uint32_t)L.n * 64u;
           const int nkb = L.kb_h + L.kb_x;
@@ -715,7 +730,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
               bulk_g2s(sRingX + xs * kXChunkBytes, args.x_tiled + ((size_t)tile * prog.kbx + (kb - L.kb_h)) * kXChunkBytes,
                        kXChunkBytes, &bar_xfull[xs]);
             }
-            const bool load_w = wi % kPairProducers == p;
+            const bool load_w = wi % n_prod == p;
             const uint32_t ws = wi % S, use = wi / S;
             if (load_w) {
               mbar_wait_guard<100>(&bar_wempty[ws], (use & 1) ^ 1);
@@ -723,22 +738,39 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
               bulk_g2s(sRingW + ws * w_stage_bytes, args.w_packed + L.w_off + (size_t)kb * (2u * half_bytes) + rank * half_bytes,
                        half_bytes, &bar_wfull[ws]);
             }
-            if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
-              if (load_x) {
-                mbar_wait_guard<100>(&bar_xfull[xs], xuse & 1);
-                mbar_arrive_remote(mapa_u32(smem_u32(&bar_xfull[xs]), 0));
-              }
-              if (load_w) {
-                mbar_wait_guard<100>(&bar_wfull[ws], use & 1);
-                mbar_arrive_remote(mapa_u32(smem_u32(&bar_wfull[ws]), 0));
-              }
+            if (rank != 0 && load_x) {          // relay to the leader once this CTA's bytes are in shared memory
+              mbar_wait_guard<100>(&bar_xfull[xs], xuse & 1);
+              mbar_arrive_remote(mapa_u32(smem_u32(&bar_xfull[xs]), 0));
             }
+            // (the weight stages are relayed by the peer's watcher warp below: a producer that waited for its own copy to land
+            // before issuing the next one moved one chunk per L2 round trip - three producers barely fed one 512-cycle chunk
+            // of tensor work each)
+          }
+         }
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer CTA: weight-stage watcher =====================
+    // tells the leader "my half of weight stage s has landed", stage by stage in ring order
+    if (lane == 0) {
+      const uint32_t wfull_leader = mapa_u32(smem_u32(&bar_wfull[0]), 0);
+      uint32_t ws = 0, wpar = 0;
+      for (int g0 = cluster; g0 < n_groups; g0 += T * n_clusters) {
+        for (int l = 0; l < n_layers; ++l) {
+          const int nchunks_w = (prog.layers[l].kb_h + prog.layers[l].kb_x + 1) * T;
+          for (int i = 0; i < nchunks_w; ++i) {
+            mbar_wait_guard<40>(&bar_wfull[ws], wpar);
+            mbar_arrive_remote(wfull_leader + 8u * ws);
+            if (++ws == S) { ws = 0; wpar ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
+  } else if (warp == 1 || warp == 3) {
+    // ===================== MMA issuer (one thread of the leader CTA; duo: two - warp 1 issues the units of tile pair 0, warp 3
+    // those of tile pair 1: a 128-wide layer is 9 MMAs of 64 cycles, and the polls + commits around them cost one thread
+    // ~1.5 k cycles per unit) =====================
     // A single thread runs ~5 cycles per dependent instruction and every try_wait / commit costs 60-180 cycles
     // (scripts/ubench_tc.cu, test 8), while a K = 64 chunk lasts only 512 cycles on the tensor core: the loop
     // therefore works on GROUPS of up to three chunks - all their barriers polled in one parallel try_wait,
@@ -750,26 +782,44 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     // elect.sync: tcgen05.mma takes its descriptors from uniform registers, and when the issue code ran on one lane of
     // a divergent branch the compiler had to move 7 values per MMA through R2UR in a wait-loop (~130 cycles per MMA).
     if (rank == 0) {
-      uint32_t u = 0, hpar = 0;                      // unit counter; parity of the hready phase the next H-reading unit waits for
+      uint32_t u = 0;                                // unit counter
+      uint32_t hpar_bits = 0u;                       // bit t: parity of the hready phase tile pair t's next H-reading unit waits for
       uint32_t ws = 0, wpar = 0, xs = 0, xpar = 0;   // weight / feature ring cursors + phase parities
       bool prev_had_h = true;
       const uint64_t desc_hi = umma_desc(0);
       const uint32_t wfull0 = smem_u32(&bar_wfull[0]), wempty0 = smem_u32(&bar_wempty[0]);
       const uint32_t xfull0 = smem_u32(&bar_xfull[0]), xempty0 = smem_u32(&bar_xempty[0]);
       const uint32_t hready_a = smem_u32(&bar_hready[0]), tfull0 = smem_u32(&bar_tfull[0]);
-      const uint32_t tfree_a = smem_u32(&bar_tfree[0]);
+      const uint32_t tfree_a = smem_u32(&bar_tfree[0]), tlast_a = smem_u32(&bar_tlast[0]);
       uint32_t tfpar = 0;
       bool head_hist[2] = {false, false};
       const uint32_t h16 = (smem_u32(sH) >> 4) & 0x3FFF, x16 = (smem_u32(sRingX) >> 4) & 0x3FFF;
       const uint32_t w16 = (smem_u32(sRingW) >> 4) & 0x3FFF;
       const uint64_t ones_desc = umma_desc_sw32(smem_u32(sOnes));
       const uint32_t wstage16 = (uint32_t)w_stage_bytes >> 4;
-      for (int g = cluster; g < n_groups; g += n_clusters) {
-        for (int l = 0; l < n_layers; ++l, ++u) {
+      uint32_t iter = 0;
+      const int my_t = warp == 3 ? 1 : 0;
+      for (int g0 = cluster; g0 < n_groups; g0 += T * n_clusters, ++iter) {
+        for (int l = 0; l < n_layers; ++l) {
+         for (int t = 0; t < T; ++t, ++u) {
           const LayerDev L = prog.layers[l];
           const uint32_t idesc = umma_idesc_f16(L.n, 2 * kTileM);
           const int kb_h = L.kb_h, nkb = L.kb_h + L.kb_x;
-          const uint32_t acc = tmem_base + (u & 1) * 256;
+          if (args.duo && t != my_t) {               // the other issuer's unit: step the ring cursors over its stages
+            uint32_t adv = (uint32_t)nkb + 1u + ws;
+            while (adv >= S) { adv -= S; wpar ^= 1u; }
+            ws = adv;
+            uint32_t advx = (uint32_t)L.kb_x + xs;
+            while (advx >= (uint32_t)kPairStagesX) { advx -= kPairStagesX; xpar ^= 1u; }
+            xs = advx;
+            continue;
+          }
+
+          const uint32_t abuf = args.duo ? (uint32_t)(2 * t + (l & 1)) : (u & 1);       // accumulator buffer / tfull barrier
+          const uint32_t acc = tmem_base + (args.duo ? abuf * 128u : abuf * 256u);
+          const uint32_t hready_t = hready_a + 8u * (uint32_t)(t * kPairMaxKbh);
+          const uint32_t h16_t = h16 + (uint32_t)t * (h_tile_bytes >> 4);
+          const uint32_t hpar = (hpar_bits >> t) & 1u;
           const bool tl = args.timeline && blockIdx.x == 0 && u < 64 && lane == 0;
           long long wait_sum = 0;
           if (tl) args.timeline[u * 12 + 0] = clock64();
@@ -784,6 +834,15 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             // operand chunk of this unit as well (signalled by epilogue(u - 1), which runs after epilogue(u - 2)).
             // A hidden layer with an fp32 head re-reads its accumulator after it has signalled all operand chunks
             // (deferred head pass): its buffer is free only once bar_tfree completes.
+            if (args.duo) {
+              // Buffer (t, l & 1) was last read by the epilogue of unit (t, l - 2), which ran before the epilogue of (t, l - 1)
+              // whose chunks this warp waited for when it issued that unit - except across iterations: nothing waits for the
+              // previous iteration's LAST layer's epilogue, so the first unit that reuses ITS buffer (layer 0 or 1, by parity)
+              // waits for bar_tlast.  (With an even layer count that is layer 1: the slow head epilogue gets a whole unit of slack.)
+              const int l_reuse = (n_layers - 1) & 1;
+              if (l == l_reuse && iter > 0 && l_reuse < n_layers) mbar_wait2_spin(wfull0 + 8u * ws, wpar, tlast_a + 8u * (uint32_t)t, (iter - 1) & 1u);
+              else mbar_wait2_spin(wfull0 + 8u * ws, wpar, wfull0 + 8u * ws, wpar);
+            } else {
             if (head_hist[u & 1]) {
               mbar_wait2_spin(tfree_a, tfpar, tfree_a, tfpar);
               tfpar ^= 1u;
@@ -792,6 +851,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             if (u < 2 || prev_had_h) mbar_wait2_spin(wfull0 + 8u * ws, wpar, wfull0 + 8u * ws, wpar);
             else mbar_wait2_spin(wfull0 + 8u * ws, wpar, kb_h > 0 ? hready_a : xfull0 + 8u * xs, kb_h > 0 ? hpar : xpar);
             prev_had_h = kb_h > 0;
+            }
             tc_fence_after();
             if (elect_one()) {
               tc_mma_f16_pair(acc, ones_desc, desc_hi | (uint64_t)(w16 + ws * wstage16), idesc, 0u);
@@ -817,7 +877,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                 if (i + 1 < nst) { if (++s_ == S) { s_ = 0; p_ ^= 1; } }
               }
             }
-            const uint32_t ob = is_h ? hready_a + 8u * (uint32_t)(kb + cnt - 1) : xfull0 + 8u * xs;
+            const uint32_t ob = is_h ? hready_t + 8u * (uint32_t)(kb + cnt - 1) : xfull0 + 8u * xs;
             const uint32_t op = is_h ? hpar : xpar;
             const long long c0 = tl ? clock64() : 0;
             mbar_wait3_spin(wb[0], wp[0], wb[1], wp[1], ob, op);
@@ -832,7 +892,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             const bool leader_lane = elect_one();
 #pragma unroll 1
             for (int i = 0; i < cnt; ++i) {
-              const uint32_t a16 = is_h ? h16 + (uint32_t)(kb + i) * (kXChunkBytes >> 4) : x16 + xs * (kXChunkBytes >> 4);
+              const uint32_t a16 = is_h ? h16_t + (uint32_t)(kb + i) * (kXChunkBytes >> 4) : x16 + xs * (kXChunkBytes >> 4);
               const uint64_t adesc = desc_hi | (uint64_t)a16;
               const uint64_t bdesc = desc_hi | (uint64_t)(w16 + ws * wstage16);
               if (leader_lane) {
@@ -841,7 +901,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
                   tc_mma_f16_pair(acc, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
                 tc_commit_pair_addr(wempty0 + 8u * ws);
                 if (!is_h) tc_commit_pair_addr(xempty0 + 8u * xs);
-                if (last_group && i == cnt - 1) tc_commit_pair_addr(tfull0 + 8u * (u & 1));     // accumulator complete
+                if (last_group && i == cnt - 1) tc_commit_pair_addr(tfull0 + 8u * abuf);       // accumulator complete
               }
               if (++ws == S) { ws = 0; wpar ^= 1; }
               if (!is_h) { if (++xs == kPairStagesX) { xs = 0; xpar ^= 1; } }
@@ -851,8 +911,9 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             ++gi3;
             kb += cnt;
           }
-          if (kb_h) hpar ^= 1;
+          if (kb_h) hpar_bits ^= 1u << t;
           if (tl) { args.timeline[u * 12 + 1] = clock64(); args.timeline[u * 12 + 8] = wait_sum; }
+         }
         }
       }
     }
@@ -864,25 +925,142 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     const int r = q * 32 + lane;
     const uint32_t hready0 = mapa_u32(smem_u32(&bar_hready[0]), 0);
     const uint32_t tfree0 = mapa_u32(smem_u32(&bar_tfree[0]), 0);
+    const uint32_t tlast0 = mapa_u32(smem_u32(&bar_tlast[0]), 0);
     const uint32_t sparams_u32 = smem_u32(sParams) - 4u * (uint32_t)prog.head_base;   // indexed with whole-block offsets
     const uint32_t headx_u32 = smem_u32(s_headx) + 16u * r;
     // this thread's 16-byte slots in a K-chunk of H: row r, 16-byte groups 4 ch .. 4 ch + 3 (128B swizzle)
     const uint32_t h_row = smem_u32(sH) + 128u * r;
-    uint32_t h_off[4];
+    uint32_t h_off0[4];
 #pragma unroll
-    for (int gq = 0; gq < 4; ++gq) h_off[gq] = h_row + ((uint32_t)((4 * ch + gq) ^ (r & 7)) << 4);
+    for (int gq = 0; gq < 4; ++gq) h_off0[gq] = h_row + ((uint32_t)((4 * ch + gq) ^ (r & 7)) << 4);
     uint32_t u = 0;
-    for (int g = cluster; g < n_groups; g += n_clusters) {
-      const int tile = 2 * g + (int)rank;
-      const int64_t row = (int64_t)tile * kTileM + r;
-      const bool row_ok = row < args.rows;
-      for (int l = 0; l < n_layers; ++l, ++u) {
+    uint32_t tf_use = 0;                                      // bit b: parity of the next phase of bar_tfull[b] to wait for
+    if (args.duo) {
+      // ---------- duo schedule: warps 4-7 drain the units of tile pair 0, warps 8-11 those of tile pair 1, concurrently (an
+      // epilogue of a 128-wide unit is a ~1.2 k-cycle latency chain - TMEM load, convert, store, fence, arrive - not a
+      // throughput problem).  Each warp takes all 64 columns of a chunk for its 32 rows; the head's dot products stay in one thread.
+      const int t = ch;
+      uint32_t hq[2][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          hq[hh][gq] = h_row + (uint32_t)t * h_tile_bytes + ((uint32_t)((4 * hh + gq) ^ (r & 7)) << 4);
+      const uint32_t hready_t = hready0 + 8u * (uint32_t)(t * kPairMaxKbh);
+      for (int g0 = cluster; g0 < n_groups; g0 += 2 * n_clusters) {
+        const int g = g0 + t * n_clusters;
+        const int64_t row = (int64_t)(2 * g + (int)rank) * kTileM + r;
+        const bool row_ok = g < n_groups && row < args.rows;
+        for (int l = 0; l < n_layers; ++l) {
+          const LayerDev L = prog.layers[l];
+          const bool last = (l == n_layers - 1);
+          const bool relu = L.relu != 0;
+          const int nchunks = L.n >> 6;
+          const uint32_t abuf = (uint32_t)(2 * t + (l & 1));
+          const uint32_t acc = tmem_base + abuf * 128u + ((uint32_t)(q * 32) << 16);
+          mbar_wait_guard<20>(&bar_tfull[abuf], (tf_use >> abuf) & 1u);
+          tf_use ^= 1u << abuf;
+          tc_fence_after();
+          const HeadDev Hd = prog.heads[L.head >= 0 ? L.head : 0];
+          float hacc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int c = 0; c < nchunks; ++c) {
+            uint32_t va[32], vb[32];
+            tmem_ld32_nowait(acc + (uint32_t)(c * 64), va);
+            tmem_ld32_nowait(acc + (uint32_t)(c * 64 + 32), vb);
+            tmem_wait_ld();
+            if (!last) {
+              const uint32_t cb = (uint32_t)c * kXChunkBytes;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t (&v)[32] = hh ? vb : va;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                  uint32_t p0, p1, p2, p3;
+                  if (relu) {
+                    p0 = cvt_relu_f16x2(v[gq * 8 + 0], v[gq * 8 + 1]); p1 = cvt_relu_f16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                    p2 = cvt_relu_f16x2(v[gq * 8 + 4], v[gq * 8 + 5]); p3 = cvt_relu_f16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
+                  } else {
+                    p0 = cvt_f16x2(v[gq * 8 + 0], v[gq * 8 + 1]); p1 = cvt_f16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                    p2 = cvt_f16x2(v[gq * 8 + 4], v[gq * 8 + 5]); p3 = cvt_f16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
+                  }
+                  sts128(hq[hh][gq] + cb, p0, p1, p2, p3);
+                }
+              }
+              fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
+              tc_fence_before();          // TMEM loads of this chunk ordered before the arrive
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(hready_t + 8u * c);
+            } else if (L.head >= 0) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const uint32_t (&v)[32] = hh ? vb : va;
+                const int c0 = c * 64 + hh * 32;
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                  if (n < Hd.hn) {
+                    const uint32_t w4 = sparams_u32 + 4u * (uint32_t)(Hd.w_off + n * L.n + c0);
+                    float a = hacc[n];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      const float4 w = lds128(w4 + 16u * j);
+                      const float f0 = __uint_as_float(v[4 * j + 0]), f1 = __uint_as_float(v[4 * j + 1]);
+                      const float f2 = __uint_as_float(v[4 * j + 2]), f3 = __uint_as_float(v[4 * j + 3]);
+                      a = fmaf(relu ? fmaxf(f0, 0.f) : f0, w.x, a); a = fmaf(relu ? fmaxf(f1, 0.f) : f1, w.y, a);
+                      a = fmaf(relu ? fmaxf(f2, 0.f) : f2, w.z, a); a = fmaf(relu ? fmaxf(f3, 0.f) : f3, w.w, a);
+                    }
+                    hacc[n] = a;
+                  }
+                }
+              }
+            }
+          }
+          if (last) {                       // accumulator read: the next iteration's layer 0 of this tile pair may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tlast0 + 8u * (uint32_t)t);
+            if (L.head >= 0 && row_ok) {
+              const float4 hb = lds128(sparams_u32 + 4u * Hd.b_off);
+              const float hbias[4] = {hb.x, hb.y, hb.z, hb.w};
+              float* o = args.out[Hd.slot] + row * Hd.hn;
+#pragma unroll
+              for (int n = 0; n < 4; ++n) {
+                if (n >= Hd.hn) break;
+                float x = hacc[n] + hbias[n];
+                if (Hd.post == 1) {
+                  float z = x + Hd.shift;
+                  x = z > 20.f ? z : log1pf(expf(z));
+                } else if (Hd.post == 2) {
+                  x = (1.f / (1.f + expf(-x))) * (1.f + 2.f * Hd.shift) - Hd.shift;
+                } else if (Hd.post == 3) {
+                  x = args.add[row * Hd.hn + n] + x;
+                } else if (Hd.post == 4) {
+                  x = (n < 3) ? 1.f / (1.f + expf(-x)) : fmaxf(x, 0.f);
+                }
+                o[n] = x;
+              }
+            }
+          }
+        }
+      }
+    } else
+    for (int g0 = cluster; g0 < n_groups; g0 += T * n_clusters) {
+      for (int l = 0; l < n_layers; ++l) {
+       for (int t = 0; t < T; ++t, ++u) {
+        const int g = g0 + t * n_clusters;                     // >= n_groups: padding tile pair of a duo iteration (nothing stored)
+        const int tile = 2 * g + (int)rank;
+        const int64_t row = (int64_t)tile * kTileM + r;
+        const bool row_ok = g < n_groups && row < args.rows;
+        uint32_t h_off[4];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) h_off[gq] = h_off0[gq] + (uint32_t)t * h_tile_bytes;
+        const uint32_t hready_t = hready0 + 8u * (uint32_t)(t * kPairMaxKbh);
         const LayerDev L = prog.layers[l];
         const bool last = (l == n_layers - 1);
         const bool has_head = L.head >= 0;
         const bool relu = L.relu != 0;
         const int nchunks = L.n >> 6;
-        const uint32_t acc = tmem_base + (u & 1) * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        const uint32_t abuf = args.duo ? (uint32_t)(2 * t + (l & 1)) : (u & 1);
+        const uint32_t acc = tmem_base + (args.duo ? abuf * 128u : abuf * 256u) + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
         const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && u < 64;
         // Per-ray bias (view-direction term): when a tile spans a whole number of rays (or one ray spans whole tiles) its
         // <= 4 bias vectors are fetched into shared memory BEFORE the wait for the accumulator, so the L2 latency is
@@ -905,7 +1083,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           }
         }
         if (tl) args.timeline[u * 12 + 3] = clock64();
-        mbar_wait_guard<20>(&bar_tfull[u & 1], (u >> 1) & 1);
+        mbar_wait_guard<20>(&bar_tfull[abuf], (tf_use >> abuf) & 1u);
+        tf_use ^= 1u << abuf;
         tc_fence_after();
         if (tl) args.timeline[u * 12 + 4] = clock64();
 
@@ -914,7 +1093,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           fence_proxy_async();        // H stores (generic proxy) -> visible to the tensor core (async proxy)
           tc_fence_before();          // TMEM loads of this chunk ordered before the arrive
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(hready0 + 8u * c);
+          if (lane == 0) mbar_arrive_remote(hready_t + 8u * c);
         };
 
         const HeadDev Hd = prog.heads[has_head ? L.head : 0];
@@ -1062,6 +1241,10 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         }
         {
           if (last) tc_fence_before();
+          if (last && args.duo) {                 // accumulator read: the next iteration's layer 0 of this tile pair may overwrite it
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tlast0 + 8u * (uint32_t)t);
+          }
           if (has_head) {                         // combine the two column halves, then post-process
             if (ch == 1) sts128(headx_u32, __float_as_uint(hacc[0]), __float_as_uint(hacc[1]), __float_as_uint(hacc[2]), __float_as_uint(hacc[3]));
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -1092,6 +1275,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           }
         }
         if (tl) args.timeline[u * 12 + 5] = clock64();
+       }
       }
     }
   } else if (args.fused_ipe == 2 && warp >= kFeatWarp0) {
@@ -1103,16 +1287,23 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     const uint32_t xremote = rank != 0 ? mapa_u32(smem_u32(&bar_xfull[0]), 0) : 0u;
     const uint32_t row_u32 = smem_u32(sRingX) + 128u * (uint32_t)r, r7 = (uint32_t)(r & 7);
     uint32_t xi = 0;
-    for (int g = cluster; g < n_groups; g += n_clusters) {
-      const int64_t row = (int64_t)(2 * g + (int)rank) * kTileM + r;
-      const bool ok = row < args.rows;
-      float p[3] = {0.f, 0.f, 0.f};
-      if (ok) { p[0] = args.fx[row * 3 + 0]; p[1] = args.fx[row * 3 + 1]; p[2] = args.fx[row * 3 + 2]; }
-      uint32_t pk[32];                                         // the row's 64 fp16 features
-      if (args.f_ident) fourier_row<true>(p, args.f_nfreq, args.f_hann, ok, pk);
-      else fourier_row<false>(p, args.f_nfreq, args.f_hann, ok, pk);
+    for (int g0 = cluster; g0 < n_groups; g0 += T * n_clusters) {
+      float pa[3] = {0.f, 0.f, 0.f}, pb[3] = {0.f, 0.f, 0.f};
+      const int64_t row_a = (int64_t)(2 * g0 + (int)rank) * kTileM + r;
+      const int64_t row_b = (int64_t)(2 * (g0 + n_clusters) + (int)rank) * kTileM + r;
+      const bool ok_a = row_a < args.rows, ok_b = T == 2 && g0 + n_clusters < n_groups && row_b < args.rows;
+      if (ok_a) { pa[0] = args.fx[row_a * 3 + 0]; pa[1] = args.fx[row_a * 3 + 1]; pa[2] = args.fx[row_a * 3 + 2]; }
+      if (ok_b) { pb[0] = args.fx[row_b * 3 + 0]; pb[1] = args.fx[row_b * 3 + 1]; pb[2] = args.fx[row_b * 3 + 2]; }
       for (int l = 0; l < n_layers; ++l) {
-        if (prog.layers[l].kb_x == 0) continue;
+       if (prog.layers[l].kb_x == 0) continue;
+       for (int t = 0; t < T; ++t) {
+        // the row's 64 fp16 features: re-encoded per reading layer (3 sincos + doublings), so that two tile pairs in flight do not
+        // hold two encoded rows in registers
+        const float p[3] = {t ? pb[0] : pa[0], t ? pb[1] : pa[1], t ? pb[2] : pa[2]};
+        const bool ok = t ? ok_b : ok_a;
+        uint32_t pk[32];
+        if (args.f_ident) fourier_row<true>(p, args.f_nfreq, args.f_hann, ok, pk);
+        else fourier_row<false>(p, args.f_nfreq, args.f_hann, ok, pk);
         const int xs = xi % kPairStagesX;
         mbar_wait_guard<40>(&bar_xempty[xs], ((xi / kPairStagesX) & 1) ^ 1);
         const uint32_t slot = row_u32 + (uint32_t)xs * kXChunkBytes;
@@ -1125,6 +1316,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           else mbar_arrive(&bar_xfull[xs]);
         }
         ++xi;
+       }
       }
     }
   } else if (args.fused_ipe == 1 && warp >= kFeatWarp0) {
@@ -1552,7 +1744,9 @@ struct hos_mlp {
   int pair_stages = 0;     // depth of its weight ring
   int max_clusters = 0;    // co-resident 2-CTA clusters (persistent grid of the pair kernel)
   int ipe_perm = 0;        // weights packed for the fused-IPE column order
-  int variant = 0;         // kernel selection of THIS handle: 0 automatic, 1 single-CTA kernel, 2 cluster-pair kernel
+  int variant = 0;         // kernel selection of THIS handle: 0 automatic, 1 single-CTA kernel, 2 cluster-pair kernel,
+                           // 3 cluster-pair kernel with one tile pair in flight (A/B against the duo schedule)
+  int duo_ok = 0;          // the pair kernel can keep two tile pairs in flight for this program (narrow layers)
   long long* timeline = nullptr;   // optional debug buffer of THIS handle (hos_mlp_debug_timeline)
 };
 
@@ -1640,7 +1834,11 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   for (int l = 0; l < n_layers; ++l) pair_ok = pair_ok && (layers[l].out_dim % 64) == 0;
   for (int l = 0; l + 1 < n_layers; ++l) pair_ok = pair_ok && layers[l].out_dim == P.kbh * kKB;   // one hready phase count
   pair_ok = pair_ok && P.kbh <= kPairMaxKbh;
-  const size_t pair_fixed = 1024 + (size_t)P.kbh * kXChunkBytes + kOnesBytes + (size_t)kPairStagesX * kXChunkBytes +
+  // duo schedule (two tile pairs in flight): four 128-column accumulators, so every layer <= 128 wide; no per-ray bias and no
+  // fp32 head on a hidden layer (their epilogues hold the accumulator beyond the last operand chunk)
+  bool duo_ok = pair_ok && nmax <= 128;
+  for (int l = 0; l < n_layers; ++l) duo_ok = duo_ok && !layers[l].rowbias && (layers[l].head < 0 || l == n_layers - 1);
+  const size_t pair_fixed = 1024 + (size_t)(duo_ok ? 2 : 1) * P.kbh * kXChunkBytes + kOnesBytes + (size_t)kPairStagesX * kXChunkBytes +
                             (((size_t)(poff - (uint32_t)P.head_base) + 3) & ~(size_t)3) * 4 + (kPairBars + 1) * 8 + 16 +
                             kTileM * 4 * sizeof(float) +
                             kRowBiasVecs * 128 * sizeof(float);
@@ -1649,6 +1847,7 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   pair_ok = pair_ok && pair_stages >= 3;
   const size_t smem_pair = pair_fixed + (size_t)pair_stages * nmax * 64;
   m->pair_stages = pair_stages;
+  m->duo_ok = duo_ok && pair_ok && pair_stages >= 3;
   if (pair_ok && smem_pair <= 227 * 1024) {
     m->smem_pair = smem_pair;
     if (cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
@@ -1759,10 +1958,12 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
     for (int i = 0; i < 16; ++i) a.f_hann[i] = fe->hann[i];
   }
   a.timeline = m->timeline;
+  // two tile pairs in flight when the program allows it and every cluster still gets at least two tile pairs
+  a.duo = m->duo_ok && m->variant != 3 && a.fused_ipe != 1 && (a.ntiles + 1) / 2 >= 2 * m->max_clusters;
   static const IpeArgs kNoIpe = {};
-  HOS_REQUIRE(m->variant != 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
+  HOS_REQUIRE(m->variant < 2 || m->smem_pair, "hos_mlp_forward: the cluster-pair kernel does not support this program");
   // the pair kernel walks groups of 4 tiles; tiny batches keep more SMs busy on the single-CTA kernel
-  const bool pair = m->smem_pair && m->variant != 1 && (m->variant == 2 || a.ntiles >= 2);
+  const bool pair = m->smem_pair && m->variant != 1 && (m->variant >= 2 || a.ntiles >= 2);
   HOS_REQUIRE(!fe || pair, "hos_mlp_forward_fourier: needs the cluster-pair kernel (uniform hidden width, >= 2 row tiles)");
   if (pair) {
     const int n_groups = (a.ntiles + 1) / 2;
@@ -1786,7 +1987,7 @@ int hos_mlp_forward(hos_mlp_t* m, const void* x_tiled, int64_t rows, const float
 }
 
 int hos_mlp_fourier_supported(const hos_mlp_t* m, int64_t rows) {
-  return m && m->smem_pair && m->variant != 1 && !m->ipe_perm && m->prog.kbx == 1 && (m->variant == 2 || (rows + kTileM - 1) / kTileM >= 2);
+  return m && m->smem_pair && m->variant != 1 && !m->ipe_perm && m->prog.kbx == 1 && (m->variant >= 2 || (rows + kTileM - 1) / kTileM >= 2);
 }
 
 int hos_mlp_forward_fourier(hos_mlp_t* m, const float* x, int64_t rows, int n_freqs, int include_input, const float* hann_host,
@@ -1802,7 +2003,8 @@ int hos_mlp_forward_fourier(hos_mlp_t* m, const float* x, int64_t rows, int n_fr
 }
 
 int hos_mlp_set_variant(hos_mlp_t* m, int variant) {
-  HOS_REQUIRE(m && variant >= 0 && variant <= 2, "hos_mlp_set_variant: handle + 0 = auto, 1 = single-CTA kernel, 2 = cluster-pair kernel");
+  HOS_REQUIRE(m && variant >= 0 && variant <= 3,
+              "hos_mlp_set_variant: handle + 0 = auto, 1 = single-CTA kernel, 2 = cluster-pair kernel, 3 = pair kernel, one tile pair in flight");
   m->variant = variant;
   return HOS_OK;
 }

@@ -415,10 +415,11 @@ MLP_TIMELINE = None      # optional int64 CUDA tensor (>= 1024): debug stamps of
 
 
 def set_mlp_variant(variant: int):
-    """0 = automatic, 1 = single-CTA tcgen05 kernel, 2 = cluster-pair (cta_group::2, ping-pong) kernel.  The choice is a
-    field of each ``hos_mlp_t`` handle (``hos_mlp_set_variant(mlp, v)``); this sets the value FusedMLP objects apply."""
+    """0 = automatic, 1 = single-CTA tcgen05 kernel, 2 = cluster-pair (cta_group::2) kernel, 3 = cluster-pair kernel with one
+    tile pair in flight (A/B against the duo schedule of narrow networks).  The choice is a field of each ``hos_mlp_t`` handle
+    (``hos_mlp_set_variant(mlp, v)``); this sets the value FusedMLP objects apply."""
     global MLP_VARIANT
-    assert variant in (0, 1, 2)
+    assert variant in (0, 1, 2, 3)
     MLP_VARIANT = int(variant)
 
 

@@ -1221,3 +1221,23 @@ def test_graphed_step_replays_the_training_chunk():
     assert abs(l2 - l0) > 1e-7, "the step did not change the loss - test is vacuous"
     assert abs(l2 - l3) < 1e-6 and float((sink.flat - g2).norm()) < 1e-5 * float(g2.norm())
     human.static_shapes = False
+
+
+def test_duo_schedule_of_narrow_mlp_matches_one_tile_pair_in_flight():
+    """The non-rigid MLP (128 wide) runs the pair kernel's "duo" schedule - two tile pairs in flight per cluster, units interleaved
+    layer by layer, own accumulators / activation buffers / epilogue warps per tile pair.  Same fp16 program as the schedule with
+    one tile pair in flight (variant 3): the rgb differs only by the summation order of the 3-wide head (fp32)."""
+    hb = {k: cu(v) for k, v in synth.make_human_batch(1500, ray_seed=11).items()}     # 1500 x 128 points: odd number of tile pairs per cluster
+    outs = []
+    for variant in (0, 3):
+        ops.set_mlp_variant(variant)
+        try:
+            net = _human(stage2=True, precision="fp16")
+            with torch.no_grad():
+                out = net(**hb, cycle_outputs=False)
+            torch.cuda.synchronize()
+            outs.append(out["rgb"].clone())
+        finally:
+            ops.set_mlp_variant(0)
+    assert torch.isfinite(outs[0]).all()
+    assert max_abs(outs[0], outs[1]) < 2e-4, max_abs(outs[0], outs[1])
