@@ -1469,7 +1469,7 @@ __device__ __forceinline__ void gemm_cluster_body(const GemmArgs& args) {
   const int param_floats = args.n * (1 + args.hn) + 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sParams + ((param_floats + 3) & ~3));
   // The A and W rings move in lock step, so stage s of both shares one pair of barriers:
-  uint64_t* bar_full = bars;                                // leader: A + W of both CTAs landed (2 tx arrivals + 2 relays); peer: its own two
+  uint64_t* bar_full = bars;                                // leader: A + W of both CTAs landed (2 tx arrivals + 1 relay); peer: its own two
   uint64_t* bar_empty = bar_full + kGemmStages;             // multicast commit: stage s of both rings consumed
   uint64_t* bar_tfull = bar_empty + kGemmStages;            // [2] multicast commit: accumulator buffer complete
   uint64_t* bar_tempty = bar_tfull + 2;                     // [2] leader only: drained by the 16 epilogue warps of the pair
@@ -1487,7 +1487,8 @@ __device__ __forceinline__ void gemm_cluster_body(const GemmArgs& args) {
 
   for (int i = threadIdx.x; i < param_floats; i += kMlpThreads) sParams[i] = args.params[i];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], CS / 2); }
+    // leader: own A + own W + ONE relay from the peer's watcher warp; peer: its own two
+    for (int s = 0; s < kGemmStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 3u : 2u); mbar_init(&bar_empty[s], CS / 2); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1535,11 +1536,24 @@ __device__ __forceinline__ void gemm_cluster_body(const GemmArgs& args) {
                                                        : args.a1 + ((size_t)tile * args.kb1 + (kb - args.kb0)) * kXChunkBytes;
               bulk_g2s(ring + st * kXChunkBytes, src, kXChunkBytes, &full[st]);
             }
-            if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
-              mbar_wait_guard<100>(&full[st], use & 1);
-              mbar_arrive_remote(mapa_u32(smem_u32(&full[st]), leader));
-            }
           }
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer CTA: completion watcher =====================
+    // tells the leader "both of my operands of stage s have landed", stage by stage.  A separate warp, so that a producer never
+    // waits for a copy to ARRIVE before issuing its next one (with the relay in the producer threads each of them moved one chunk
+    // per L2 round trip).
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[0]), leader);
+      uint32_t st = 0, par = 0;
+      for (int g = cluster; g < n_groups; g += n_clusters) {
+        const int nch = nblk * KB;
+        for (int i = 0; i < nch; ++i) {
+          mbar_wait_guard<40>(&bar_full[st], par);
+          mbar_arrive_remote(full_leader + 8u * st);
+          if (++st == kGemmStages) { st = 0; par ^= 1; }
         }
       }
     }

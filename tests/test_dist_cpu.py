@@ -46,6 +46,17 @@ def _worker(rank, world, port, n_rays, mode, q):
         ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 1.5)) for p in net.parameters())
         fg.zero_()
         ok = ok and float(fg.flat.abs().max()) == 0.0 and not fg.reduced
+        # deferred mode (a backward replayed from a CUDA graph): reduce_bucket() calls from inside the backward are ignored,
+        # finish() reduces everything, and the object is ready for the next step without zero_() having run on the host
+        fg.defer = True
+        for step in range(2):
+            fg.flat.zero_()                    # what the replayed graph does (no host-side bookkeeping)
+            for name, p in net.named_parameters():
+                fg.add_(name, torch.full_like(p, float(rank + 1 + step)))
+            fg.reduce_bucket(0)
+            ok = ok and not fg.works and not fg.reduced
+            fg.finish()
+            ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 1.5 + step)) for p in net.parameters()) and not fg.reduced
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
