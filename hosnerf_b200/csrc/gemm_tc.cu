@@ -129,7 +129,7 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
   float* s_headx = reinterpret_cast<float*>(sStage + (size_t)args.nbuf_out * out_buf_bytes);     // [128][4]
   float* sBias = s_headx + kTileM * 4;                      // [256] bias of the current column block (bias_smem)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + (args.bias_smem ? 256 : 0));
-  uint64_t* bar_full = bars;                                // leader: A + B of both CTAs landed (2 tx arrivals + 2 relays); peer: its own two
+  uint64_t* bar_full = bars;                                // leader: A + B of both CTAs landed (2 tx arrivals + 1 relay); peer: its own two
   uint64_t* bar_empty = bar_full + kG2MaxStages;            // multicast commit: stage consumed
   uint64_t* bar_tfull = bar_empty + kG2MaxStages;           // [2] multicast commit: accumulator buffer complete
   uint64_t* bar_tempty = bar_tfull + 2;                     // [2] leader only: drained by the 16 epilogue warps of the pair
@@ -145,7 +145,7 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
 
   if (args.bias_smem && threadIdx.x < 256) sBias[threadIdx.x] = (args.bias && (int)threadIdx.x < args.n) ? args.bias[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kG2MaxStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 4u : 2u); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < kG2MaxStages; ++s) { mbar_init(&bar_full[s], rank == 0 ? 3u : 2u); mbar_init(&bar_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&bar_tfull[s], 1); mbar_init(&bar_tempty[s], 2 * kG2EpiWarps); }
     for (int s = 0; s < 3; ++s) mbar_init(&bar_mask[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,12 +202,23 @@ gemm_tma_kernel(const __grid_constant__ G2Args args, const __grid_constant__ G2M
                 }
               }
             }
-            if (rank != 0) {          // relay to the leader once this CTA's bytes are in shared memory
-              if (args.dbg & 2) mbar_wait_guard<0>(&bar_full[st], use & 1);
-              else G2_WAIT(100, &bar_full[st], use & 1, 2, (int)ci, (int)st);
-              mbar_arrive_remote(mapa_u32(smem_u32(&bar_full[st]), 0));
-            }
           }
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer CTA: completion watcher =====================
+    // tells the leader "both of my operands of stage s have landed", stage by stage - the producers only issue copies and never
+    // wait for one to arrive (with the relay in the producer threads each moved one chunk per L2 / HBM round trip)
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[0]), 0);
+      uint32_t st = 0, par = 0;
+      for (int g = cluster; g < n_groups; g += n_clusters) {
+        const int nch = nblk * KB;
+        for (int i = 0; i < nch; ++i) {
+          mbar_wait_guard<40>(&bar_full[st], par);
+          mbar_arrive_remote(full_leader + 8u * st);
+          if (++st == (uint32_t)S) { st = 0; par ^= 1; }
         }
       }
     }
