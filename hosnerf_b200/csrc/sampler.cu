@@ -25,6 +25,7 @@ struct SamplerSmem {
   float t0[kMaxKnots / 3 + 1];
   float t1[kMaxKnots / 3 + 1];
   float red[32];
+  double tot[32];              // per-chunk totals / carries of the CDF scan
   double carry;
 };
 
@@ -190,17 +191,46 @@ __device__ void cdf_ray(SamplerSmem& sm, int M) {
   float tot = block_reduce_sum(part, sm.red);
   for (int j = threadIdx.x; j < M; j += blockDim.x) sm.wts[j] = sm.wts[j] / tot;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    int lane = threadIdx.x;
-    double carry = 0.0;
-    for (int base = 0; base < M - 1; base += 32) {
-      int j = base + lane;
-      double v = (j < M - 1) ? (double)sm.wts[j] : 0.0;
-      double inc = warp_incl_sum_d(v, lane) + carry;
-      if (j < M - 1) sm.cw[j + 1] = fminf((float)inc, 1.0f);
-      carry = __shfl_sync(0xffffffffu, inc, 31);
+  // Inclusive sum in double, 32 elements per warp scan.  Every warp scans its own chunks (all chunks of a ray are in flight at
+  // once instead of one warp walking them one after the other: the double-precision scan was the longest serial stretch of
+  // the kernel); the running carry is then added in chunk order - carry(c+1) = scan_c[31] + carry(c), inc = scan + carry -
+  // which is operation for operation what the single-warp loop computed.
+  {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nchunk = (M - 1 + 31) >> 5;                    // <= 32 (M <= kMaxKnots)
+    double* tot = sm.tot;                                    // [nchunk] chunk totals, then carries
+    double loc[4];                                           // this warp's chunks c = wid, wid + nw, ... (<= 4 with 8 warps)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = wid + i * nw;
+      loc[i] = 0.0;
+      if (c < nchunk) {
+        const int j = c * 32 + lane;
+        const double v = (j < M - 1) ? (double)sm.wts[j] : 0.0;
+        loc[i] = warp_incl_sum_d(v, lane);
+        if (lane == 31) tot[c] = loc[i];
+      }
     }
-    if (lane == 0) { sm.cw[0] = 0.f; sm.cw[M] = 1.f; }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                  // carries in chunk order (exclusive): tot[c] <- carry(c)
+      double carry = 0.0;
+      for (int c = 0; c < nchunk; ++c) {
+        const double t = tot[c];
+        tot[c] = carry;
+        carry = t + carry;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = wid + i * nw;
+      if (c < nchunk) {
+        const int j = c * 32 + lane;
+        const double inc = loc[i] + tot[c];
+        if (j < M - 1) sm.cw[j + 1] = fminf((float)inc, 1.0f);
+      }
+    }
+    if (threadIdx.x == 0) { sm.cw[0] = 0.f; sm.cw[M] = 1.f; }
   }
   __syncthreads();
 }

@@ -15,3 +15,5 @@ with torch.no_grad():
         for _ in range(10): net(b, 1.0, False, False, 0.1, 1e6)
         torch.cuda.synchronize()
 print(p.key_averages().table(sort_by="cuda_time_total", row_limit=12, max_name_column_width=60))
+print("resample launches (us):", [round(e.device_time, 1) for e in p.events() if "resample_level" in e.name][:8])
+print("composite launches (us):", [round(e.device_time, 1) for e in p.events() if "composite_mip360" in e.name][:8])
