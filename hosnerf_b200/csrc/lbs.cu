@@ -44,6 +44,9 @@ __device__ __forceinline__ void tri_setup(int G, float gx, float gy, float gz, T
   c.base = (z0 * G + y0) * G + x0;
   c.w[0] = wx0 * wy0 * wz0; c.w[1] = wx1 * wy0 * wz0; c.w[2] = wx0 * wy1 * wz0; c.w[3] = wx1 * wy1 * wz0;
   c.w[4] = wx0 * wy0 * wz1; c.w[5] = wx1 * wy0 * wz1; c.w[6] = wx0 * wy1 * wz1; c.w[7] = wx1 * wy1 * wz1;
+  // interior cell (the common case): both corners of every axis inside, i.e. 0 <= x0 <= G - 2 - one unsigned compare per axis
+  const unsigned g1 = (unsigned)(G - 1);
+  if ((unsigned)x0 < g1 && (unsigned)y0 < g1 && (unsigned)z0 < g1) { c.valid = 0xffu; return; }
   const unsigned bx0 = x0 >= 0 && x0 < G, bx1 = x1 >= 0 && x1 < G;
   const unsigned by0 = y0 >= 0 && y0 < G, by1 = y1 >= 0 && y1 < G;
   const unsigned bz0 = z0 >= 0 && z0 < G, bz1 = z1 >= 0 && z1 < G;
@@ -88,10 +91,9 @@ __global__ void __launch_bounds__(256)
 lbs_warp_kernel(const float* __restrict__ pts, const float* __restrict__ R, const float* __restrict__ T,
                 const float* __restrict__ vol, LbsParams prm, int64_t P, int bones, int G,
                 float* __restrict__ x_skel, float* __restrict__ mask) {
-  __shared__ float sR[kMaxBones * 9];
-  __shared__ float sT[kMaxBones * 3];
-  for (int i = threadIdx.x; i < bones * 9; i += blockDim.x) sR[i] = R[i];
-  for (int i = threadIdx.x; i < bones * 3; i += blockDim.x) sT[i] = T[i];
+  __shared__ float4 sRT[kMaxBones * 3];                  // per bone: (R row 0, Tx), (R row 1, Ty), (R row 2, Tz) - three 16-byte loads
+  for (int i = threadIdx.x; i < bones * 3; i += blockDim.x)
+    sRT[i] = make_float4(R[i * 3 + 0], R[i * 3 + 1], R[i * 3 + 2], T[i]);
   __syncthreads();
   const size_t vstride = (size_t)G * G * G;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
@@ -99,11 +101,11 @@ lbs_warp_kernel(const float* __restrict__ pts, const float* __restrict__ R, cons
     float ax = 0.f, ay = 0.f, az = 0.f, wsum = 0.f;
 #pragma unroll 2
     for (int b = 0; b < bones; ++b) {
-      const float* r = sR + b * 9;
+      const float4 r0 = sRT[b * 3 + 0], r1 = sRT[b * 3 + 1], r2 = sRT[b * 3 + 2];
       // matmul(R_i, pts.T): K=3 GEMM micro-kernel order (fma chain), then the separate "+ T_i"
-      float qx = fmaf(r[2], pz, fmaf(r[1], py, r[0] * px)) + sT[b * 3 + 0];
-      float qy = fmaf(r[5], pz, fmaf(r[4], py, r[3] * px)) + sT[b * 3 + 1];
-      float qz = fmaf(r[8], pz, fmaf(r[7], py, r[6] * px)) + sT[b * 3 + 2];
+      float qx = fmaf(r0.z, pz, fmaf(r0.y, py, r0.x * px)) + r0.w;
+      float qy = fmaf(r1.z, pz, fmaf(r1.y, py, r1.x * px)) + r1.w;
+      float qz = fmaf(r2.z, pz, fmaf(r2.y, py, r2.x * px)) + r2.w;
       float gx = (qx - prm.bbox_min[0]) * prm.bbox_scale[0] - 1.0f;
       float gy = (qy - prm.bbox_min[1]) * prm.bbox_scale[1] - 1.0f;
       float gz = (qz - prm.bbox_min[2]) * prm.bbox_scale[2] - 1.0f;
