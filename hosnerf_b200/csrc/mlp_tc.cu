@@ -624,9 +624,11 @@ __device__ __forceinline__ void fourier_row(const float (&p)[3], int nfreq, cons
   for (int j = 0; j < 32; ++j) pk[j] = cvt_f16x2(__float_as_uint(ok ? vals[2 * j] : 0.f), __float_as_uint(ok ? vals[2 * j + 1] : 0.f));
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
-mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
-                const __grid_constant__ IpeArgs ipe, const int stages_w) {
+// DUO is a template parameter (not a runtime flag): the one-tile-pair schedule of the 256-wide networks - the headline kernel -
+// must compile exactly as it did before the duo schedule existed (as a runtime flag the extra loop level and indexing cost
+// it 4 %: 1.140 -> 1.188 ms per C2 step).
+template <bool DUO>
+__device__ __forceinline__ void mlp_pair_body(const MlpProgram& prog, const MlpArgs& args, const IpeArgs& ipe, const int stages_w) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int w_stage_bytes = prog.n_max * 64;               // this CTA's half of an [n_max x 64] fp16 chunk
@@ -634,7 +636,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   // flight and walks the units (layer l, tile pair t) as l0t0 l0t1 l1t0 l1t1 ...: while one tile pair is in the layer-to-layer
   // hand-off (commit -> epilogue -> first operand chunk: 1.5 - 2.8 k cycles against 0.5 k cycles of tensor work for a 128-wide
   // layer) the other one's MMAs run.  Each tile pair has its own activation buffer, accumulator pair and hready barriers.
-  const int T = args.duo ? 2 : 1;
+  constexpr int T = DUO ? 2 : 1;
   const uint32_t h_tile_bytes = (uint32_t)prog.kbh * kXChunkBytes;
   unsigned char* sH = smem;                                // [T][kbh][16 KB] activations (A operand of the next layer)
   unsigned char* sOnes = sH + T * h_tile_bytes;            // [4 KB] constant A operand of the bias MMA: [128 x 16], columns 0, 1 = 1.0
@@ -684,7 +686,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
       mbar_init(&bar_xempty[s], 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(&bar_tfull[s], 1);
-    const uint32_t epi_arrivals = args.duo ? (uint32_t)kEpiWarps : 2u * kEpiWarps;       // duo: four epilogue warps per CTA and tile pair
+    const uint32_t epi_arrivals = DUO ? (uint32_t)kEpiWarps : 2u * kEpiWarps;       // duo: four epilogue warps per CTA and tile pair
     for (int s = 0; s < 2 * kPairMaxKbh; ++s) mbar_init(&bar_hready[s], epi_arrivals);
     mbar_init(&bar_tfree[0], 2 * kEpiWarps);
     for (int s = 0; s < 2; ++s) mbar_init(&bar_tlast[s], epi_arrivals);
@@ -700,12 +702,12 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0 || warp == 2 || (warp == 3 && !args.duo)) {
+  if (warp == 0 || warp == 2 || (warp == 3 && !DUO)) {
     // ===================== weight producers: chunk i -> producer i % P, ring stage i % S =====================
     // (duo: two producers - warp 3 of the leader is the second MMA issuer; with the relay in the watcher warp a producer only
     // issues copies and never waits for one to land)
     if (lane == 0) {
-      const uint32_t n_prod = args.duo ? 2u : (uint32_t)kPairProducers;
+      const uint32_t n_prod = DUO ? 2u : (uint32_t)kPairProducers;
       const uint32_t p = warp == 0 ? 0u : (uint32_t)(warp - 1);
       uint32_t wi = 0, xi = 0;
       for (int g0 = cluster; g0 < n_groups; g0 += T * n_clusters) {
@@ -805,7 +807,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
           const LayerDev L = prog.layers[l];
           const uint32_t idesc = umma_idesc_f16(L.n, 2 * kTileM);
           const int kb_h = L.kb_h, nkb = L.kb_h + L.kb_x;
-          if (args.duo && t != my_t) {               // the other issuer's unit: step the ring cursors over its stages
+          if (DUO && t != my_t) {               // the other issuer's unit: step the ring cursors over its stages
             uint32_t adv = (uint32_t)nkb + 1u + ws;
             while (adv >= S) { adv -= S; wpar ^= 1u; }
             ws = adv;
@@ -815,8 +817,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             continue;
           }
 
-          const uint32_t abuf = args.duo ? (uint32_t)(2 * t + (l & 1)) : (u & 1);       // accumulator buffer / tfull barrier
-          const uint32_t acc = tmem_base + (args.duo ? abuf * 128u : abuf * 256u);
+          const uint32_t abuf = DUO ? (uint32_t)(2 * t + (l & 1)) : (u & 1);       // accumulator buffer / tfull barrier
+          const uint32_t acc = tmem_base + (DUO ? abuf * 128u : abuf * 256u);
           const uint32_t hready_t = hready_a + 8u * (uint32_t)(t * kPairMaxKbh);
           const uint32_t h16_t = h16 + (uint32_t)t * (h_tile_bytes >> 4);
           const uint32_t hpar = (hpar_bits >> t) & 1u;
@@ -834,7 +836,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
             // operand chunk of this unit as well (signalled by epilogue(u - 1), which runs after epilogue(u - 2)).
             // A hidden layer with an fp32 head re-reads its accumulator after it has signalled all operand chunks
             // (deferred head pass): its buffer is free only once bar_tfree completes.
-            if (args.duo) {
+            if (DUO) {
               // Buffer (t, l & 1) was last read by the epilogue of unit (t, l - 2), which ran before the epilogue of (t, l - 1)
               // whose chunks this warp waited for when it issued that unit - except across iterations: nothing waits for the
               // previous iteration's LAST layer's epilogue, so the first unit that reuses ITS buffer (layer 0 or 1, by parity)
@@ -935,7 +937,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     for (int gq = 0; gq < 4; ++gq) h_off0[gq] = h_row + ((uint32_t)((4 * ch + gq) ^ (r & 7)) << 4);
     uint32_t u = 0;
     uint32_t tf_use = 0;                                      // bit b: parity of the next phase of bar_tfull[b] to wait for
-    if (args.duo) {
+    if (DUO) {
       // ---------- duo schedule: warps 4-7 drain the units of tile pair 0, warps 8-11 those of tile pair 1, concurrently (an
       // epilogue of a 128-wide unit is a ~1.2 k-cycle latency chain - TMEM load, convert, store, fence, arrive - not a
       // throughput problem).  Each warp takes all 64 columns of a chunk for its 32 rows; the head's dot products stay in one thread.
@@ -1059,8 +1061,8 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         const bool has_head = L.head >= 0;
         const bool relu = L.relu != 0;
         const int nchunks = L.n >> 6;
-        const uint32_t abuf = args.duo ? (uint32_t)(2 * t + (l & 1)) : (u & 1);
-        const uint32_t acc = tmem_base + (args.duo ? abuf * 128u : abuf * 256u) + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
+        const uint32_t abuf = DUO ? (uint32_t)(2 * t + (l & 1)) : (u & 1);
+        const uint32_t acc = tmem_base + (DUO ? abuf * 128u : abuf * 256u) + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32);
         const bool tl = args.timeline && blockIdx.x == 0 && threadIdx.x == kEpiWarp0 * 32 && u < 64;
         // Per-ray bias (view-direction term): when a tile spans a whole number of rays (or one ray spans whole tiles) its
         // <= 4 bias vectors are fetched into shared memory BEFORE the wait for the accumulator, so the L2 latency is
@@ -1241,7 +1243,7 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
         }
         {
           if (last) tc_fence_before();
-          if (last && args.duo) {                 // accumulator read: the next iteration's layer 0 of this tile pair may overwrite it
+          if (last && DUO) {                 // accumulator read: the next iteration's layer 0 of this tile pair may overwrite it
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(tlast0 + 8u * (uint32_t)t);
           }
@@ -1345,6 +1347,18 @@ mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols));
   }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_pair_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
+                const __grid_constant__ IpeArgs ipe, const int stages_w) {
+  mlp_pair_body<false>(prog, args, ipe, stages_w);
+}
+// two tile pairs in flight per cluster (narrow networks), see mlp_pair_body
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_duo_kernel(const __grid_constant__ MlpProgram prog, const __grid_constant__ MlpArgs args,
+               const __grid_constant__ IpeArgs ipe, const int stages_w) {
+  mlp_pair_body<true>(prog, args, ipe, stages_w);
 }
 
 // ----------------------------------------------------------------------------- packing
@@ -1864,7 +1878,8 @@ hos_mlp_t* hos_mlp_create(int in_dim, int n_layers, const hos_mlp_layer* layers,
   m->duo_ok = duo_ok && pair_ok && pair_stages >= 3;
   if (pair_ok && smem_pair <= 227 * 1024) {
     m->smem_pair = smem_pair;
-    if (cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(mlp_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
       cudaGetLastError();
       m->smem_pair = 0;
     } else {
@@ -1982,8 +1997,11 @@ static int mlp_launch(hos_mlp_t* m, const void* x_tiled, const IpeArgs* ipe, int
   if (pair) {
     const int n_groups = (a.ntiles + 1) / 2;
     const int clusters = n_groups < m->max_clusters ? n_groups : m->max_clusters;
-    mlp_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_pair, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe,
-                                                                                      m->pair_stages);
+    if (a.duo)
+      mlp_duo_kernel<<<2 * clusters, kMlpThreads, m->smem_pair, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe, m->pair_stages);
+    else
+      mlp_pair_kernel<<<2 * clusters, kMlpThreads, m->smem_pair, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe,
+                                                                                        m->pair_stages);
   } else {
     int grid = a.ntiles < kNumSMs ? a.ntiles : kNumSMs;
     mlp_tc_kernel<<<grid, kMlpThreads, m->smem_bytes, (cudaStream_t)stream>>>(m->prog, a, ipe ? *ipe : kNoIpe);
