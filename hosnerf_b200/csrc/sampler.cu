@@ -370,7 +370,14 @@ resample_level_kernel(const float* __restrict__ sdist, const float* __restrict__
     }
   }
   __syncthreads();
-  cdf_ray(sm, M);
+  if (M == 1 && sm.knots[off + 1] > sm.knots[off]) {
+    // first level: one interval.  softmax of a single finite logit is exp(0) / exp(0) = 1 whatever the logit, so the CDF is
+    // {0, 1}: what cdf_ray would store, without its block-wide max / sum reductions
+    if (threadIdx.x == 0) { sm.cw[0] = 0.f; sm.cw[1] = 1.f; }
+    __syncthreads();
+  } else {
+    cdf_ray(sm, M);
+  }
   float* so = sdist_out + (size_t)ray * (S + 1);
   invert_ray(sm, off, M, u_base, jitter ? jitter + (size_t)ray * jitter_cols : nullptr, jitter_cols,
              max_jitter, S, lo, hi, so, nullptr, nullptr, tdist_out + (size_t)ray * (S + 1), s_near, s_far);

@@ -312,7 +312,8 @@ def test_lbs_identity_property():
 def test_linear_and_head_f32():
     gen = torch.Generator().manual_seed(0)
     for (m, k1, k2, n) in [(1000, 504, 0, 256), (333, 256, 504, 256), (129, 36, 0, 128), (500, 128, 36, 128),
-                           (257, 256, 63, 256), (64, 1024, 504, 1024)]:
+                           (257, 256, 63, 256), (64, 1024, 504, 1024),
+                           (4096, 27, 0, 128), (1001, 20, 7, 64), (77, 27, 0, 256), (300, 27, 0, 96)]:      # skinny products: small kernel (96: tiled)
         x1 = torch.randn(m, k1, generator=gen)
         x2 = torch.randn(m, k2, generator=gen) if k2 else None
         w = torch.randn(n, k1 + k2, generator=gen) / (k1 + k2) ** 0.5
