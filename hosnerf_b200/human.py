@@ -716,7 +716,11 @@ class Network(nn.Module):
             dists = torch.cat([z[..., 1:] - z[..., :-1], torch.full_like(z[..., :1], 1e10)], dim=-1) * torch.norm(rays_d[..., None, :], dim=-1)
             rgb = torch.sigmoid(raw[..., :3])
             alpha = (1.0 - torch.exp(-F.relu(raw[..., 3]) * dists)) * mask2
-            T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], dim=-1), dim=-1)[:, :-1]
+            if static:       # exp(cumsum(log)): torch's cumprod backward reads a flag back to the host (not capturable); factors >= 1e-10
+                lg = torch.log(1. - alpha + 1e-10)
+                T = torch.exp(torch.cumsum(lg, dim=-1) - lg)
+            else:
+                T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1. - alpha + 1e-10], dim=-1), dim=-1)[:, :-1]
             w = alpha * T
             acc = torch.sum(w, -1)
             ret.update(rgb=torch.sum(w[..., None] * rgb, -2) + (1. - acc[..., None]) * bgcolor.to(dev)[None, :] / 255.,

@@ -1241,3 +1241,32 @@ def test_duo_schedule_of_narrow_mlp_matches_one_tile_pair_in_flight():
             ops.set_mlp_variant(0)
     assert torch.isfinite(outs[0]).all()
     assert max_abs(outs[0], outs[1]) < 2e-4, max_abs(outs[0], outs[1])
+
+
+def test_static_shape_stage2_training_matches_indexed_form():
+    """Stage-2 ``Network.forward`` under autograd with ``static_shapes`` (device-side bone chain, dense cycle path, exp-cumsum-log
+    transmittance): same rgb / alpha and parameter gradients as the default form."""
+    hb = {k: cu(v) for k, v in synth.make_human_batch(64).items()}
+    hb["is_train"] = True
+    for k in ("time", "iter_val"):
+        if isinstance(hb.get(k), torch.Tensor):
+            hb[k] = float(hb[k].reshape(-1)[0])
+    hb["rand"] = torch.rand(64, 128, generator=torch.Generator().manual_seed(3)).to(DEV)
+    net = _human(stage2=True)
+    res = []
+    for static in (False, True):
+        net.static_shapes = static
+        for p in net.parameters():
+            p.grad = None
+        out = net(**hb)
+        (out["rgb"].mean() + out["alpha"].mean()).backward()
+        res.append((out["rgb"].detach().clone(), out["alpha"].detach().clone(),
+                    {k: (None if p.grad is None else p.grad.clone()) for k, p in net.named_parameters()}))
+    net.static_shapes = False
+    (rgb_a, al_a, g_a), (rgb_b, al_b, g_b) = res
+    assert max_abs(rgb_a, rgb_b) < 5e-5 and max_abs(al_a, al_b) < 5e-5
+    scale = max(float(g.norm()) for g in g_a.values() if g is not None)
+    for k, g in g_a.items():
+        if g is None or float(g.norm()) < 1e-6 * scale:
+            continue
+        assert g_b[k] is not None and float((g_b[k] - g).norm()) < 2e-2 * float(g.norm()) + 1e-5 * scale, k
